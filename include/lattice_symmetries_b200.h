@@ -1,0 +1,312 @@
+/*
+ * lattice_symmetries_b200.h -- C ABI of the B200-native hot-path library.
+ *
+ * liblattice_symmetries_b200.so is a drop-in for the two native pieces the
+ * reference's Haskell host and Python cffi wrapper link against on this path:
+ *
+ *   (1) libkernels.a            kernels/{kernels.c,indexing.c,reference.c}
+ *   (2) liblattice_symmetries_chapel.so   chapel/src/ (all .chpl)
+ *
+ * Every entry point below names the reference declaration it replaces
+ * (file:line in twesterhout/lattice-symmetries @ 36215fe).  Struct layouts are
+ * field-for-field those of kernels/lattice_symmetries_types.h (the contract
+ * the Haskell Storable instances in haskell/src/LatticeSymmetries/FFI.hs:69-143
+ * marshal into); static_asserts in csrc/abi_layout.cu pin the offsets.
+ *
+ * All pointers in the ls_hs_ / ls_chpl_ / ls_internal_ entry points are HOST
+ * pointers, exactly as in the reference.  The ls_b200_ entry points at the
+ * bottom are extensions for callers that keep vectors resident in HBM.
+ *
+ * There is NO CPU fallback: every compute entry point runs CUDA kernels for
+ * sm_100a and reports failure through ls_hs_error() when no device is usable.
+ */
+#pragma once
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- types: kernels/lattice_symmetries_types.h ------------------------- */
+
+/* :27-32 (Chapel's chpl-external-array.h when present) */
+typedef struct chpl_external_array {
+  void *elts;
+  uint64_t num_elts;
+  void *freer; /* void (*)(void*) called with elts, or NULL when borrowed */
+} chpl_external_array;
+
+/* :43-56 -- interleaved (re, im); layout-compatible with _Complex double and
+ * std::complex<double>. */
+typedef struct ls_hs_scalar {
+  double _real;
+  double _imag;
+} ls_hs_scalar;
+
+/* :81-85 */
+typedef enum ls_hs_particle_type {
+  LS_HS_SPIN,
+  LS_HS_SPINFUL_FERMION,
+  LS_HS_SPINLESS_FERMION
+} ls_hs_particle_type;
+
+/* :87-98 */
+typedef void (*ls_hs_internal_state_index_kernel_type)(
+    ptrdiff_t batch_size, uint64_t const *alphas, ptrdiff_t alphas_stride,
+    ptrdiff_t *indices, ptrdiff_t indices_stride, void const *private_data);
+typedef void (*ls_hs_internal_is_representative_kernel_type)(
+    ptrdiff_t batch_size, uint64_t const *alphas, ptrdiff_t alphas_stride,
+    uint8_t *are_representatives, double *norms, void const *private_data);
+typedef void (*ls_hs_internal_state_info_kernel_type)(
+    ptrdiff_t batch_size, uint64_t const *alphas, ptrdiff_t alphas_stride,
+    uint64_t *betas, ptrdiff_t betas_stride, ls_hs_scalar *characters,
+    double *norms, void const *private_data);
+
+/* :100-107 */
+typedef struct ls_hs_basis_kernels {
+  ls_hs_internal_state_info_kernel_type state_info_kernel;
+  void *state_info_data;
+  ls_hs_internal_is_representative_kernel_type is_representative_kernel;
+  void *is_representative_data;
+  ls_hs_internal_state_index_kernel_type state_index_kernel;
+  void *state_index_data;
+} ls_hs_basis_kernels;
+
+/* :109-119 -- refcount is `_Atomic int` in C11; same size/alignment as int. */
+typedef struct ls_hs_permutation_group {
+  int refcount;
+  int number_bits;
+  int number_shifts;
+  int number_masks;
+  uint64_t *masks;    /* [number_shifts][number_masks] row-major */
+  uint64_t *shifts;   /* [number_shifts] */
+  double *eigvals_re; /* [number_masks] */
+  double *eigvals_im; /* [number_masks] */
+  void *haskell_payload;
+} ls_hs_permutation_group;
+
+/* :121-133 */
+typedef struct ls_hs_basis {
+  int refcount;
+  int number_sites;
+  int number_particles; /* -1 when unset */
+  int number_up;        /* -1 when unset */
+  ls_hs_particle_type particle_type;
+  int spin_inversion; /* 0 when none */
+  bool state_index_is_identity;
+  bool requires_projection;
+  ls_hs_basis_kernels *kernels;
+  chpl_external_array representatives;
+  void *haskell_payload;
+} ls_hs_basis;
+
+/* :140-151 -- single 64-bit word per mask on this path */
+typedef struct ls_hs_nonbranching_terms {
+  int number_terms;
+  int number_bits;
+  ls_hs_scalar const *v;
+  uint64_t const *m;
+  uint64_t const *l;
+  uint64_t const *r;
+  uint64_t const *x;
+  uint64_t const *s;
+} ls_hs_nonbranching_terms;
+
+/* :153-161 */
+typedef struct ls_hs_operator {
+  int refcount;
+  ls_hs_basis const *basis;
+  ls_hs_nonbranching_terms const *off_diag_terms; /* NULL when empty */
+  ls_hs_nonbranching_terms const *diag_terms;     /* NULL when empty */
+  void *haskell_payload;
+} ls_hs_operator;
+
+/* :170-180 -- the vtable the Chapel library registers at init
+ * (chapel/src/LatticeSymmetries.chpl:18-33). */
+typedef struct ls_chpl_kernels {
+  void (*enumerate_states)(ls_hs_basis const *, uint64_t, uint64_t,
+                           chpl_external_array *);
+  void (*operator_apply_off_diag)(ls_hs_operator *, int64_t, uint64_t *,
+                                  chpl_external_array *, chpl_external_array *,
+                                  chpl_external_array *, int64_t);
+  void (*operator_apply_diag)(ls_hs_operator *, int64_t, uint64_t *,
+                              chpl_external_array *, int64_t);
+  void (*matrix_vector_product)(ls_hs_operator *, int, double const *,
+                                double *);
+} ls_chpl_kernels;
+
+/* ---- (1) replaces libkernels.a ------------------------------------------ */
+
+/* kernels/reference.c:11-36 */
+void ls_hs_set_exception_handler(void (*handler)(char const *message));
+void ls_hs_error(char const *message);
+void ls_hs_fatal_error(char const *func, int line, char const *message);
+
+/* kernels/reference.c:40-64 */
+void ls_hs_internal_destroy_external_array(chpl_external_array *arr);
+int ls_hs_internal_read_refcount(int const *refcount);
+void ls_hs_internal_write_refcount(int *refcount, int value);
+int ls_hs_internal_inc_refcount(int *refcount);
+int ls_hs_internal_dec_refcount(int *refcount);
+
+/* kernels/kernels.c:112-193 -- copies the group tables to the device (the
+ * reference borrows the Haskell-owned arrays); tolerates number_masks == 0. */
+void *ls_internal_create_halide_kernel_data(ls_hs_permutation_group const *g,
+                                            int spin_inversion);
+void ls_internal_destroy_halide_kernel_data(void *p);
+
+/* kernels/kernels.c:195-244, :246-319 -- names kept because the Haskell host
+ * stores their ADDRESSES (haskell/src/LatticeSymmetries/Basis.hs:915-925). */
+void ls_hs_is_representative_halide_kernel(ptrdiff_t batch_size,
+                                           uint64_t const *alphas,
+                                           ptrdiff_t alphas_stride,
+                                           uint8_t *are_representatives,
+                                           double *norms,
+                                           void const *private_data);
+void ls_hs_state_info_halide_kernel(ptrdiff_t batch_size,
+                                    uint64_t const *alphas,
+                                    ptrdiff_t alphas_stride, uint64_t *betas,
+                                    ptrdiff_t betas_stride,
+                                    ls_hs_scalar *characters, double *norms,
+                                    void const *private_data);
+
+/* kernels/indexing.c:94-127, :273-325 */
+typedef struct ls_hs_state_index_binary_search_data
+    ls_hs_state_index_binary_search_data;
+ls_hs_state_index_binary_search_data *
+ls_hs_create_state_index_binary_search_kernel_data(
+    chpl_external_array const *representatives, int number_bits,
+    int prefix_bits);
+void ls_hs_destroy_state_index_binary_search_kernel_data(
+    ls_hs_state_index_binary_search_data *cache);
+void ls_hs_state_index_binary_search_kernel(ptrdiff_t batch_size,
+                                            uint64_t const *spins,
+                                            ptrdiff_t spins_stride,
+                                            ptrdiff_t *indices,
+                                            ptrdiff_t indices_stride,
+                                            void const *private_kernel_data);
+
+/* kernels/reference.c:137-211 */
+void ls_hs_state_index(ls_hs_basis const *basis, ptrdiff_t batch_size,
+                       uint64_t const *spins, ptrdiff_t spins_stride,
+                       ptrdiff_t *indices, ptrdiff_t indices_stride);
+void ls_hs_is_representative(ls_hs_basis const *basis, ptrdiff_t batch_size,
+                             uint64_t const *alphas, ptrdiff_t alphas_stride,
+                             uint8_t *are_representatives, double *norms);
+void ls_hs_state_info(ls_hs_basis const *basis, ptrdiff_t batch_size,
+                      uint64_t const *alphas, ptrdiff_t alphas_stride,
+                      uint64_t *betas, ptrdiff_t betas_stride,
+                      ls_hs_scalar *characters, double *norms);
+void ls_hs_build_representatives(ls_hs_basis *basis, uint64_t lower,
+                                 uint64_t upper);
+void ls_hs_unchecked_set_representatives(ls_hs_basis *basis,
+                                         chpl_external_array const *states,
+                                         int cache_bits);
+
+/* kernels/reference.c:67-134 */
+void ls_internal_operator_apply_diag_x1(ls_hs_operator const *op,
+                                        ptrdiff_t batch_size,
+                                        uint64_t const *alphas, double *ys,
+                                        double const *xs);
+void ls_internal_operator_apply_off_diag_x1(ls_hs_operator const *op,
+                                            ptrdiff_t batch_size,
+                                            uint64_t const *alphas,
+                                            uint64_t *betas,
+                                            ls_hs_scalar *coeffs,
+                                            ptrdiff_t *offsets,
+                                            double const *xs);
+
+/* kernels/reference.c:214-225 */
+ls_chpl_kernels const *ls_hs_internal_get_chpl_kernels(void);
+void ls_hs_internal_set_chpl_kernels(ls_chpl_kernels const *kernels);
+
+/* ---- (2) replaces liblattice_symmetries_chapel.so ------------------------ */
+
+/* chapel/src/library.c:19-34; LatticeSymmetries.chpl:29-33 */
+void ls_chpl_init(void);
+void ls_chpl_finalize(void);
+void ls_chpl_init_kernels(void);
+
+/* chapel/src/StatesEnumeration.chpl:692-709 (lower/upper are ignored there
+ * and recomputed from the basis, :683-688; same here). */
+void ls_chpl_enumerate_representatives(ls_hs_basis const *basis,
+                                       uint64_t lower, uint64_t upper,
+                                       chpl_external_array *dest);
+/* chapel/src/BatchedOperator.chpl:298-357 */
+void ls_chpl_operator_apply_diag(ls_hs_operator *op, int64_t count,
+                                 uint64_t *alphas, chpl_external_array *coeffs,
+                                 int64_t num_tasks);
+void ls_chpl_operator_apply_off_diag(ls_hs_operator *op, int64_t count,
+                                     uint64_t *alphas,
+                                     chpl_external_array *betas,
+                                     chpl_external_array *coeffs,
+                                     chpl_external_array *offsets,
+                                     int64_t num_tasks);
+/* chapel/src/DistributedMatrixVector.chpl:1090-1105 */
+void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors,
+                                   double const *x, double *y);
+
+/* ---- extensions: device-resident path ----------------------------------- */
+
+/* Number of CUDA kernels this library has launched in this process. */
+uint64_t ls_b200_kernel_launch_count(void);
+/* Device-time (ms, CUDA events on the library stream) of the most recent
+ * matvec / basis-build kernel; name selects "matvec" or "build". */
+double ls_b200_last_kernel_ms(char const *name);
+/* The CUDA stream (cudaStream_t) all library work is ordered on. */
+void *ls_b200_stream(void);
+int ls_b200_device_count(void);
+
+/* Device views of a built basis: sorted representatives, their norms
+ * (state_info convention, sqrt(n/|G|)); pointers stay owned by the library. */
+int ls_b200_basis_device_view(ls_hs_basis const *basis,
+                              uint64_t const **representatives,
+                              double const **norms, uint64_t *count);
+
+/* y[row_begin:row_end] = (H x)[row_begin:row_end] with x (full length dim)
+ * and y (length row_end-row_begin) in DEVICE memory; asynchronous on
+ * ls_b200_stream().  Returns 0 on success.  The rows are the contiguous
+ * representative range owned by this rank (multi-GPU: x is the all-gathered
+ * vector). */
+int ls_b200_matvec_device(ls_hs_operator const *op, int64_t row_begin,
+                          int64_t row_end, double const *x_dev, double *y_dev);
+/* Complex128 variant (interleaved re, im).  Extension: the reference's matvec
+ * is real-only (DistributedMatrixVector.chpl:1090-1091). */
+int ls_b200_matvec_device_c128(ls_hs_operator const *op, int64_t row_begin,
+                               int64_t row_end, ls_hs_scalar const *x_dev,
+                               ls_hs_scalar *y_dev);
+/* Waits for the device matvecs issued so far; returns 0 on success, 1 (after
+ * calling ls_hs_error) when an operator left the basis with a non-zero
+ * coefficient -- the reference's "invalid index" halt,
+ * chapel/src/DistributedMatrixVector.chpl:127-135. */
+int ls_b200_matvec_sync(void);
+/* Number of off-diagonal matrix elements (emitted (row, term) pairs) in the
+ * row range: the unit of the matvec throughput metric. */
+int64_t ls_b200_count_matrix_elements(ls_hs_operator const *op,
+                                      int64_t row_begin, int64_t row_end);
+
+/* Sharded basis construction: scan the candidates whose combinadic / linear
+ * index lies in [index_begin, index_end) of the basis' enumeration range and
+ * return this shard's representatives (ascending) and norms in device memory
+ * (caller frees with ls_b200_device_free).  total_candidates (optional out)
+ * is the size of the whole enumeration range. */
+int ls_b200_build_shard(ls_hs_basis const *basis, uint64_t index_begin,
+                        uint64_t index_end, uint64_t **representatives_dev,
+                        double **norms_dev, uint64_t *count);
+uint64_t ls_b200_number_candidates(ls_hs_basis const *basis);
+/* Install an (all-gathered) device-resident representative list + norms as
+ * the basis' representatives; the library takes ownership of both buffers and
+ * mirrors the states to pinned host memory for basis->representatives. */
+int ls_b200_set_representatives_device(ls_hs_basis *basis,
+                                       uint64_t *representatives_dev,
+                                       double *norms_dev, uint64_t count,
+                                       int cache_bits);
+void *ls_b200_device_malloc(size_t bytes);
+void ls_b200_device_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,182 @@
+// index.cu -- state -> index ranking over the sorted representatives.
+// Replaces kernels/indexing.c: the prefix-bucket table (:45-117) is built on
+// the device by one lower_bound per prefix, and the search kernel (:273-325)
+// runs one needle per thread.  Results (index or -1) are identical.
+#include "state.hpp"
+
+namespace lsb {
+
+IndexView IndexData::view() const {
+  IndexView v{};
+  v.reps = d_reps;
+  v.number_states = number_states;
+  v.offsets32 = d_offsets32;
+  v.offsets64 = d_offsets64;
+  v.shift = shift;
+  v.identity = identity ? 1 : 0;
+  v.number_buckets = uint64_t(1) << prefix_bits;
+  return v;
+}
+
+IndexData::~IndexData() {
+  if (owns_d_reps) cudaFree(d_reps);
+  cudaFree(d_offsets32);
+  cudaFree(d_offsets64);
+  cudaFree(d_norms);
+  magic = 0;
+}
+
+// offsets[p] = first index whose (rep >> shift) >= p  (kernels/indexing.c:63-69)
+template <class T>
+__global__ void __launch_bounds__(256)
+bucket_offsets_kernel(uint64_t const *__restrict__ reps, int64_t n, int shift, int64_t number_offsets,
+                      T *__restrict__ offsets) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < number_offsets;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = 0, hi = n;
+    if (p == number_offsets - 1) {
+      lo = n;
+    } else {
+      uint64_t const key = (uint64_t)p;
+      while (lo < hi) {
+        int64_t const mid = (lo + hi) >> 1;
+        if ((__ldg(reps + mid) >> shift) < key) lo = mid + 1; else hi = mid;
+      }
+    }
+    offsets[p] = (T)lo;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+state_index_kernel(IndexView ix, int64_t n, uint64_t const *__restrict__ needles,
+                   int64_t *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = state_index(ix, needles[i]);
+}
+
+// Adaptive prefix width: about two representatives per bucket, table capped so
+// that it stays L2-friendly.  The reference's caller-chosen width (22 or 26,
+// kernels/reference.c:188, chapel/src/CommonParameters.chpl:7) only affects
+// speed, never results, so we are free to choose.
+static int choose_prefix_bits(int64_t n, int number_bits, int requested) {
+  int want = 1;
+  while (want < 40 && (int64_t(1) << want) < n / 2) ++want;
+  int const cap = 27;
+  int p = std::min(want, cap);
+  p = std::max(p, std::min(requested, 16));
+  p = std::min(p, number_bits);
+  return std::max(p, 0);
+}
+
+void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
+  Runtime &rt = runtime();
+  ix.prefix_bits = choose_prefix_bits(ix.number_states, ix.number_bits, requested_prefix_bits);
+  ix.shift = ix.number_bits - ix.prefix_bits;
+  int64_t const number_offsets = (int64_t(1) << ix.prefix_bits) + 1;
+  unsigned const blocks = (unsigned)std::min<int64_t>((number_offsets + 255) / 256, (int64_t)rt.sm_count * 16);
+  if (ix.number_states < (int64_t(1) << 32)) {
+    CUDA_CHECK(cudaMalloc(&ix.d_offsets32, sizeof(uint32_t) * (size_t)number_offsets));
+    bucket_offsets_kernel<uint32_t><<<blocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, ix.shift,
+                                                                 number_offsets, ix.d_offsets32);
+  } else {
+    CUDA_CHECK(cudaMalloc(&ix.d_offsets64, sizeof(int64_t) * (size_t)number_offsets));
+    bucket_offsets_kernel<int64_t><<<blocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, ix.shift,
+                                                                number_offsets, ix.d_offsets64);
+  }
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+IndexData *index_of(ls_hs_basis const *basis) {
+  if (basis == nullptr || basis->kernels == nullptr) return nullptr;
+  auto *ix = static_cast<IndexData *>(basis->kernels->state_index_data);
+  if (ix == nullptr || ix->magic != kIndexMagic) return nullptr;
+  return ix;
+}
+
+// Creates the index object from host representatives (or adopts the device
+// copy a just-finished build left in the registry).
+IndexData *create_index(uint64_t const *host_reps, int64_t count, int number_bits, int prefix_bits) {
+  auto *ix = new IndexData();
+  ix->number_states = count;
+  ix->host_reps = host_reps;
+  ix->number_bits = number_bits;
+  auto &reg = built_registry();
+  auto it = host_reps ? reg.find(host_reps) : reg.end();
+  if (it != reg.end() && (int64_t)it->second.count == count) {
+    ix->d_reps = it->second.d_reps;
+    ix->d_norms = it->second.d_norms;
+    reg.erase(it);
+  } else if (count > 0) {
+    CUDA_CHECK(cudaMalloc(&ix->d_reps, sizeof(uint64_t) * (size_t)count));
+    CUDA_CHECK(cudaMemcpyAsync(ix->d_reps, host_reps, sizeof(uint64_t) * (size_t)count,
+                               cudaMemcpyHostToDevice, runtime().stream));
+  }
+  if (count > 0 && number_bits > 0) build_bucket_table(*ix, prefix_bits);
+  CUDA_CHECK(cudaStreamSynchronize(runtime().stream));
+  return ix;
+}
+
+struct IndexScratch {
+  DeviceBuffer<uint64_t> needles;
+  DeviceBuffer<int64_t> out;
+};
+static IndexScratch &index_scratch() {
+  static IndexScratch s;
+  return s;
+}
+
+}  // namespace lsb
+
+using namespace lsb;
+
+extern "C" {
+
+ls_hs_state_index_binary_search_data *ls_hs_create_state_index_binary_search_kernel_data(
+    chpl_external_array const *representatives, int const number_bits, int const prefix_bits) {
+  IndexData *ix = nullptr;
+  guarded(__func__, [&] {
+    ix = create_index(static_cast<uint64_t const *>(representatives->elts),
+                      (int64_t)representatives->num_elts, number_bits, prefix_bits);
+  });
+  return reinterpret_cast<ls_hs_state_index_binary_search_data *>(ix);
+}
+
+void ls_hs_destroy_state_index_binary_search_kernel_data(ls_hs_state_index_binary_search_data *cache) {
+  if (cache == nullptr) return;
+  auto *ix = reinterpret_cast<IndexData *>(cache);
+  LSB_CHECK(ix->magic == kIndexMagic, "not an index object of this library");
+  std::lock_guard<std::mutex> lock(runtime().mutex);
+  delete ix;
+}
+
+void ls_hs_state_index_binary_search_kernel(ptrdiff_t const batch_size, uint64_t const *spins,
+                                            ptrdiff_t const spins_stride, ptrdiff_t *indices,
+                                            ptrdiff_t const indices_stride,
+                                            void const *private_kernel_data) {
+  auto const *ix = static_cast<IndexData const *>(private_kernel_data);
+  LSB_CHECK(ix != nullptr && ix->magic == kIndexMagic, "invalid state_index kernel data");
+  LSB_CHECK(indices_stride == 1, "expected indices_stride==1");  // indexing.c:280
+  LSB_CHECK(spins_stride == 1, "expected spins_stride==1");      // indexing.c:281
+  static_assert(sizeof(ptrdiff_t) == sizeof(int64_t), "ptrdiff_t must be 64-bit");
+  guarded(__func__, [&] {
+    IndexScratch &sc = index_scratch();
+    Runtime &rt = runtime();
+    constexpr int64_t chunk = int64_t(1) << 22;
+    for (int64_t begin = 0; begin < batch_size; begin += chunk) {
+      int64_t const n = std::min<int64_t>(chunk, batch_size - begin);
+      uint64_t *d_in = sc.needles.reserve((size_t)n);
+      int64_t *d_out = sc.out.reserve((size_t)n);
+      CUDA_CHECK(cudaMemcpyAsync(d_in, spins + begin, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, rt.stream));
+      unsigned const blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 16);
+      state_index_kernel<<<blocks, 256, 0, rt.stream>>>(ix->view(), n, d_in, d_out);
+      count_launch();
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaMemcpyAsync(indices + begin, d_out, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, rt.stream));
+      CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    }
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// plane_table.cuh -- the per-element "plane renaming" table of the bit-sliced
+// kernels, held in constant memory.
+//
+// For group element j and output bit i the image of a state takes its bit i
+// from source bit perm_j[i] (Benes.hs:338-345 permuteBits').  With 32 states
+// transposed into bit planes stored column-wise in shared memory, plane i of
+// the image is simply plane perm_j[i] of the input, i.e. a byte offset
+// perm_j[i] * (threads per block) * 4 from the thread's own column.  The table
+// index is warp-uniform, so the offsets arrive through the uniform datapath
+// (LDCU) and cost no ALU/LSU issue slots.
+//
+// Constant memory is per translation unit: every .cu that includes this header
+// owns a private copy and uploads it on demand.
+#pragma once
+
+#include <vector>
+
+#include "state.hpp"
+
+namespace lsb {
+
+constexpr int kMaxPermTable = 24576;  // uint16 entries (48 KB of constant memory)
+static __constant__ uint16_t c_plane_offset[kMaxPermTable];
+static uint64_t g_plane_table_owner = 0;  // GroupData::id, NP and block size currently resident
+
+// Planes are padded to a multiple of four (np >= number_bits); padding planes
+// map onto themselves.  Returns false when the table does not fit.
+static inline bool upload_plane_offsets(GroupData const &g, int np, int threads_per_block) {
+  size_t const entries = (size_t)g.number_masks * (size_t)np;
+  if (entries > (size_t)kMaxPermTable) return false;
+  if ((size_t)(np - 1) * (size_t)threads_per_block * 4 > 0xffffu) return false;
+  uint64_t const tag = (g.id << 20) | ((uint64_t)np << 12) | (uint64_t)threads_per_block;
+  if (g_plane_table_owner == tag) return true;
+  std::vector<uint16_t> table(entries);
+  for (int j = 0; j < g.number_masks; ++j)
+    for (int i = 0; i < np; ++i) {
+      int const src = i < g.number_bits ? g.perm[(size_t)j * g.number_bits + i] : i;
+      table[(size_t)j * np + i] = (uint16_t)(src * threads_per_block * 4);
+    }
+  CUDA_CHECK(cudaMemcpyToSymbolAsync(c_plane_offset, table.data(), entries * sizeof(uint16_t), 0,
+                                     cudaMemcpyHostToDevice, runtime().stream));
+  CUDA_CHECK(cudaStreamSynchronize(runtime().stream));  // table is a stack temporary
+  g_plane_table_owner = tag;
+  return true;
+}
+
+// True when element 0 is the identity with character exactly 1 (always the
+// case for groups built by Group.hs:174-183, whose ascending order puts the
+// identity permutation first); lets kernels skip it.
+static inline bool identity_is_first(GroupData const &g) {
+  if (g.number_masks == 0 || g.re[0] != 1.0 || g.im[0] != 0.0) return false;
+  for (int i = 0; i < g.number_bits; ++i)
+    if (g.perm[(size_t)i] != i) return false;
+  return true;
+}
+
+}  // namespace lsb

@@ -1,0 +1,153 @@
+// runtime.cu -- process runtime + the ABI glue of kernels/reference.c
+// (error handler, refcounts, external arrays, the ls_chpl_kernels vtable) and
+// of chapel/src/library.c (ls_chpl_init / ls_chpl_finalize).
+#include <atomic>
+
+#include "state.hpp"
+
+namespace lsb {
+
+Runtime &runtime() {
+  static Runtime rt;
+  return rt;
+}
+
+void Runtime::ensure() {
+  if (stream != nullptr) return;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw CudaFailure{"no CUDA device available: liblattice_symmetries_b200 has no CPU fallback"};
+  // One rank per GPU: honour the device already selected by the process
+  // (torch.cuda.set_device / CUDA_VISIBLE_DEVICES), else LOCAL_RANK.
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  if (char const *s = getenv("LS_B200_DEVICE")) dev = atoi(s) % count;
+  CUDA_CHECK(cudaSetDevice(dev));
+  device = dev;
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  sm_count = prop.multiProcessorCount;
+  smem_optin = prop.sharedMemPerBlockOptin;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreate(&ev0));
+  CUDA_CHECK(cudaEventCreate(&ev1));
+}
+
+std::unordered_map<void const *, BuiltReps> &built_registry() {
+  static std::unordered_map<void const *, BuiltReps> m;
+  return m;
+}
+
+}  // namespace lsb
+
+using namespace lsb;
+
+extern "C" {
+
+// ---- kernels/reference.c:11-36 ---------------------------------------------
+void ls_hs_fatal_error(char const *func, int const line, char const *message) {
+  fprintf(stderr, "[Error]   [%s#%i] %s\n[Error]   Aborting ...", func, line, message);
+  abort();
+}
+
+typedef void (*error_handler_type)(char const *);
+static void default_error_handler(char const *message) {
+  fprintf(stderr, "[Error]   %s\n[Error]   Aborting ...", message);
+  abort();
+}
+static std::atomic<error_handler_type> g_error_handler{default_error_handler};
+
+void ls_hs_set_exception_handler(error_handler_type handler) {
+  if (handler == nullptr) handler = default_error_handler;
+  g_error_handler.store(handler);
+}
+
+void ls_hs_error(char const *message) {
+  error_handler_type handler = g_error_handler.load();
+  LSB_CHECK(handler != nullptr, "error handler is NULL");
+  (*handler)(message);
+}
+
+// ---- kernels/reference.c:40-64 ---------------------------------------------
+void ls_hs_internal_destroy_external_array(chpl_external_array *arr) {
+  LSB_CHECK(arr != nullptr, "trying to destroy a NULL chpl_external_array");
+  if (arr->freer != nullptr) {
+    auto const free_func = reinterpret_cast<void (*)(void *)>(arr->freer);
+    (*free_func)(arr->elts);
+  }
+}
+
+int ls_hs_internal_read_refcount(int const *refcount) {
+  return __atomic_load_n(refcount, __ATOMIC_SEQ_CST);
+}
+void ls_hs_internal_write_refcount(int *refcount, int value) {
+  __atomic_store_n(refcount, value, __ATOMIC_SEQ_CST);
+}
+int ls_hs_internal_inc_refcount(int *refcount) {
+  return __atomic_fetch_add(refcount, 1, __ATOMIC_SEQ_CST);
+}
+int ls_hs_internal_dec_refcount(int *refcount) {
+  return __atomic_fetch_sub(refcount, 1, __ATOMIC_SEQ_CST);
+}
+
+// ---- kernels/reference.c:214-225 -------------------------------------------
+static ls_chpl_kernels g_chpl_kernels = {nullptr, nullptr, nullptr, nullptr};
+ls_chpl_kernels const *ls_hs_internal_get_chpl_kernels(void) { return &g_chpl_kernels; }
+void ls_hs_internal_set_chpl_kernels(ls_chpl_kernels const *kernels) { g_chpl_kernels = *kernels; }
+
+// ---- chapel/src/LatticeSymmetries.chpl:18-33, chapel/src/library.c:19-34 ----
+void ls_chpl_init_kernels(void) {
+  ls_chpl_kernels k;
+  k.enumerate_states = &ls_chpl_enumerate_representatives;
+  k.operator_apply_off_diag = &ls_chpl_operator_apply_off_diag;
+  k.operator_apply_diag = &ls_chpl_operator_apply_diag;
+  k.matrix_vector_product = &ls_chpl_matrix_vector_product;
+  ls_hs_internal_set_chpl_kernels(&k);
+}
+
+void ls_chpl_init(void) {
+  // The Chapel runtime boots here in the reference; we register the vtable and
+  // bring up the device eagerly so that a missing GPU is reported at init.
+  ls_chpl_init_kernels();
+  guarded("ls_chpl_init", [] {});
+}
+
+void ls_chpl_finalize(void) {
+  // The reference's chpl_library_finalize() ends in exit(0)
+  // (python/lattice_symmetries/__init__.py:58); we just drain the stream.
+  Runtime &rt = runtime();
+  if (rt.stream != nullptr) cudaStreamSynchronize(rt.stream);
+}
+
+// ---- extensions ---------------------------------------------------------------
+uint64_t ls_b200_kernel_launch_count(void) { return runtime().launches.load(); }
+
+double ls_b200_last_kernel_ms(char const *name) {
+  Runtime &rt = runtime();
+  if (name != nullptr && strcmp(name, "build") == 0) return rt.last_build_ms;
+  return rt.last_matvec_ms;
+}
+
+void *ls_b200_stream(void) {
+  void *s = nullptr;
+  guarded("ls_b200_stream", [&] { s = (void *)runtime().stream; });
+  return s;
+}
+
+int ls_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void *ls_b200_device_malloc(size_t bytes) {
+  void *p = nullptr;
+  guarded("ls_b200_device_malloc", [&] { CUDA_CHECK(cudaMalloc(&p, bytes)); });
+  return p;
+}
+void ls_b200_device_free(void *p) {
+  if (p != nullptr) cudaFree(p);
+}
+
+}  // extern "C"
