@@ -258,6 +258,10 @@ uint64_t ls_b200_kernel_launch_count(void);
 double ls_b200_last_kernel_ms(char const *name);
 /* The CUDA stream (cudaStream_t) all library work is ordered on. */
 void *ls_b200_stream(void);
+/* Order all subsequent library work on the caller's stream instead (e.g. the
+ * stream NCCL collectives are enqueued behind); NULL restores the library's
+ * own stream.  Drains the previous stream first.  Returns 0 on success. */
+int ls_b200_set_stream(void *cuda_stream);
 int ls_b200_device_count(void);
 
 /* Device views of a built basis: sorted representatives, their norms
@@ -306,6 +310,13 @@ int ls_b200_set_representatives_device(ls_hs_basis *basis,
                                        int cache_bits);
 void *ls_b200_device_malloc(size_t bytes);
 void ls_b200_device_free(void *p);
+/* Copies ordered on ls_b200_stream(); both return after the copy completed
+ * (0 on success).  `host` may be pageable or pinned. */
+int ls_b200_copy_to_device(void *dst_dev, void const *src_host, size_t bytes);
+int ls_b200_copy_to_host(void *dst_host, void const *src_dev, size_t bytes);
+/* Pinned host allocations for callers that stage vectors themselves. */
+void *ls_b200_host_malloc(size_t bytes);
+void ls_b200_host_free(void *p);
 
 #ifdef __cplusplus
 }

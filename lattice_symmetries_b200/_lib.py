@@ -164,6 +164,7 @@ PROTOTYPES = {
     "ls_b200_kernel_launch_count": (C.c_uint64, []),
     "ls_b200_last_kernel_ms": (C.c_double, [C.c_char_p]),
     "ls_b200_stream": (C.c_void_p, []),
+    "ls_b200_set_stream": (C.c_int, [C.c_void_p]),
     "ls_b200_device_count": (C.c_int, []),
     "ls_b200_basis_device_view": (
         C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
@@ -179,7 +180,73 @@ PROTOTYPES = {
         C.c_int, [C.POINTER(ls_hs_basis), C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
     "ls_b200_device_malloc": (C.c_void_p, [C.c_size_t]),
     "ls_b200_device_free": (None, [C.c_void_p]),
+    "ls_b200_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ls_b200_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ls_b200_host_malloc": (C.c_void_p, [C.c_size_t]),
+    "ls_b200_host_free": (None, [C.c_void_p]),
 }
+
+
+class DeviceArray:
+    """A device allocation owned through the C ABI (ls_b200_device_malloc);
+    numpy in / numpy out.  Host-side plumbing for tests, bench and the Lanczos
+    driver -- no torch types cross the boundary."""
+
+    def __init__(self, count: int, dtype):
+        import numpy as np
+        self.dtype = np.dtype(dtype)
+        self.count = int(count)
+        self.ptr = lib.ls_b200_device_malloc(max(self.nbytes, 8))
+        check_error()
+        if not self.ptr:
+            raise MemoryError(f"ls_b200_device_malloc({self.nbytes}) failed")
+
+    @property
+    def nbytes(self) -> int:
+        return self.count * self.dtype.itemsize
+
+    @classmethod
+    def from_numpy(cls, a) -> "DeviceArray":
+        import numpy as np
+        a = np.ascontiguousarray(a)
+        d = cls(a.size, a.dtype)
+        d.upload(a)
+        return d
+
+    def upload(self, a) -> None:
+        import numpy as np
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.size == self.count
+        lib.ls_b200_copy_to_device(self.ptr, a.ctypes.data, self.nbytes)
+        check_error()
+
+    def numpy(self):
+        import numpy as np
+        out = np.empty(self.count, dtype=self.dtype)
+        lib.ls_b200_copy_to_host(out.ctypes.data, self.ptr, self.nbytes)
+        check_error()
+        return out
+
+    def free(self) -> None:
+        if self.ptr:
+            lib.ls_b200_device_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def device_to_numpy(ptr: int, count: int, dtype):
+    """Copy ``count`` elements from a raw device pointer."""
+    import numpy as np
+    out = np.empty(int(count), dtype=np.dtype(dtype))
+    if count:
+        lib.ls_b200_copy_to_host(out.ctypes.data, ptr, out.nbytes)
+        check_error()
+    return out
 
 
 def _load():

@@ -46,7 +46,8 @@ inline void cuda_check(cudaError_t e, char const *expr, char const *file, int li
 // ---- process-wide runtime ---------------------------------------------------
 struct Runtime {
   std::mutex mutex;  // serialises host entry points
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream work is ordered on (own_stream unless overridden)
+  cudaStream_t own_stream = nullptr;
   int device = -1;
   int sm_count = 0;
   size_t smem_optin = 0;

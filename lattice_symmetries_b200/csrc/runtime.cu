@@ -13,7 +13,7 @@ Runtime &runtime() {
 }
 
 void Runtime::ensure() {
-  if (stream != nullptr) return;
+  if (own_stream != nullptr) return;
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -29,7 +29,8 @@ void Runtime::ensure() {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
   sm_count = prop.multiProcessorCount;
   smem_optin = prop.sharedMemPerBlockOptin;
-  CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+  stream = own_stream;
   CUDA_CHECK(cudaEventCreate(&ev0));
   CUDA_CHECK(cudaEventCreate(&ev1));
 }
@@ -135,6 +136,17 @@ void *ls_b200_stream(void) {
   return s;
 }
 
+int ls_b200_set_stream(void *cuda_stream) {
+  int status = -1;
+  guarded("ls_b200_set_stream", [&] {
+    Runtime &rt = runtime();
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    rt.stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : rt.own_stream;
+    status = 0;
+  });
+  return status;
+}
+
 int ls_b200_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -148,6 +160,37 @@ void *ls_b200_device_malloc(size_t bytes) {
 }
 void ls_b200_device_free(void *p) {
   if (p != nullptr) cudaFree(p);
+}
+
+int ls_b200_copy_to_device(void *dst_dev, void const *src_host, size_t bytes) {
+  int status = -1;
+  guarded("ls_b200_copy_to_device", [&] {
+    if (bytes > 0) {
+      CUDA_CHECK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, runtime().stream));
+      CUDA_CHECK(cudaStreamSynchronize(runtime().stream));
+    }
+    status = 0;
+  });
+  return status;
+}
+int ls_b200_copy_to_host(void *dst_host, void const *src_dev, size_t bytes) {
+  int status = -1;
+  guarded("ls_b200_copy_to_host", [&] {
+    if (bytes > 0) {
+      CUDA_CHECK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, runtime().stream));
+      CUDA_CHECK(cudaStreamSynchronize(runtime().stream));
+    }
+    status = 0;
+  });
+  return status;
+}
+void *ls_b200_host_malloc(size_t bytes) {
+  void *p = nullptr;
+  guarded("ls_b200_host_malloc", [&] { CUDA_CHECK(cudaMallocHost(&p, bytes)); });
+  return p;
+}
+void ls_b200_host_free(void *p) {
+  if (p != nullptr) cudaFreeHost(p);
 }
 
 }  // extern "C"

@@ -1,0 +1,213 @@
+"""Multi-GPU sharding of the two hot paths: one process per GPU, ``torch.distributed``
+for the plumbing (NCCL over NVLink on the GPUs, gloo in the CPU tests).
+
+The reference distributes basis states over Chapel locales by *hash*
+(chapel/src/StatesEnumeration.chpl:198-212) and pushes (state, coefficient)
+pairs to their owners through GASNet PUTs
+(chapel/src/DistributedMatrixVector.chpl:226-339, :545-579).  Here:
+
+* **basis build** -- candidates are addressed by their combinadic index, rank r
+  scans the contiguous index range ``shard_bounds(total, P, r)``; the shards are
+  already globally ordered, so assembling the basis is one all-gather of the
+  counts plus one broadcast of every shard into its slot of the full array.  No
+  collective on the data path of the scan itself.
+* **matvec** -- rows (= contiguous ranges of sorted representatives) are split
+  evenly; the pull-form kernel writes only its own rows, so the single exchange
+  step is the all-gather of the x shards (``all_gather_into_tensor`` straight
+  into the replicated, padded vector).  y needs no reduction.
+
+The exchange logic below is independent of where the shard was computed: it
+takes tensors (CPU or CUDA), so the world_size-2 gloo tests drive it with
+shards produced on the CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+__all__ = ["shard_bounds", "row_bounds", "exchange_shards", "ShardedOperator", "build_sharded", "init_process"]
+
+ALIGN = 32  # candidate shards start on a multiple of 32 (one bit-sliced word)
+
+
+def shard_bounds(total: int, world: int, rank: int, align: int = ALIGN) -> Tuple[int, int]:
+    """Contiguous candidate-index range of ``rank``: boundaries are multiples of
+    ``align``, sizes differ by at most ``align``, the union is [0, total)."""
+    words = (total + align - 1) // align
+    lo = (words * rank) // world * align
+    hi = (words * (rank + 1)) // world * align
+    return min(lo, total), min(hi, total)
+
+
+def row_bounds(dim: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """Even row split with a fixed chunk = ceil(dim / world): returns
+    (row_begin, row_end, chunk).  Trailing ranks may own fewer (or zero) rows;
+    the replicated vector is padded to world * chunk."""
+    chunk = (dim + world - 1) // world if dim > 0 else 0
+    lo = min(rank * chunk, dim)
+    hi = min((rank + 1) * chunk, dim)
+    return lo, hi, chunk
+
+
+def exchange_shards(local, group=None):
+    """All ranks contribute a 1-D tensor (their shard, possibly empty); every rank
+    receives (full, offsets) where ``full`` is the concatenation in rank order and
+    ``offsets[r]`` the start of rank r's shard.  Works on CPU (gloo) and CUDA (NCCL)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    count = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    counts = torch.zeros(world, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(counts, count, group=group)
+    counts = counts.cpu().tolist()
+    offsets = [0]
+    for c in counts:
+        offsets.append(offsets[-1] + int(c))
+    full = torch.empty(offsets[-1], dtype=local.dtype, device=local.device)
+    rank = dist.get_rank(group)
+    full[offsets[rank]:offsets[rank + 1]].copy_(local)
+    for r in range(world):
+        if counts[r] > 0:
+            src = dist.get_global_rank(group, r) if group is not None else r
+            dist.broadcast(full[offsets[r]:offsets[r + 1]], src=src, group=group)
+    return full, offsets
+
+
+# ---- CUDA side ---------------------------------------------------------------------------
+class _RawDevice:
+    """Zero-copy view of a raw device pointer for ``torch.as_tensor``."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {
+            "shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+def tensor_from_pointer(ptr: int, count: int, dtype: str):
+    """dtype: 'u8' (uint64 viewed as int64, NCCL has no uint64 arithmetic but moves bytes) or 'f8'."""
+    import torch
+    if count == 0:
+        return torch.empty(0, dtype=torch.int64 if dtype == "u8" else torch.float64, device="cuda")
+    typestr = "<i8" if dtype == "u8" else "<f8"
+    return torch.as_tensor(_RawDevice(ptr, count, typestr), device="cuda")
+
+
+_stream = None
+
+
+def init_process(local_rank: Optional[int] = None):
+    """Select this rank's GPU and order all library work on a dedicated torch
+    stream, so that NCCL collectives and our kernels interleave without host syncs."""
+    import os
+    import torch
+    from . import _lib
+    global _stream
+    if local_rank is None:
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    _lib.ensure_init()
+    if _stream is None:
+        _stream = torch.cuda.Stream()
+        _lib.lib.ls_b200_set_stream(_stream.cuda_stream)
+        _lib.check_error()
+    torch.cuda.set_stream(_stream)
+    return _stream
+
+
+def build_sharded(basis, group=None) -> List[int]:
+    """Build ``basis`` across the ranks of ``group``: every rank scans its
+    candidate range on its own GPU, the shards are exchanged over NCCL and the
+    full sorted representative list (+ norms) is installed on every rank.
+    Returns the shard offsets (rank r built rows [offsets[r], offsets[r+1]))."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    total = basis.number_candidates
+    lo, hi = shard_bounds(total, world, rank)
+    d_reps, d_norms, count = basis.build_shard(lo, hi)
+    local_reps = tensor_from_pointer(d_reps, count, "u8")
+    full_reps, offsets = exchange_shards(local_reps, group)
+    dim = offsets[-1]
+    # the library takes ownership of buffers it allocated itself
+    own_reps = _lib.lib.ls_b200_device_malloc(max(8 * dim, 8))
+    tensor_from_pointer(own_reps, dim, "u8").copy_(full_reps)
+    own_norms = None
+    if basis.has_permutation_symmetries:
+        local_norms = tensor_from_pointer(d_norms, count, "f8")
+        full_norms, _ = exchange_shards(local_norms, group)
+        own_norms = _lib.lib.ls_b200_device_malloc(max(8 * dim, 8))
+        tensor_from_pointer(own_norms, dim, "f8").copy_(full_norms)
+    torch.cuda.current_stream().synchronize()
+    if d_reps:
+        _lib.lib.ls_b200_device_free(d_reps)
+    if d_norms:
+        _lib.lib.ls_b200_device_free(d_norms)
+    basis.set_representatives_device(own_reps, own_norms, dim)
+    return offsets
+
+
+@dataclass
+class _Layout:
+    dim: int
+    world: int
+    rank: int
+    row_begin: int
+    row_end: int
+    chunk: int
+
+
+class ShardedOperator:
+    """y = H x with rows sharded over the ranks and x replicated by all-gather.
+
+    ``x_full`` is a padded replicated vector of length world * chunk; ``matvec``
+    computes this rank's rows into its slot of ``y_full`` and all-gathers in
+    place, so the output can be fed straight back in (Lanczos)."""
+
+    def __init__(self, operator, group=None):
+        import torch.distributed as dist
+        self.op = operator
+        self.group = group
+        dim = operator.basis.number_states
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lo, hi, chunk = row_bounds(dim, world, rank)
+        self.layout = _Layout(dim, world, rank, lo, hi, chunk)
+
+    def empty_vector(self, dtype=None):
+        import torch
+        L = self.layout
+        return torch.zeros(L.world * L.chunk, dtype=dtype or torch.float64, device="cuda")
+
+    def local_rows(self, v):
+        L = self.layout
+        return v[L.row_begin:L.row_end]
+
+    def matvec(self, x_full, y_full, gather: bool = True) -> None:
+        import torch
+        import torch.distributed as dist
+        L = self.layout
+        cplx = x_full.dtype == torch.complex128
+        if L.row_end > L.row_begin:
+            y_ptr = y_full.data_ptr() + L.row_begin * y_full.element_size()
+            self.op.matvec_device(x_full.data_ptr(), y_ptr, L.row_begin, L.row_end, complex_vectors=cplx)
+        if gather and L.world > 1:
+            mine = y_full[L.rank * L.chunk:(L.rank + 1) * L.chunk]
+            if cplx:
+                dist.all_gather_into_tensor(torch.view_as_real(y_full), torch.view_as_real(mine), group=self.group)
+            else:
+                dist.all_gather_into_tensor(y_full, mine, group=self.group)
+
+    def dot(self, a_full, b_full):
+        """Global <a, b> from the local rows (one all-reduce of a scalar)."""
+        import torch
+        import torch.distributed as dist
+        s = torch.vdot(self.local_rows(a_full), self.local_rows(b_full)).reshape(1)
+        if self.layout.world > 1:
+            if s.dtype == torch.complex128:
+                dist.all_reduce(torch.view_as_real(s), group=self.group)
+            else:
+                dist.all_reduce(s, group=self.group)
+        return s

@@ -1,0 +1,395 @@
+"""GPU parity tests: the CUDA path (through the Python host mirror -> C ABI of
+include/lattice_symmetries_b200.h) against the CPU oracle on the same inputs.
+
+Bar: bit-exact for representatives, norms, indices, flags, (beta, coeff, offsets)
+rows; 1e-12 relative for matvec output (BASELINE.json north_star); 1e-10 for
+ground-state energies.  Run with ``pytest -m gpu`` on a B200.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+MATVEC_RTOL = 1e-12
+
+
+def _ls():
+    import lattice_symmetries_b200 as ls
+    return ls
+
+
+def _rel_err(a, b):
+    scale = max(float(np.linalg.norm(b)), 1e-300)
+    return float(np.linalg.norm(a - b)) / scale
+
+
+# ---- problems ------------------------------------------------------------------------
+def _model_problem(model) -> H.Problem:
+    particle = 0 if model.particle == "spin-1/2" else 1
+    return H.Problem(model.name, model.number_sites, model.expression, particle=particle,
+                     hamming_weight=model.hamming_weight, number_particles=model.number_particles,
+                     spin_inversion=model.spin_inversion, symmetries=model.symmetries)
+
+
+def _problems():
+    from lattice_symmetries_b200 import lattices as L
+    return {
+        "chain10": H.chain10_getting_started,
+        "chain16_symm": lambda: _model_problem(L.heisenberg_chain(16)),
+        "chain20_k3": lambda: _model_problem(L.heisenberg_chain(20, translation_sector=3, parity_sector=None,
+                                                                spin_inversion=None)),
+        "chain24_symm": lambda: _model_problem(L.heisenberg_chain(24)),     # BASELINE configs[0]
+        "kagome12_complex": H.kagome12_complex_sector,
+        "kagome18_c2": lambda: _model_problem(L.kagome_heisenberg(18)),
+        "kagome24_c2v_inv": lambda: _model_problem(L.kagome_heisenberg(24, spin_inversion=1)),
+        "ladder_2x8_dm": lambda: _model_problem(L.ladder_dm(8)),            # configs[2] shape, scaled down
+        "hubbard_2x4": H.hphi_04_hubbard_square,                            # configs[3] shape, scaled down
+        "hubbard_3x3_43": lambda: _model_problem(L.hubbard_square(3, 3, number_particles=(4, 3))),
+        "hphi01": H.hphi_01_kagome,
+        "hphi02": H.hphi_02_ladder,
+        "hphi03": H.hphi_03_hcor,
+        "hphi05": H.hphi_05_hubbard_tri,
+        "chain12_inv_only": lambda: H.Problem(
+            "chain12_inv_only", 12, L.heisenberg_chain(12).expression, hamming_weight=6, spin_inversion=-1),
+        "chain10_inv_nohw": lambda: H.Problem(
+            "chain10_inv_nohw", 10, L.heisenberg_chain(10).expression, spin_inversion=1),
+    }
+
+
+SYMMETRIC = ["chain10", "chain16_symm", "chain20_k3", "chain24_symm", "kagome12_complex", "kagome18_c2",
+             "kagome24_c2v_inv", "ladder_2x8_dm"]
+ALL = list(_problems().keys())
+REAL_MATVEC = [k for k in ALL if k not in ("ladder_2x8_dm", "kagome12_complex", "chain20_k3")]
+
+
+@pytest.fixture(scope="module")
+def built():
+    """name -> (problem, oracle setup, product basis, product operator), cached per module."""
+    cache = {}
+
+    def get(name, oracle):
+        if name not in cache:
+            ls = _ls()
+            p = _problems()[name]()
+            setup = p.oracle_setup(oracle)
+            basis = p.product_basis()
+            basis.build()
+            op = ls.Operator(basis, p.expr)
+            cache[name] = (p, setup, basis, op)
+        return cache[name]
+    return get
+
+
+# ---- (a-9) basis construction ----------------------------------------------------------
+@pytest.mark.parametrize("name", ALL)
+def test_build_matches_oracle(oracle, built, name):
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    got = basis.states
+    assert got.dtype == np.uint64
+    assert got.shape == reps.shape, (got.shape, reps.shape)
+    assert np.array_equal(got, reps)
+    assert np.all(got[1:] > got[:-1]) if got.size > 1 else True
+
+
+@pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome12_complex", "kagome24_c2v_inv"])
+@pytest.mark.parametrize("mode", ["scalar", "bitsliced"])
+def test_build_kernel_variants_agree(oracle, name, mode, monkeypatch):
+    """Both pass-A kernels (bit-sliced plane renaming / scalar Benes walk) emit the oracle's list."""
+    monkeypatch.setenv("LS_B200_BUILD", mode)
+    p = _problems()[name]()
+    reps = p.oracle_basis(oracle).enumerate()
+    basis = p.product_basis()
+    basis.build()
+    assert np.array_equal(basis.states, reps)
+
+
+@pytest.mark.parametrize("name", SYMMETRIC)
+def test_built_norms_bit_exact(oracle, built, name):
+    from lattice_symmetries_b200 import _lib
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    d_reps, d_norms, count = basis.device_view()
+    assert count == reps.shape[0]
+    assert np.array_equal(_lib.device_to_numpy(d_reps, count, np.uint64), reps)
+    norms = _lib.device_to_numpy(d_norms, count, np.float64)
+    _, _, want = ob.group.state_info(reps)
+    assert np.array_equal(norms.view(np.uint64), want.view(np.uint64))
+
+
+@pytest.mark.parametrize("name", ["chain24_symm", "kagome18_c2", "hubbard_2x4", "hphi01"])
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_build_concatenates(oracle, built, name, shards):
+    """Contiguous candidate-index shards (one per rank) concatenate to the full sorted list."""
+    from lattice_symmetries_b200 import _lib
+    from lattice_symmetries_b200.distributed import shard_bounds
+    p, (ob, reps, *_), basis, op = built(name, oracle)
+    fresh = p.product_basis()
+    total = fresh.number_candidates
+    parts = []
+    for r in range(shards):
+        lo, hi = shard_bounds(total, shards, r)
+        d_reps, d_norms, count = fresh.build_shard(lo, hi)
+        parts.append(_lib.device_to_numpy(d_reps, count, np.uint64))
+        _lib.lib.ls_b200_device_free(d_reps)
+        if d_norms:
+            _lib.lib.ls_b200_device_free(d_norms)
+    assert np.array_equal(np.concatenate(parts), reps)
+
+
+def test_basis_lists_reference_known_answers():
+    """python/test/test_api.py:38-42, python/run_tests.py:102-113."""
+    ls = _ls()
+    b = ls.SpinBasis(4)
+    b.build()
+    assert np.array_equal(b.states, np.arange(16, dtype=np.uint64))
+    assert np.array_equal(b.index(b.states), np.arange(16))
+    b = ls.SpinfulFermionBasis(2)
+    b.build()
+    assert np.array_equal(b.states, np.arange(16, dtype=np.uint64))
+    b = ls.SpinfulFermionBasis(2, 1)
+    b.build()
+    assert b.states.tolist() == [1, 2, 4, 8]
+    b = ls.SpinlessFermionBasis(5, 2)
+    b.build()
+    assert b.states.tolist() == sorted(x for x in range(32) if bin(x).count("1") == 2)
+
+
+# ---- (a-1, a-2) per-state kernels ---------------------------------------------------------
+@pytest.mark.parametrize("name", SYMMETRIC)
+def test_state_info_and_is_representative(oracle, built, name):
+    p, (ob, reps, *_), basis, op = built(name, oracle)
+    rng = np.random.default_rng(42)
+    n = p.number_sites
+    hw = p.hamming_weight if p.hamming_weight is not None else n // 2
+    states = np.concatenate([H.random_fixed_hamming_states(rng, n, hw, 20000), reps[:20000]])
+    betas, chars, norms = basis.state_info(states)
+    wb, wc, wn = ob.group.state_info(states)
+    assert np.array_equal(betas, wb)
+    assert np.array_equal(norms.view(np.uint64), wn.view(np.uint64))
+    # the character is only defined where the norm is non-zero
+    live = wn > 0
+    assert np.array_equal(chars[live].view(np.float64).view(np.uint64), wc[live].view(np.float64).view(np.uint64))
+    flags, sums = basis.is_representative(states)
+    wf, ws = ob.group.is_representative(states)
+    assert np.array_equal(flags, wf)
+    keep = wf == 1
+    assert np.array_equal(sums[keep].view(np.uint64), ws[keep].view(np.uint64))
+
+
+def test_state_info_empty_and_strided(oracle, built):
+    p, (ob, reps, *_), basis, op = built("chain16_symm", oracle)
+    betas, chars, norms = basis.state_info(np.zeros(0, dtype=np.uint64))
+    assert betas.shape == (0,) and chars.shape == (0,) and norms.shape == (0,)
+    b, c, nrm = basis.state_info(int(reps[3]))
+    assert b == int(reps[3]) and c == 1.0 + 0j and nrm > 0
+
+
+# ---- (a-4) state_index ----------------------------------------------------------------------
+@pytest.mark.parametrize("name", ALL)
+def test_state_index(oracle, built, name):
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    rng = np.random.default_rng(7)
+    present = reps[rng.integers(0, reps.shape[0], size=min(50000, 4 * reps.shape[0]))]
+    absent = present ^ np.uint64(1)  # mostly not in the basis
+    junk = rng.integers(0, 2 ** min(63, ob.number_bits), size=1000, dtype=np.uint64)
+    needles = np.concatenate([reps[:1], reps[-1:], present, absent, junk])
+    got = basis.index(needles)
+    want = index(needles)
+    assert np.array_equal(got, want)
+    assert np.array_equal(basis.index(reps), np.arange(reps.shape[0]))
+    if oracle.ref_available():
+        assert np.array_equal(got, oracle.ref_state_index(reps, ob.number_bits, 22, needles))
+
+
+# ---- (a-5, a-6) rows of H ---------------------------------------------------------------------
+@pytest.mark.parametrize("name", ALL)
+def test_operator_apply(oracle, built, name):
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    rng = np.random.default_rng(3)
+    states = reps[rng.integers(0, reps.shape[0], size=min(5000, reps.shape[0]))]
+    xs = rng.standard_normal(states.shape[0])
+    for scale in (None, xs):
+        betas, coeffs, offsets = op.apply_off_diag(states, scale)
+        wb, wc, wo = oracle.apply_off_diag(off, states, scale)
+        assert np.array_equal(offsets, wo)
+        assert np.array_equal(betas, wb)
+        assert np.array_equal(coeffs.view(np.float64).view(np.uint64), wc.view(np.float64).view(np.uint64))
+        ys = op.apply_diag(states, scale)
+        wy = oracle.apply_diag(diag, states, scale)
+        assert np.allclose(ys, wy, rtol=1e-15, atol=1e-15)
+
+
+@pytest.mark.parametrize("particles,expected", [(None, H.HUBBARD2_MATRIX_16), (2, H.HUBBARD2_MATRIX_6)])
+def test_hubbard_dense_matrices(particles, expected):
+    """python/run_tests.py:128-177 through the vtable's single-state row queries."""
+    ls = _ls()
+    p = H.hubbard2(particles)
+    basis = p.product_basis()
+    basis.build()
+    op = ls.Operator(basis, p.expr)
+    M = H.dense_from_rows(op.apply_diag_to_basis_state, op.apply_off_diag_to_basis_state, basis.states)
+    assert np.array_equal(M, expected)
+    # and the matvec reproduces the same matrix column by column
+    dim = basis.number_states
+    cols = np.stack([op.apply_to_state_vector(e) for e in np.eye(dim)], axis=1)
+    assert np.allclose(cols, expected, atol=1e-14)
+
+
+# ---- (a-7, a-8) matvec ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", REAL_MATVEC)
+def test_matvec_matches_oracle(oracle, built, name):
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    rng = np.random.default_rng(42)
+    x = rng.standard_normal(reps.shape[0])
+    x /= np.linalg.norm(x)
+    y = op.apply_to_state_vector(x)
+    want, nnz = oracle.matvec(ob, off, diag, index, x)
+    assert _rel_err(y, want) < MATVEC_RTOL, _rel_err(y, want)
+    assert np.allclose(y, want, rtol=1e-11, atol=1e-13)  # chapel/test/TestMatrixVectorProduct.chpl:15-16
+    assert op.count_matrix_elements() == nnz
+
+
+@pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome24_c2v_inv"])
+def test_matvec_scalar_variant_agrees(oracle, built, name, monkeypatch):
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(reps.shape[0])
+    y0 = op.apply_to_state_vector(x)
+    monkeypatch.setenv("LS_B200_MATVEC", "scalar")
+    y1 = op.apply_to_state_vector(x)
+    assert _rel_err(y1, y0) < MATVEC_RTOL
+
+
+@pytest.mark.parametrize("name", ["chain16_symm", "kagome18_c2", "hubbard_2x4"])
+def test_matvec_device_row_ranges(oracle, built, name):
+    """Device-resident entry point on contiguous row shards == host-pointer entry point."""
+    from lattice_symmetries_b200 import _lib
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    dim = reps.shape[0]
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(dim)
+    want = op.apply_to_state_vector(x)
+    d_x = _lib.DeviceArray.from_numpy(x)
+    parts = []
+    bounds = [0, dim // 3, dim // 3, (2 * dim) // 3 + 1, dim]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        d_y = _lib.DeviceArray(hi - lo, np.float64)
+        op.matvec_device(d_x.ptr, d_y.ptr, lo, hi, sync=True)
+        parts.append(d_y.numpy())
+    assert np.array_equal(np.concatenate(parts), want)
+
+
+@pytest.mark.parametrize("name", ["ladder_2x8_dm", "kagome12_complex", "chain20_k3", "chain16_symm"])
+def test_matvec_complex_hermitian_and_dense(oracle, built, name):
+    """Complex128 vectors are an extension with no reference oracle:
+    validate against a dense matrix assembled from the oracle's per-state
+    primitives with the rule H[j,i] = chi v sign n_j / n_i (BatchedOperator.chpl:207-253)."""
+    from lattice_symmetries_b200 import _lib
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    dim = reps.shape[0]
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal(dim) + 1j * rng.standard_normal(dim)
+    # dense reference (columns)
+    betas, coeffs, offsets = oracle.apply_off_diag(off, reps)
+    rb, rc, rn = ob.group.state_info(betas)
+    _, _, n_alpha = ob.group.state_info(reps)
+    j = index(rb)
+    col = np.repeat(np.arange(dim), np.diff(offsets))
+    live = rn > 0
+    assert np.all(j[live] >= 0)
+    val = np.where(live, coeffs * rc * rn / n_alpha[col], 0)
+    want = np.zeros(dim, dtype=np.complex128)
+    np.add.at(want, j[live], (val * x[col])[live])
+    want += oracle.apply_diag(diag, reps) * x
+    d_x = _lib.DeviceArray.from_numpy(x)
+    d_y = _lib.DeviceArray(dim, np.complex128)
+    op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
+    y = d_y.numpy()
+    assert _rel_err(y, want) < MATVEC_RTOL, _rel_err(y, want)
+    # Hermiticity: <u, H v> == conj(<v, H u>)
+    u = rng.standard_normal(dim) + 1j * rng.standard_normal(dim)
+    d_u = _lib.DeviceArray.from_numpy(u)
+    op.matvec_device(d_u.ptr, d_y.ptr, complex_vectors=True, sync=True)
+    hu = d_y.numpy()
+    assert abs(np.vdot(u, y) - np.conj(np.vdot(x, hu))) < 1e-10 * (np.linalg.norm(u) * np.linalg.norm(y))
+
+
+def test_matvec_invalid_sector_raises(oracle):
+    """DistributedMatrixVector.chpl:127-135: an operator that leaves the symmetry
+    sector halts the reference; here it surfaces through ls_hs_error."""
+    ls = _ls()
+    from lattice_symmetries_b200 import lattices as L
+    m = L.heisenberg_chain(12)
+    basis = m.basis()
+    basis.build()
+    bad = ls.Operator(basis, ls.Expr("σ⁺₀ σ⁻₁ + σ⁻₀ σ⁺₁ + 0.3 σᶻ₀ σᶻ₅"))  # not translation invariant
+    x = np.ones(basis.number_states)
+    with pytest.raises(RuntimeError, match="invalid index"):
+        bad.apply_to_state_vector(x)
+    # the library stays usable afterwards
+    good = m.operator(basis)
+    assert np.isfinite(good.apply_to_state_vector(x)).all()
+
+
+def test_matvec_input_validation(oracle, built):
+    p, setup, basis, op = built("chain16_symm", oracle)
+    with pytest.raises(TypeError):
+        op.apply_to_state_vector(np.zeros(basis.number_states, dtype=np.float32))
+    with pytest.raises(ValueError):
+        op.apply_to_state_vector(np.zeros(basis.number_states + 1))
+
+
+# ---- energies (pin build + index + matvec jointly) ----------------------------------------------
+def test_chain10_ground_state_energy(oracle, built):
+    """python/example/getting_started.py:49-51."""
+    import scipy.sparse.linalg as sla
+    p, setup, basis, op = built("chain10", oracle)
+    assert basis.number_states == 13
+    dim = basis.number_states
+    Hm = np.stack([op.apply_to_state_vector(e) for e in np.eye(dim)], axis=1)
+    assert np.allclose(Hm, Hm.T, atol=1e-13)
+    assert np.isclose(np.linalg.eigvalsh(Hm)[0], -18.06178542, atol=1e-8)
+    w = sla.eigsh(op, k=1, which="SA", tol=1e-12)[0]
+    assert np.isclose(w[0], -18.06178542, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["hphi01", "hphi02", "hphi03", "hubbard_2x4", "hphi05"])
+def test_hphi_energies(oracle, built, name):
+    """test/0N_*/HPhi/output/zvo_energy.dat:1 via eigsh on the GPU operator."""
+    import scipy.sparse.linalg as sla
+    p, setup, basis, op = built(name, oracle)
+    w = sla.eigsh(op, k=1, which="SA", tol=1e-12)[0]
+    assert np.isclose(w[0], p.energy, rtol=0, atol=1e-9), (w[0], p.energy)
+
+
+def test_lanczos_matches_eigsh(oracle, built):
+    from lattice_symmetries_b200.lanczos import lanczos_ground_state
+    import scipy.sparse.linalg as sla
+    p, setup, basis, op = built("chain24_symm", oracle)
+    e0 = lanczos_ground_state(op, max_iters=200, tol=1e-12, seed=1).energy
+    w = sla.eigsh(op, k=1, which="SA", tol=1e-12)[0]
+    assert abs(e0 - w[0]) < 1e-10 * abs(w[0])
+
+
+# ---- golden fixtures (tests/golden, generated by tests/golden/make_golden.py) -------------------
+def test_golden_fixtures():
+    import json
+    from pathlib import Path
+    ls = _ls()
+    golden = Path(__file__).parent / "golden"
+    from golden import make_golden as G
+    for name in G.CASES:
+        data = np.load(golden / f"{name}.npz")
+        p = G.CASES[name]()
+        basis = p.product_basis()
+        basis.build()
+        assert np.array_equal(basis.states, data["representatives"]), name
+        op = ls.Operator(basis, p.expr)
+        if "y" in data.files:
+            y = op.apply_to_state_vector(data["x"])
+            assert _rel_err(y, data["y"]) < MATVEC_RTOL, name
