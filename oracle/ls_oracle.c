@@ -571,7 +571,12 @@ LS_ORACLE_API int64_t oracle_matvec(oracle_basis const *b,
                                     ptrdiff_t row_begin, ptrdiff_t row_end,
                                     double const *x, double *y,
                                     int zero_and_diag) {
-  if (zero_and_diag) {
+  /* flags: bit 0 = zero y and apply the diagonal first (localDiagonal);
+   * bit 1 = SAMPLING mode for the CPU-baseline timing only: `reps` is a sorted
+   * PREFIX of the basis, matrix elements that leave it are searched for (same
+   * work) and then dropped instead of raising the invalid-index error. */
+  int const tolerate_missing = (zero_and_diag & 2) != 0;
+  if (zero_and_diag & 1) {
     if (diag != NULL && diag->number_terms > 0)
       oracle_apply_diag(diag, dim, reps, y, x);
     else
@@ -642,7 +647,7 @@ LS_ORACLE_API int64_t oracle_matvec(oracle_basis const *b,
           if (idx[k] >= 0) {
 #pragma omp atomic
             y[idx[k]] += c;
-          } else {
+          } else if (!tolerate_missing) {
             bad = 1;
           }
         }

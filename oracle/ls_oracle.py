@@ -260,7 +260,7 @@ def apply_off_diag(terms: Terms, alphas, xs=None):
 
 
 def matvec(basis: Basis, off: Terms, diag: Terms, index: Index, x: np.ndarray, row_begin: int = 0,
-           row_end: Optional[int] = None) -> Tuple[np.ndarray, int]:
+           row_end: Optional[int] = None, sampling_prefix: bool = False) -> Tuple[np.ndarray, int]:
     """Push-form y = H x as the reference assembles it; returns (y, number of
     off-diagonal matrix elements emitted from the columns [row_begin, row_end))."""
     reps = index.reps
@@ -270,7 +270,7 @@ def matvec(basis: Basis, off: Terms, diag: Terms, index: Index, x: np.ndarray, r
     if row_end is None:
         row_end = dim
     n = lib().oracle_matvec(C.byref(basis.c), off.ptr(), diag.ptr(), index.handle, _p(reps, u64_p), dim,
-                            row_begin, row_end, _p(x, f64_p), _p(y, f64_p), 1)
+                            row_begin, row_end, _p(x, f64_p), _p(y, f64_p), 3 if sampling_prefix else 1)
     if n < 0:
         raise RuntimeError("oracle_matvec: invalid index (operator does not respect the basis symmetries)")
     return y, int(n)

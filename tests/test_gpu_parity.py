@@ -170,9 +170,13 @@ def test_state_info_and_is_representative(oracle, built, name):
     betas, chars, norms = basis.state_info(states)
     wb, wc, wn = ob.group.state_info(states)
     assert np.array_equal(betas, wb)
-    assert np.array_equal(norms.view(np.uint64), wn.view(np.uint64))
-    # the character is only defined where the norm is non-zero
-    live = wn > 0
+    # States outside the sector have a mathematically-zero stabiliser sum; with complex
+    # characters the reference's fp sum leaves +-1e-16 noise there (sqrt -> ~1e-9 or NaN,
+    # SURVEY 8a-2).  The CUDA path clamps that band to exactly 0; everything else is bit-exact.
+    live = wn > 1e-6
+    assert np.array_equal(norms[live].view(np.uint64), wn[live].view(np.uint64))
+    assert np.all(norms[~live] == 0.0)
+    assert live.sum() >= reps[:20000].shape[0]
     assert np.array_equal(chars[live].view(np.float64).view(np.uint64), wc[live].view(np.float64).view(np.uint64))
     flags, sums = basis.is_representative(states)
     wf, ws = ob.group.is_representative(states)
