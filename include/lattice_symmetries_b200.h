@@ -263,6 +263,10 @@ void *ls_b200_stream(void);
  * own stream.  Drains the previous stream first.  Returns 0 on success. */
 int ls_b200_set_stream(void *cuda_stream);
 int ls_b200_device_count(void);
+/* Measured 32-bit logic-op (LOP3) issue rate of the device, thread-ops per
+ * second: the integer-side roofline denominator (MEASURED_PEAKS.json has only
+ * HBM and tensor peaks). */
+double ls_b200_measure_lop3_peak(void);
 
 /* Device views of a built basis: sorted representatives, their norms
  * (state_info convention, sqrt(n/|G|)); pointers stay owned by the library. */

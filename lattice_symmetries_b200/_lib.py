@@ -166,6 +166,7 @@ PROTOTYPES = {
     "ls_b200_stream": (C.c_void_p, []),
     "ls_b200_set_stream": (C.c_int, [C.c_void_p]),
     "ls_b200_device_count": (C.c_int, []),
+    "ls_b200_measure_lop3_peak": (C.c_double, []),
     "ls_b200_basis_device_view": (
         C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ls_b200_matvec_device": (C.c_int, [C.POINTER(ls_hs_operator), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

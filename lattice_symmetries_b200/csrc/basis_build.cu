@@ -317,23 +317,21 @@ build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint6
   int const nbits = g.number_bits;
 #pragma unroll 1
   for (int j = 0; j < G; ++j) {
-    uint16_t const *off = c_plane_offset + j * NP;
-    uint32_t lt = 0, eq = 0xffffffffu, ltf = 0, eqf = 0xffffffffu;
+    uint16_t const *off = c_plane_offset + j * (NP + kPlaneRowExtra);
+    // With spin inversion both y and ~y must be >= x; the smaller of the two is
+    // z = y ^ top(y) (top = the most significant live bit decides their order),
+    // so one comparison per plane covers both images.
+    uint32_t top = 0;
+    if (INV) top = *reinterpret_cast<uint32_t const *>(column + off[NP]);
+    uint32_t lt = 0, eq = 0xffffffffu;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      uint32_t const y = *reinterpret_cast<uint32_t const *>(column + off[i]);
-      cmp_step(y, xr[i], lt, eq);
-      if (INV) {
-        if (i < NP - 3 || i < nbits) cmp_step_flipped(y, xr[i], ltf, eqf);
-      }
+      uint32_t z = *reinterpret_cast<uint32_t const *>(column + off[i]);
+      if (INV) z ^= (i < NP - 3 || i < nbits) ? top : 0u;  // padding planes stay zero
+      cmp_step(z, xr[i], lt, eq);
     }
     alive &= ~lt;
-    uint32_t ev = (identity_first && j == 0) ? 0u : eq;
-    if (INV) {
-      alive &= ~ltf;
-      ev |= eqf;
-    }
-    events |= ev;
+    events |= (identity_first && j == 0) ? 0u : eq;
     if (__all_sync(0xffffffffu, alive == 0)) break;
   }
   events &= alive;

@@ -9,7 +9,7 @@
 // states.  Outputs are identical to the reference's; only the schedule differs.
 //
 // Everything here is __host__ __device__ so that tests/ can run the exact
-// same code on the CPU against the oracle (tests/emulate_bitslice.cpp).
+// same code on the CPU against the oracle.
 #pragma once
 
 #include <cstdint>

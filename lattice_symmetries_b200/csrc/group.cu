@@ -21,6 +21,9 @@ GroupView GroupData::view() const {
   v.re = d_re;
   v.im = d_im;
   v.perm = d_perm;
+  v.cvals = d_cvals;
+  v.cinfo = d_cinfo;
+  v.number_chars = cinfo.empty() ? 0 : (int)(cvals.size() / 2);
   for (int k = 0; k < depth && k < kMaxDepth; ++k) v.shifts[k] = (unsigned)shifts[k];
   return v;
 }
@@ -30,6 +33,8 @@ GroupData::~GroupData() {
   cudaFree(d_re);
   cudaFree(d_im);
   cudaFree(d_perm);
+  cudaFree(d_cvals);
+  cudaFree(d_cinfo);
   magic = 0;
 }
 
@@ -194,8 +199,37 @@ void *ls_internal_create_halide_kernel_data(ls_hs_permutation_group const *g, in
                 "Benes network is not a permutation of the live bits");
       self->perm[e * (size_t)nb + (size_t)__builtin_ctzll(y)] = (uint8_t)j;
     }
+  // Distinct character values: the bit-sliced matvec tracks, per state, the
+  // index of the character of the minimising image instead of the element.
+  {
+    std::vector<double> &cv = self->cvals;
+    cv = {1.0, 0.0};
+    auto find = [&cv](double re, double im) -> int {
+      for (size_t k = 0; k < cv.size() / 2; ++k)
+        if (memcmp(&cv[2 * k], &re, 8) == 0 && memcmp(&cv[2 * k + 1], &im, 8) == 0) return (int)k;
+      cv.push_back(re);
+      cv.push_back(im);
+      return (int)(cv.size() / 2 - 1);
+    };
+    self->cinfo.resize(G);
+    bool fits = true;
+    for (size_t e = 0; e < G && fits; ++e) {
+      int const a = find(self->re[e], self->im[e]);
+      int b = 0;
+      if (spin_inversion != 0) b = find((double)spin_inversion * self->re[e], (double)spin_inversion * self->im[e]);
+      if (a > 255 || b > 255) fits = false;
+      self->cinfo[e] = (uint16_t)(a | (b << 8));
+    }
+    if (!fits) self->cinfo.clear();
+  }
   guarded(__func__, [&] {
     if (G == 0) return;
+    CUDA_CHECK(cudaMalloc(&self->d_cvals, sizeof(double) * self->cvals.size()));
+    CUDA_CHECK(cudaMemcpy(self->d_cvals, self->cvals.data(), sizeof(double) * self->cvals.size(), cudaMemcpyHostToDevice));
+    if (!self->cinfo.empty()) {
+      CUDA_CHECK(cudaMalloc(&self->d_cinfo, sizeof(uint16_t) * G));
+      CUDA_CHECK(cudaMemcpy(self->d_cinfo, self->cinfo.data(), sizeof(uint16_t) * G, cudaMemcpyHostToDevice));
+    }
     CUDA_CHECK(cudaMalloc(&self->d_masks, sizeof(uint64_t) * G * std::max<size_t>(D, 1)));
     CUDA_CHECK(cudaMalloc(&self->d_re, sizeof(double) * G));
     CUDA_CHECK(cudaMalloc(&self->d_im, sizeof(double) * G));

@@ -15,6 +15,7 @@ IndexView IndexData::view() const {
   v.shift = shift;
   v.identity = identity ? 1 : 0;
   v.number_buckets = uint64_t(1) << prefix_bits;
+  v.steps = steps;
   return v;
 }
 
@@ -45,6 +46,24 @@ bucket_offsets_kernel(uint64_t const *__restrict__ reps, int64_t n, int shift, i
     }
     offsets[p] = (T)lo;
   }
+}
+
+// Largest bucket of the table (sets the trip count of the branchless search).
+template <class T>
+__global__ void __launch_bounds__(256)
+max_bucket_kernel(T const *__restrict__ offsets, int64_t number_buckets, unsigned long long *__restrict__ out) {
+  unsigned long long local = 0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < number_buckets;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long const w = (unsigned long long)(offsets[p + 1] - offsets[p]);
+    local = w > local ? w : local;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long const other = __shfl_xor_sync(0xffffffffu, local, o);
+    local = other > local ? other : local;
+  }
+  if ((threadIdx.x & 31) == 0 && local != 0) atomicMax(out, local);
 }
 
 __global__ void __launch_bounds__(256)
@@ -86,6 +105,20 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
   }
   count_launch();
   CUDA_CHECK(cudaGetLastError());
+  unsigned long long *d_max = nullptr, h_max = 0;
+  CUDA_CHECK(cudaMalloc(&d_max, sizeof h_max));
+  CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof h_max, rt.stream));
+  if (ix.d_offsets32 != nullptr)
+    max_bucket_kernel<uint32_t><<<blocks, 256, 0, rt.stream>>>(ix.d_offsets32, number_offsets - 1, d_max);
+  else
+    max_bucket_kernel<int64_t><<<blocks, 256, 0, rt.stream>>>(ix.d_offsets64, number_offsets - 1, d_max);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof h_max, cudaMemcpyDeviceToHost, rt.stream));
+  CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+  cudaFree(d_max);
+  ix.steps = 0;
+  while ((h_max >> ix.steps) != 0) ++ix.steps;
 }
 
 IndexData *index_of(ls_hs_basis const *basis) {
@@ -113,7 +146,11 @@ IndexData *create_index(uint64_t const *host_reps, int64_t count, int number_bit
     CUDA_CHECK(cudaMemcpyAsync(ix->d_reps, host_reps, sizeof(uint64_t) * (size_t)count,
                                cudaMemcpyHostToDevice, runtime().stream));
   }
-  if (count > 0 && number_bits > 0) build_bucket_table(*ix, prefix_bits);
+  if (count > 0 && number_bits > 0) {
+    build_bucket_table(*ix, prefix_bits);
+  } else {
+    while ((ix->number_states >> ix->steps) != 0) ++ix->steps;
+  }
   CUDA_CHECK(cudaStreamSynchronize(runtime().stream));
   return ix;
 }

@@ -125,7 +125,7 @@ constexpr int kMvThreads = 128;
 constexpr int kMvCap = kMvThreads * 32;  // queue entries per round
 constexpr int kMvRowsPerThread = 2;
 constexpr int kMvMaxRows = kMvThreads * kMvRowsPerThread;
-constexpr int kMvIdxPlanes = 10;  // bit-sliced path: |G| <= 1024
+constexpr int kMvIdxPlanes = 8;  // bit-sliced path: at most 256 distinct character values
 
 enum : int { kModeNone = 0, kModeInversion = 1, kModeGroup = 2, kModeGroupScalar = 3 };
 
@@ -134,7 +134,9 @@ struct MatvecArgs {
   IndexView ix;
   TermsView off, diag;
   int mode;
-  int identity_first;
+  int number_idx_planes;  // ceil(log2(number of distinct characters))
+  int number_chars;
+  double2 const *cvals;  // distinct character values; chars[cidx] in the kernel
   int complex_vectors;  // x, xs, y hold interleaved (re, im)
   int rows_per_tile;
   int spin_inversion;
@@ -153,11 +155,11 @@ struct MvSmem {
   int diag_m, diag_r, diag_s, diag_v;         // diagonal terms
   int chars;                                  // double2[|G|]
   int row_alpha, row_off, row_acc, row_diag;  // per-row arrays
-  int queue, meta, values_im, planes;
+  int queue, meta, cidx, values_im, planes;
   int total;
 };
 
-static MvSmem mv_layout(int T_off, int T_diag, int G, int np, bool complex_vectors, bool group) {
+static MvSmem mv_layout(int T_off, int T_diag, int number_chars, int np, bool complex_vectors, bool group) {
   MvSmem L{};
   int p = 0;
   auto take = [&](int bytes) {
@@ -174,13 +176,14 @@ static MvSmem mv_layout(int T_off, int T_diag, int G, int np, bool complex_vecto
   L.diag_r = take(8 * T_diag);
   L.diag_s = take(8 * T_diag);
   L.diag_v = take(16 * T_diag);
-  L.chars = take(16 * G);
+  L.chars = take(16 * number_chars);
   L.row_alpha = take(8 * kMvMaxRows);
   L.row_off = take(4 * (kMvMaxRows + 1));
   L.row_acc = take(16 * kMvMaxRows);
   L.row_diag = take(16 * kMvMaxRows);
   L.queue = take(8 * kMvCap);  // betas in, real parts of the contributions out
   L.meta = take(2 * kMvCap);
+  L.cidx = take(kMvCap);
   L.values_im = take(complex_vectors ? 8 * kMvCap : 0);
   L.planes = take(group ? 4 * np * kMvThreads : 0);
   L.total = p;
@@ -246,6 +249,7 @@ matvec_kernel(MatvecArgs const a, MvSmem const L) {
   uint64_t *queue = reinterpret_cast<uint64_t *>(smem + L.queue);
   double *values_re = reinterpret_cast<double *>(smem + L.queue);  // aliases the queue (same owner per slot)
   uint16_t *meta = reinterpret_cast<uint16_t *>(smem + L.meta);
+  uint8_t *cidx = reinterpret_cast<uint8_t *>(smem + L.cidx);
   double *values_im = reinterpret_cast<double *>(smem + L.values_im);
   uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.planes);
   __shared__ uint32_t s_total;
@@ -275,7 +279,7 @@ matvec_kernel(MatvecArgs const a, MvSmem const L) {
     d_s[t] = a.diag.s[t];
     d_v[t] = a.diag.v[t];
   }
-  for (int j = tid; j < G; j += kMvThreads) chars[j] = make_double2(a.g.re[j], a.g.im[j]);
+  for (int j = tid; j < a.number_chars; j += kMvThreads) chars[j] = a.cvals[j];
   __syncthreads();
 
   int64_t const rows_total = a.row_end - a.row_begin;
@@ -346,157 +350,191 @@ matvec_kernel(MatvecArgs const a, MvSmem const L) {
       }
       __syncthreads();
 
-      // ---- phase 3: canonicalise, rank, gather (thread per 32 entries) -----------
+      // ---- phase 3a: canonicalise (thread per 32 entries) ---------------------------
+      // In:  queue[slot] = beta.  Out: queue[slot] = representative, cidx[slot] =
+      // index (into chars[]) of the character of the minimising image.
       int const nwords = (nwin + 31) >> 5;
-      if (tid < nwords) {
-        uint32_t lo[32], hi[32], info[32];  // per lane: representative, element | flipped << 10
-        int const lanes = min(32, nwin - 32 * tid);
-        {
-          uint64_t const pad = queue[tid];  // lane 0 of this word is always valid
-#pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            uint64_t const b = (k < lanes) ? queue[k * kMvThreads + tid] : pad;
-            lo[k] = (uint32_t)b;
-            hi[k] = (uint32_t)(b >> 32);
-          }
-        }
+      // Whole warps enter (a warp-uniform condition) so that the group loop runs
+      // converged and its per-element table reads use the uniform datapath; threads
+      // past the last word carry lane 0 of word 0 and store nothing.
+      if ((tid & ~31) < nwords) {
+        int const lanes = max(0, min(32, nwin - 32 * tid));
         if (a.mode == kModeGroup) {
-          transpose32(lo);
-          if (NP > 32) transpose32(hi);
           uint32_t r[NP];
+          {
+            uint32_t lo[32], hi[32];
+            uint64_t const pad = queue[lanes > 0 ? tid : 0];  // lane 0 of a live word is always valid
 #pragma unroll
-          for (int i = 0; i < NP; ++i) {
-            r[i] = (i < 32) ? lo[i] : hi[i - 32];
-            planes[i * kMvThreads + tid] = r[i];
+            for (int k = 0; k < 32; ++k) {
+              uint64_t const b = (k < lanes) ? queue[k * kMvThreads + tid] : pad;
+              lo[k] = (uint32_t)b;
+              hi[k] = (uint32_t)(b >> 32);
+            }
+            transpose32(lo);
+            if (NP > 32) transpose32(hi);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+              r[i] = (i < 32) ? lo[i] : hi[(i < 32) ? 0 : i - 32];
+              planes[i * kMvThreads + tid] = r[i];
+            }
           }
-          __syncwarp();  // a thread only ever reads its own column
+          __syncwarp();  // all 32 lanes are here (see above); a thread only reads back its own column
           unsigned char const *column = reinterpret_cast<unsigned char const *>(planes + tid);
           uint32_t idx[kMvIdxPlanes];
 #pragma unroll
-          for (int p = 0; p < kMvIdxPlanes; ++p) idx[p] = 0;
-          uint32_t fl = 0, touched = 0;  // minimum is a flipped image / is not the input itself
-          // Element 0 is the identity when identity_first: its image is the
-          // initial minimum, nothing to compare.  Its flipped image still counts.
+          for (int p = 0; p < kMvIdxPlanes; ++p) idx[p] = 0;  // character 0 == 1+0i: the input itself (generator.cpp:105-106)
           int const nbits = a.g.number_bits;
+          int const nidx = a.number_idx_planes;
 #pragma unroll 1
           for (int j = 0; j < G; ++j) {
-            uint16_t const *po = c_plane_offset + j * NP;
-            uint32_t y[NP];
+            uint16_t const *po = c_plane_offset + j * (NP + kPlaneRowExtra);
+            // z = min(y, ~y) = y ^ top(y) when spin inversion is present (see basis_build.cu)
+            uint32_t top = 0;
+            if (INV) top = *reinterpret_cast<uint32_t const *>(column + po[NP]);
+            uint32_t z[NP];
+            uint32_t lt = 0;
 #pragma unroll
-            for (int i = 0; i < NP; ++i) y[i] = *reinterpret_cast<uint32_t const *>(column + po[i]);
-            if (!(a.identity_first && j == 0)) {
-              uint32_t lt = 0;
-#pragma unroll
-              for (int i = 0; i < NP; ++i) lt = ((y[i] ^ r[i]) & r[i]) | (~(y[i] ^ r[i]) & lt);
-#pragma unroll
-              for (int i = 0; i < NP; ++i) r[i] = (lt & y[i]) | (~lt & r[i]);
-#pragma unroll
-              for (int p = 0; p < kMvIdxPlanes; ++p) {
-                uint32_t const bit = 0u - (((unsigned)j >> p) & 1u);
-                idx[p] = (idx[p] & ~lt) | (lt & bit);
-              }
-              fl &= ~lt;
-              touched |= lt;
+            for (int i = 0; i < NP; ++i) {
+              z[i] = *reinterpret_cast<uint32_t const *>(column + po[i]);
+              if (INV) z[i] ^= (i < NP - 3 || i < nbits) ? top : 0u;  // padding planes stay zero
+              lt = ((z[i] ^ r[i]) & r[i]) | (~(z[i] ^ r[i]) & lt);   // one LOP3: z < r, most significant plane last
             }
-            if (INV) {
-              uint32_t lt = 0;
 #pragma unroll
-              for (int i = 0; i < NP; ++i) {
-                // planes >= number_bits are padding: zero in every image
-                uint32_t const yf = (i < NP - 3 || i < nbits) ? ~y[i] : y[i];
-                lt = ((yf ^ r[i]) & r[i]) | (~(yf ^ r[i]) & lt);
-              }
-#pragma unroll
-              for (int i = 0; i < NP; ++i) {
-                uint32_t const yf = (i < NP - 3 || i < nbits) ? ~y[i] : y[i];
-                r[i] = (lt & yf) | (~lt & r[i]);
-              }
-#pragma unroll
-              for (int p = 0; p < kMvIdxPlanes; ++p) {
-                uint32_t const bit = 0u - (((unsigned)j >> p) & 1u);
-                idx[p] = (idx[p] & ~lt) | (lt & bit);
-              }
-              fl |= lt;
-              touched |= lt;
+            for (int i = 0; i < NP; ++i) r[i] = (lt & z[i]) | (~lt & r[i]);
+            if (nidx > 0) {
+              unsigned const ci = po[NP + 1];
+              auto update = [&](int p) {
+                uint32_t const c = 0u - ((ci >> p) & 1u);          // chi_j
+                uint32_t const cf = 0u - ((ci >> (8 + p)) & 1u);   // inversion * chi_j
+                uint32_t const nb = INV ? ((top & cf) | (~top & c)) : c;
+                idx[p] = (lt & nb) | (~lt & idx[p]);
+              };
+              update(0);
+              if (nidx > 1) update(1);
+              if (nidx > 2) { update(2); update(3); }
+              if (nidx > 4) { update(4); update(5); update(6); update(7); }
             }
           }
           // back to one state per word
+          {
+            uint32_t lo[32], hi[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            lo[i] = (i < NP) ? r[i] : 0u;
-            hi[i] = (i + 32 < NP) ? r[(i + 32 < NP) ? i + 32 : 0] : 0u;
-            info[i] = (i < kMvIdxPlanes) ? idx[(i < kMvIdxPlanes) ? i : 0]
-                                         : (i == kMvIdxPlanes ? fl : (i == kMvIdxPlanes + 1 ? touched : 0u));
+            for (int i = 0; i < 32; ++i) {
+              lo[i] = (i < NP) ? r[(i < NP) ? i : 0] : 0u;
+              hi[i] = (i + 32 < NP) ? r[(i + 32 < NP) ? i + 32 : 0] : 0u;
+            }
+            transpose32(lo);
+            if (NP > 32) transpose32(hi);
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k < lanes) queue[k * kMvThreads + tid] = (NP > 32) ? (((uint64_t)hi[k] << 32) | lo[k]) : (uint64_t)lo[k];
           }
-          transpose32(lo);
-          if (NP > 32) transpose32(hi);
-          transpose32(info);
-        }
-
-        // rank + gather, one lane at a time (static register indexing)
+          {
+            uint32_t info[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          double vr = 0.0, vi = 0.0;
-          if (k < lanes) {
-            uint64_t rep = ((uint64_t)hi[k] << 32) | lo[k];
+            for (int i = 0; i < 32; ++i) info[i] = (i < kMvIdxPlanes) ? idx[(i < kMvIdxPlanes) ? i : 0] : 0u;
+            if (nidx > 0) transpose32(info);
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k < lanes) cidx[k * kMvThreads + tid] = (uint8_t)info[k];
+          }
+        } else {
+#pragma unroll 1
+          for (int k = 0; k < lanes; ++k) {
             int const slot = k * kMvThreads + tid;
-            unsigned const mt = meta[slot];
-            int const t = (int)(mt & 0x7fffu);
-            double2 w = t_w[t];
-            if (mt & 0x8000u) { w.x = -w.x; w.y = -w.y; }
-            double cr = 1.0, ci = 0.0;  // rep is the input itself: character 1 (generator.cpp:105-106)
-            if (a.mode == kModeGroup) {
-              int const e = (int)(info[k] & ((1u << kMvIdxPlanes) - 1u));
-              bool const flipped = ((info[k] >> kMvIdxPlanes) & 1u) != 0;
-              bool const touched = ((info[k] >> (kMvIdxPlanes + 1)) & 1u) != 0;
-              if (touched) {
-                double2 const c = chars[e];
-                cr = flipped ? (double)a.spin_inversion * c.x : c.x;
-                ci = flipped ? (double)a.spin_inversion * c.y : c.y;
-              }
-            } else if (a.mode == kModeGroupScalar) {
+            uint64_t rep = queue[slot];
+            unsigned c = 0;
+            if (a.mode == kModeGroupScalar) {
               int e, flipped;
               uint64_t r2;
               orbit_min_global(a.g, rep, r2, e, flipped);
               rep = r2;
               if (e >= 0) {
-                double2 const c = chars[e];
-                cr = flipped ? (double)a.spin_inversion * c.x : c.x;
-                ci = flipped ? (double)a.spin_inversion * c.y : c.y;
+                unsigned const ci = __ldg(a.g.cinfo + e);
+                c = flipped ? (ci >> 8) : (ci & 0xffu);
               }
             } else if (a.mode == kModeInversion) {
               // BatchedOperator.chpl:187-199
               uint64_t const inverted = rep ^ a.inversion_mask;
               if (inverted < rep) {
                 rep = inverted;
-                cr = (double)a.spin_inversion;
+                c = 1;
               }
             }
-            int64_t const j = state_index(a.ix, rep);
-            if (j >= 0) {
-              // conj(chi) * w * xs[j]
-              double const fr = cr * w.x + ci * w.y;
-              double const fi = cr * w.y - ci * w.x;
-              if (cplx) {
-                double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.xs) + j);
-                vr = fr * xv.x - fi * xv.y;
-                vi = fr * xv.y + fi * xv.x;
-              } else {
-                vr = fr * __ldg(a.xs + j);
+            queue[slot] = rep;
+            cidx[slot] = (uint8_t)c;
+          }
+        }
+      }
+      __syncthreads();
+
+      // ---- phase 3b: rank + gather, eight independent searches in flight per thread ----
+      if (tid < nwords) {
+        int const lanes = min(32, nwin - 32 * tid);
+        constexpr int B = 8;
+#pragma unroll 1
+        for (int k0 = 0; k0 < 32; k0 += B) {
+          uint64_t needle[B];
+          int64_t lo[B], n[B];
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            bool const live = k0 + u < lanes;
+            needle[u] = live ? queue[(k0 + u) * kMvThreads + tid] : 0;
+            index_window(a.ix, needle[u], live, lo[u], n[u]);
+          }
+          if (!a.ix.identity) {
+#pragma unroll 1
+            for (int s = 0; s < a.ix.steps; ++s) {
+#pragma unroll
+              for (int u = 0; u < B; ++u) {
+                int64_t const half = n[u] >> 1;
+                int64_t const mid = lo[u] + half;
+                uint64_t const v = n[u] > 0 ? __ldg(a.ix.reps + mid) : ~uint64_t(0);
+                bool const less = v < needle[u];
+                lo[u] = less ? mid + 1 : lo[u];
+                n[u] = less ? n[u] - half - 1 : half;
               }
-            } else if ((w.x != 0.0 || w.y != 0.0)) {
-              // Not in the basis: fine when its norm vanishes (the reference
-              // multiplies by n_beta = 0), an error otherwise
-              // (DistributedMatrixVector.chpl:127-135).
-              bool bad = true;
-              if (a.mode == kModeGroup || a.mode == kModeGroupScalar)
-                bad = stabiliser_sum_global(a.g, rep) > kNormThreshold;
-              if (bad) atomicOr(a.error_flag, 1);
             }
           }
-          int const slot = k * kMvThreads + tid;
-          values_re[slot] = vr;
-          if (cplx) values_im[slot] = vi;
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            int const slot = (k0 + u) * kMvThreads + tid;
+            bool const live = k0 + u < lanes;
+            int64_t j = -1;
+            if (live) {
+              if (a.ix.identity) j = (int64_t)needle[u];
+              else if (lo[u] < a.ix.number_states && __ldg(a.ix.reps + lo[u]) == needle[u]) j = lo[u];
+            }
+            double vr = 0.0, vi = 0.0;
+            if (live) {
+              unsigned const mt = meta[slot];
+              double2 w = t_w[mt & 0x7fffu];
+              if (mt & 0x8000u) { w.x = -w.x; w.y = -w.y; }
+              if (j >= 0) {
+                double2 const c = chars[cidx[slot]];
+                // conj(chi) * w * xs[j]
+                double const fr = c.x * w.x + c.y * w.y;
+                double const fi = c.x * w.y - c.y * w.x;
+                if (cplx) {
+                  double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.xs) + j);
+                  vr = fr * xv.x - fi * xv.y;
+                  vi = fr * xv.y + fi * xv.x;
+                } else {
+                  vr = fr * __ldg(a.xs + j);
+                }
+              } else if (w.x != 0.0 || w.y != 0.0) {
+                // Not in the basis: fine when its norm vanishes (the reference
+                // multiplies by n_beta = 0), an error otherwise
+                // (DistributedMatrixVector.chpl:127-135).
+                bool bad = true;
+                if (a.mode == kModeGroup || a.mode == kModeGroupScalar)
+                  bad = stabiliser_sum_global(a.g, needle[u]) > kNormThreshold;
+                if (bad) atomicOr(a.error_flag, 1);
+              }
+            }
+            values_re[slot] = vr;
+            if (cplx) values_im[slot] = vi;
+          }
         }
       }
       __syncthreads();
@@ -626,6 +664,7 @@ static int64_t count_elements(OperatorDev &od, IndexData const &ix, int64_t row_
 struct MatvecScratch {
   DeviceBuffer<double> x, xs, y;
   int *d_error = nullptr;
+  double2 *d_plain_chars = nullptr;  // {1, +1, -1}: character table of the unprojected / inversion-only modes
 };
 static MatvecScratch &mv_scratch() {
   static MatvecScratch s;
@@ -648,6 +687,9 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   if (sc.d_error == nullptr) {
     CUDA_CHECK(cudaMalloc(&sc.d_error, sizeof(int)));
     CUDA_CHECK(cudaMemsetAsync(sc.d_error, 0, sizeof(int), rt.stream));
+    double const plain[6] = {1.0, 0.0, 1.0, 0.0, -1.0, 0.0};
+    CUDA_CHECK(cudaMalloc(&sc.d_plain_chars, sizeof plain));
+    CUDA_CHECK(cudaMemcpy(sc.d_plain_chars, plain, sizeof plain, cudaMemcpyHostToDevice));
   }
 
   MatvecArgs a{};
@@ -664,6 +706,8 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   a.spin_inversion = basis->spin_inversion;
   a.inversion_mask = basis->number_sites >= 64 ? ~uint64_t(0) : ((uint64_t(1) << basis->number_sites) - 1);
   a.mode = kModeNone;
+  a.cvals = sc.d_plain_chars;
+  a.number_chars = 1;
   int np = 4;
   bool inv = false;
   bool bitsliced = false;
@@ -676,9 +720,12 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     inv = g.spin_inversion != 0;
     char const *env = getenv("LS_B200_MATVEC");
     bool const want_scalar = env != nullptr && strcmp(env, "scalar") == 0;
-    bitsliced = !want_scalar && g.number_masks <= (1 << kMvIdxPlanes) && upload_plane_offsets(g, np, kMvThreads);
+    LSB_CHECK(!g.cinfo.empty(), "symmetry sectors with more than 256 distinct character values are not supported");
+    a.cvals = g.d_cvals;
+    a.number_chars = (int)(g.cvals.size() / 2);
+    while ((1 << a.number_idx_planes) < a.number_chars) ++a.number_idx_planes;
+    bitsliced = !want_scalar && upload_plane_offsets(g, np, kMvThreads);
     a.mode = bitsliced ? kModeGroup : kModeGroupScalar;
-    a.identity_first = identity_is_first(g) ? 1 : 0;
     // pre-scaled copy of x
     size_t const words = (size_t)dim * (complex_vectors ? 2 : 1);
     double *xs = sc.xs.reserve(words);
@@ -689,6 +736,9 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     a.xs = xs;
   } else if (info.has_spin_inversion) {
     a.mode = kModeInversion;
+    // cidx 1 = the spin-inversion character: entry 1 of the plain table is +1, entry 2 is -1
+    a.cvals = sc.d_plain_chars + (basis->spin_inversion < 0 ? 1 : 0);
+    a.number_chars = 2;
   }
 
   // tile size from the average number of matrix elements per row
@@ -703,7 +753,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   a.rows_per_tile = rows;
 
   bool const group_planes = a.mode == kModeGroup;
-  MvSmem const L = mv_layout(a.off.number_terms, a.diag.number_terms, a.g.number_masks, np, complex_vectors, group_planes);
+  MvSmem const L = mv_layout(a.off.number_terms, a.diag.number_terms, a.number_chars, np, complex_vectors, group_planes);
   LSB_CHECK((size_t)L.total <= rt.smem_optin, "operator / symmetry tables do not fit in shared memory");
   LSB_CHECK(a.off.number_terms < 0x8000, "too many off-diagonal terms");
   MatvecKernel kernel = group_planes ? pick_matvec_kernel(np, inv) : matvec_kernel<4, false>;

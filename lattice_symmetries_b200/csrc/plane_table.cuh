@@ -23,20 +23,31 @@ constexpr int kMaxPermTable = 24576;  // uint16 entries (48 KB of constant memor
 static __constant__ uint16_t c_plane_offset[kMaxPermTable];
 static uint64_t g_plane_table_owner = 0;  // GroupData::id, NP and block size currently resident
 
+// Row j of the table (kPlaneRowExtra + np entries):
+//   [0, np)   byte offset of the source plane of output plane i
+//   [np]      byte offset of the source plane of the TOP live bit (number_bits - 1):
+//             the spin-flipped image ~y is smaller than y iff that bit of y is set
+//   [np + 1]  character indices of element j (GroupData::cinfo)
 // Planes are padded to a multiple of four (np >= number_bits); padding planes
 // map onto themselves.  Returns false when the table does not fit.
+constexpr int kPlaneRowExtra = 2;
 static inline bool upload_plane_offsets(GroupData const &g, int np, int threads_per_block) {
-  size_t const entries = (size_t)g.number_masks * (size_t)np;
+  size_t const stride = (size_t)np + kPlaneRowExtra;
+  size_t const entries = (size_t)g.number_masks * stride;
   if (entries > (size_t)kMaxPermTable) return false;
   if ((size_t)(np - 1) * (size_t)threads_per_block * 4 > 0xffffu) return false;
   uint64_t const tag = (g.id << 20) | ((uint64_t)np << 12) | (uint64_t)threads_per_block;
   if (g_plane_table_owner == tag) return true;
   std::vector<uint16_t> table(entries);
-  for (int j = 0; j < g.number_masks; ++j)
+  for (int j = 0; j < g.number_masks; ++j) {
     for (int i = 0; i < np; ++i) {
       int const src = i < g.number_bits ? g.perm[(size_t)j * g.number_bits + i] : i;
-      table[(size_t)j * np + i] = (uint16_t)(src * threads_per_block * 4);
+      table[(size_t)j * stride + i] = (uint16_t)(src * threads_per_block * 4);
     }
+    int const top = g.number_bits > 0 ? g.perm[(size_t)j * g.number_bits + (g.number_bits - 1)] : 0;
+    table[(size_t)j * stride + np] = (uint16_t)(top * threads_per_block * 4);
+    table[(size_t)j * stride + np + 1] = g.cinfo.empty() ? (uint16_t)0 : g.cinfo[(size_t)j];
+  }
   CUDA_CHECK(cudaMemcpyToSymbolAsync(c_plane_offset, table.data(), entries * sizeof(uint16_t), 0,
                                      cudaMemcpyHostToDevice, runtime().stream));
   CUDA_CHECK(cudaStreamSynchronize(runtime().stream));  // table is a stack temporary

@@ -28,6 +28,10 @@ struct GroupData {
   std::vector<uint64_t> masks, shifts;
   std::vector<double> re, im;
   std::vector<uint8_t> perm;  // [|G|][number_bits], recovered from the networks
+  std::vector<double> cvals;      // distinct character values, interleaved (re, im); cvals[0] = 1+0i
+  std::vector<uint16_t> cinfo;    // per element: index of chi_j | index of (inversion * chi_j) << 8
+  double2 *d_cvals = nullptr;
+  uint16_t *d_cinfo = nullptr;
   uint64_t *d_masks = nullptr;
   double *d_re = nullptr, *d_im = nullptr;
   uint8_t *d_perm = nullptr;
@@ -45,6 +49,7 @@ struct IndexData {
   int number_bits = 0;
   int prefix_bits = 0;
   int shift = 0;
+  int steps = 0;  // bit_length(largest bucket)
   bool identity = false;
   uint64_t *d_reps = nullptr;
   bool owns_d_reps = true;

@@ -20,6 +20,11 @@ struct GroupView {
   double const *re;       // [|G|]
   double const *im;       // [|G|]
   uint8_t const *perm;    // [|G|][number_bits]: image bit i = source bit perm[i]
+  // Distinct character values (value 0 is exactly 1+0i) and, per element, the
+  // index of chi_j (low byte) and of spin_inversion * chi_j (high byte).
+  double2 const *cvals;   // [number_chars]
+  uint16_t const *cinfo;  // [|G|]
+  int number_chars;       // 0 when there are more than 256 distinct values
   unsigned shifts[kMaxDepth];
 };
 
@@ -33,6 +38,7 @@ struct IndexView {
   int shift;                  // number_bits - prefix_bits
   int identity;               // state_index_is_identity: index == state
   uint64_t number_buckets;    // 2^prefix
+  int steps;                  // bit_length(largest bucket): trip count of the branchless search
 };
 
 // Operator terms, structure-of-arrays on the device
@@ -78,6 +84,31 @@ __device__ __forceinline__ int64_t state_index(IndexView const &ix, uint64_t nee
     if (v < needle) lo = mid + 1; else hi = mid;
   }
   return (lo < ix.number_states && __ldg(ix.reps + lo) == needle) ? lo : (int64_t)-1;
+}
+
+// Search window of `needle`: [lo, lo + n) is its prefix bucket (empty when the
+// needle cannot be in the basis or `live` is false).  Followed by ix.steps
+// rounds of  half = n >> 1; mid = lo + half; reps[mid] < needle ? (lo = mid + 1,
+// n -= half + 1) : (n = half)  -- the fixed-length branchless lower bound of
+// kernels/indexing.c:196-215 -- after which reps[lo] == needle decides.
+__device__ __forceinline__ void index_window(IndexView const &ix, uint64_t needle, bool live, int64_t &lo, int64_t &n) {
+  lo = 0;
+  n = 0;
+  if (!live || ix.identity) return;
+  uint64_t const p = needle >> ix.shift;
+  if (ix.offsets32 != nullptr) {
+    if (p < ix.number_buckets) {
+      lo = (int64_t)__ldg(ix.offsets32 + p);
+      n = (int64_t)__ldg(ix.offsets32 + p + 1) - lo;
+    }
+  } else if (ix.offsets64 != nullptr) {
+    if (p < ix.number_buckets) {
+      lo = __ldg(ix.offsets64 + p);
+      n = __ldg(ix.offsets64 + p + 1) - lo;
+    }
+  } else {
+    n = ix.number_states;
+  }
 }
 
 // Scalar orbit walk: apply every group element's Benes network to x

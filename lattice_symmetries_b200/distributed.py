@@ -166,11 +166,14 @@ class ShardedOperator:
     computes this rank's rows into its slot of ``y_full`` and all-gathers in
     place, so the output can be fed straight back in (Lanczos)."""
 
-    def __init__(self, operator, group=None):
+    device = "cuda"
+
+    def __init__(self, operator, group=None, dim: Optional[int] = None):
         import torch.distributed as dist
         self.op = operator
         self.group = group
-        dim = operator.basis.number_states
+        if dim is None:
+            dim = operator.basis.number_states
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         lo, hi, chunk = row_bounds(dim, world, rank)
@@ -179,7 +182,7 @@ class ShardedOperator:
     def empty_vector(self, dtype=None):
         import torch
         L = self.layout
-        return torch.zeros(L.world * L.chunk, dtype=dtype or torch.float64, device="cuda")
+        return torch.zeros(L.world * L.chunk, dtype=dtype or torch.float64, device=self.device)
 
     def local_rows(self, v):
         L = self.layout
@@ -191,14 +194,18 @@ class ShardedOperator:
         L = self.layout
         cplx = x_full.dtype == torch.complex128
         if L.row_end > L.row_begin:
-            y_ptr = y_full.data_ptr() + L.row_begin * y_full.element_size()
-            self.op.matvec_device(x_full.data_ptr(), y_ptr, L.row_begin, L.row_end, complex_vectors=cplx)
+            self._local_rows(x_full, y_full, L.row_begin, L.row_end, cplx)
         if gather and L.world > 1:
             mine = y_full[L.rank * L.chunk:(L.rank + 1) * L.chunk]
             if cplx:
                 dist.all_gather_into_tensor(torch.view_as_real(y_full), torch.view_as_real(mine), group=self.group)
             else:
                 dist.all_gather_into_tensor(y_full, mine, group=self.group)
+
+    def _local_rows(self, x_full, y_full, row_begin: int, row_end: int, cplx: bool) -> None:
+        """y_full[row_begin:row_end] = (H x)[row_begin:row_end] on this rank's GPU."""
+        y_ptr = y_full.data_ptr() + row_begin * y_full.element_size()
+        self.op.matvec_device(x_full.data_ptr(), y_ptr, row_begin, row_end, complex_vectors=cplx)
 
     def dot(self, a_full, b_full):
         """Global <a, b> from the local rows (one all-reduce of a scalar)."""
