@@ -135,6 +135,7 @@ struct MatvecArgs {
   TermsView off, diag;
   int mode;
   int number_idx_planes;  // ceil(log2(number of distinct characters))
+  int debug_skip;         // LS_B200_MV_SKIP (profiling only): 1 = no orbit walk, 2 = no search/gather
   int number_chars;
   double2 const *cvals;  // distinct character values; chars[cidx] in the kernel
   int complex_vectors;  // x, xs, y hold interleaved (re, im)
@@ -386,7 +387,7 @@ matvec_kernel(MatvecArgs const a, MvSmem const L) {
           int const nbits = a.g.number_bits;
           int const nidx = a.number_idx_planes;
 #pragma unroll 1
-          for (int j = 0; j < G; ++j) {
+          for (int j = 0; j < ((a.debug_skip & 1) ? 0 : G); ++j) {
             uint16_t const *po = c_plane_offset + j * (NP + kPlaneRowExtra);
             // z = min(y, ~y) = y ^ top(y) when spin inversion is present (see basis_build.cu)
             uint32_t top = 0;
@@ -469,7 +470,7 @@ matvec_kernel(MatvecArgs const a, MvSmem const L) {
       __syncthreads();
 
       // ---- phase 3b: rank + gather, eight independent searches in flight per thread ----
-      if (tid < nwords) {
+      if (tid < nwords && !(a.debug_skip & 2)) {
         int const lanes = min(32, nwin - 32 * tid);
         constexpr int B = 8;
 #pragma unroll 1
@@ -706,6 +707,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   a.spin_inversion = basis->spin_inversion;
   a.inversion_mask = basis->number_sites >= 64 ? ~uint64_t(0) : ((uint64_t(1) << basis->number_sites) - 1);
   a.mode = kModeNone;
+  if (char const *dbg = getenv("LS_B200_MV_SKIP")) a.debug_skip = atoi(dbg);
   a.cvals = sc.d_plain_chars;
   a.number_chars = 1;
   int np = 4;

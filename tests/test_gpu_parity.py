@@ -193,6 +193,17 @@ def test_state_info_empty_and_strided(oracle, built):
     assert b == int(reps[3]) and c == 1.0 + 0j and nrm > 0
 
 
+def _sanitise_index(idx, dim):
+    """kernels/indexing.c:196-215 reads representatives[dim] (one past the end) for needles
+    above the largest representative of the last bucket and reports index ``dim`` when the
+    stray word happens to equal the needle (reproduced with the reference's own compiled
+    source: reps followed in memory by 593 -> index(593) == 13 == dim).  That is undefined
+    behaviour, not a contract; the only valid answer for such a needle is -1."""
+    idx = idx.copy()
+    idx[idx >= dim] = -1
+    return idx
+
+
 # ---- (a-4) state_index ----------------------------------------------------------------------
 @pytest.mark.parametrize("name", ALL)
 def test_state_index(oracle, built, name):
@@ -203,11 +214,12 @@ def test_state_index(oracle, built, name):
     junk = rng.integers(0, 2 ** min(63, ob.number_bits), size=1000, dtype=np.uint64)
     needles = np.concatenate([reps[:1], reps[-1:], present, absent, junk])
     got = basis.index(needles)
-    want = index(needles)
+    want = _sanitise_index(index(needles), reps.shape[0])
     assert np.array_equal(got, want)
     assert np.array_equal(basis.index(reps), np.arange(reps.shape[0]))
     if oracle.ref_available():
-        assert np.array_equal(got, oracle.ref_state_index(reps, ob.number_bits, 22, needles))
+        ref = _sanitise_index(oracle.ref_state_index(reps, ob.number_bits, 22, needles), reps.shape[0])
+        assert np.array_equal(got, ref)
 
 
 # ---- (a-5, a-6) rows of H ---------------------------------------------------------------------

@@ -1,0 +1,24 @@
+"""Small driver for ncu captures: build one workload, run a few matvecs.
+    ncu ... python tools/profile_workload.py kagome36 2
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import bench  # noqa: E402
+from lattice_symmetries_b200 import _lib  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "kagome36"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+model, desc = bench.make_model(name)
+basis = model.basis()
+basis.build()
+op = model.operator(basis)
+dim = basis.number_states
+x = _lib.DeviceArray.from_numpy(np.random.default_rng(0).standard_normal(dim))
+y = _lib.DeviceArray(dim, np.float64)
+for _ in range(reps):
+    op.matvec_device(x.ptr, y.ptr, sync=True)
+print(name, "dim", dim, "matvec ms", _lib.lib.ls_b200_last_kernel_ms(b"matvec"), "build ms", _lib.lib.ls_b200_last_kernel_ms(b"build"))
