@@ -54,6 +54,9 @@ struct Runtime {
   std::atomic<uint64_t> launches{0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_matvec_ms = 0, last_build_ms = 0;
+  // LS_B200_PROFILE=1: summed device time / launch count of the two matvec kernels in the last matvec
+  double last_orbit_ms = 0, last_gather_ms = 0;
+  int last_orbit_launches = 0, last_gather_launches = 0;
 
   void ensure();  // throws CudaFailure when no usable device
 };

@@ -12,6 +12,9 @@ IndexView IndexData::view() const {
   v.number_states = number_states;
   v.offsets32 = d_offsets32;
   v.offsets64 = d_offsets64;
+  v.lows16 = d_lows16;
+  v.lows32 = d_lows32;
+  v.low_mask = shift >= 64 ? ~uint64_t(0) : ((uint64_t(1) << shift) - 1);
   v.shift = shift;
   v.identity = identity ? 1 : 0;
   v.number_buckets = uint64_t(1) << prefix_bits;
@@ -23,6 +26,8 @@ IndexData::~IndexData() {
   if (owns_d_reps) cudaFree(d_reps);
   cudaFree(d_offsets32);
   cudaFree(d_offsets64);
+  cudaFree(d_lows16);
+  cudaFree(d_lows32);
   cudaFree(d_norms);
   magic = 0;
 }
@@ -46,6 +51,13 @@ bucket_offsets_kernel(uint64_t const *__restrict__ reps, int64_t n, int shift, i
     }
     offsets[p] = (T)lo;
   }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+low_bits_kernel(uint64_t const *__restrict__ reps, int64_t n, uint64_t mask, T *__restrict__ lows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    lows[i] = (T)(reps[i] & mask);
 }
 
 // Largest bucket of the table (sets the trip count of the branchless search).
@@ -74,16 +86,18 @@ state_index_kernel(IndexView ix, int64_t n, uint64_t const *__restrict__ needles
     out[i] = state_index(ix, needles[i]);
 }
 
-// Adaptive prefix width: about two representatives per bucket, table capped so
-// that it stays L2-friendly.  The reference's caller-chosen width (22 or 26,
-// kernels/reference.c:188, chapel/src/CommonParameters.chpl:7) only affects
-// speed, never results, so we are free to choose.
+// Adaptive prefix width: about eight representatives per bucket (the bucket
+// table then is ~1/16 of the low-bits array and both stay L2-resident), widened
+// when that lets the low bits fit 16-bit keys.  The reference's caller-chosen
+// width (22 or 26, kernels/reference.c:188, chapel/src/CommonParameters.chpl:7)
+// only affects speed, never results, so we are free to choose.
 static int choose_prefix_bits(int64_t n, int number_bits, int requested) {
+  (void)requested;
   int want = 1;
-  while (want < 40 && (int64_t(1) << want) < n / 2) ++want;
-  int const cap = 27;
+  while (want < 40 && (int64_t(1) << want) < n / 8) ++want;
+  int const cap = 28;
   int p = std::min(want, cap);
-  p = std::max(p, std::min(requested, 16));
+  if (number_bits - p > 16 && number_bits - 16 <= std::min(cap, want + 3)) p = number_bits - 16;
   p = std::min(p, number_bits);
   return std::max(p, 0);
 }
@@ -105,6 +119,17 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
   }
   count_launch();
   CUDA_CHECK(cudaGetLastError());
+  uint64_t const mask = ix.shift >= 64 ? ~uint64_t(0) : ((uint64_t(1) << ix.shift) - 1);
+  unsigned const lblocks = (unsigned)std::min<int64_t>((ix.number_states + 255) / 256, (int64_t)rt.sm_count * 16);
+  if (ix.shift <= 16) {
+    CUDA_CHECK(cudaMalloc(&ix.d_lows16, sizeof(uint16_t) * (size_t)ix.number_states));
+    low_bits_kernel<uint16_t><<<lblocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, mask, ix.d_lows16);
+    count_launch();
+  } else if (ix.shift <= 32) {
+    CUDA_CHECK(cudaMalloc(&ix.d_lows32, sizeof(uint32_t) * (size_t)ix.number_states));
+    low_bits_kernel<uint32_t><<<lblocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, mask, ix.d_lows32);
+    count_launch();
+  }
   unsigned long long *d_max = nullptr, h_max = 0;
   CUDA_CHECK(cudaMalloc(&d_max, sizeof h_max));
   CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof h_max, rt.stream));

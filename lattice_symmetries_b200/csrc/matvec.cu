@@ -3,8 +3,8 @@
 // Replaces the Chapel driver chapel/src/DistributedMatrixVector.chpl
 // (localDiagonal :49-71, localProcess :91-143, Producer.run :581-671,
 // localMatrixVector :1045-1058, export :1090-1105), the batched operator
-// chapel/src/BatchedOperator.chpl (:139-282 and the exports :298-357) and the
-// scalar kernels kernels/reference.c:67-134.
+// chapel/src/BatchedOperator.chpl (:139-282) and the scalar kernels
+// kernels/reference.c:67-134.
 //
 // Design (not a port).  The reference pushes: for every column i it emits
 // (beta, c) pairs, canonicalises beta, ranks it and does y[j] += c with atomic
@@ -23,19 +23,24 @@
 // reference's state_info(beta).norm equals the stored norm of its
 // representative) and folded into a pre-scaled copy xs[j] = n_j x[j].
 //
-// One fused kernel per matvec.  A block owns a tile of consecutive rows and
-//   1. (thread per row) tests every adjoint term against alpha_i, evaluates
-//      the diagonal and counts the matches; a block scan turns the counts
-//      into positions in a shared-memory queue of (beta, term, sign);
-//   2. (thread per 32 queue entries) transposes its 32 betas into bit planes
-//      (bitslice.cuh) and walks the whole group: the image under element g is
-//      a renaming of planes (plane_table.cuh), the running minimum costs two
-//      LOP3 per plane per element for 32 states, and the index of the
-//      minimising element is tracked in ten more planes;
-//   3. the same thread transposes back, ranks its 32 representatives
-//      (views.cuh state_index) and gathers conj(chi) w sign xs[j];
-//   4. (thread per row) sums the row's segment of the queue in term order.
-#include <cub/block/block_scan.cuh>
+// The rows are processed in chunks whose intermediates stay L2-resident; per
+// chunk three kernels run back to back, each at its own best occupancy:
+//   row_count_kernel   thread per row: number of matching adjoint terms; a
+//                      device scan turns the counts into CSR-style offsets;
+//   orbit_kernel       thread per 32 matrix elements (integer-issue bound):
+//                      regenerates its 32 betas from the offsets, transposes
+//                      them into bit planes (bitslice.cuh) and walks the whole
+//                      group -- the image under g is a renaming of planes
+//                      (plane_table.cuh), the running minimum costs three LOP3
+//                      per plane per element for 32 states -- and writes the
+//                      representative + the index of the minimising character;
+//   gather_kernel      thread per row (latency / HBM bound): ranks each
+//                      representative (bucket table + branchless search over
+//                      the sorted representatives, several searches in flight),
+//                      gathers conj(chi) w sign xs[j], sums in term order and
+//                      writes y[i] once.
+// Unprojected bases (and spin-inversion-only ones) skip the first two kernels.
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <memory>
@@ -120,15 +125,15 @@ OperatorDev &operator_dev(ls_hs_operator const *op) {
   return d;
 }
 
-// ---- kernel ----------------------------------------------------------------------
-constexpr int kMvThreads = 128;
-constexpr int kMvCap = kMvThreads * 32;  // queue entries per round
-constexpr int kMvRowsPerThread = 2;
-constexpr int kMvMaxRows = kMvThreads * kMvRowsPerThread;
-constexpr int kMvIdxPlanes = 8;  // bit-sliced path: at most 256 distinct character values
+// ---- kernels ---------------------------------------------------------------------
+constexpr int kOrbitThreads = 128;   // one thread = one word of 32 matrix elements
+constexpr int kGatherThreads = 128;  // one thread = one row
+constexpr int kMvIdxPlanes = 8;      // bit-sliced path: at most 256 distinct character values
+constexpr int kGatherBatch = 4;      // independent searches in flight per thread
 
 enum : int { kModeNone = 0, kModeInversion = 1, kModeGroup = 2, kModeGroupScalar = 3 };
 
+// Everything one chunk of rows needs; passed by value.
 struct MatvecArgs {
   GroupView g;
   IndexView ix;
@@ -137,67 +142,28 @@ struct MatvecArgs {
   int number_idx_planes;  // ceil(log2(number of distinct characters))
   int debug_skip;         // LS_B200_MV_SKIP (profiling only): 1 = no orbit walk, 2 = no search/gather
   int number_chars;
-  double2 const *cvals;  // distinct character values; chars[cidx] in the kernel
-  int complex_vectors;  // x, xs, y hold interleaved (re, im)
-  int rows_per_tile;
+  double2 const *cvals;  // distinct character values; chars[cidx] in the kernels
+  int complex_vectors;   // x, xs, y hold interleaved (re, im)
   int spin_inversion;
   uint64_t inversion_mask;
-  int64_t row_begin, row_end;
-  double const *norms;  // n_i of the representatives; nullptr when all 1
-  double const *x;      // caller's vector (diagonal part)
-  double const *xs;     // n_j x[j] (== x when norms is nullptr)
-  double *y;            // rows [row_begin, row_end), i.e. y[0] is row_begin
+  int64_t row_begin;     // first row of the CALL (y[0] is this row)
+  int64_t chunk_begin;   // first row of this chunk
+  int chunk_rows;
+  double const *norms;   // n_i of the representatives; nullptr when all 1
+  double const *x;       // caller's vector (diagonal part)
+  double const *xs;      // n_j x[j] (== x when norms is nullptr)
+  double *y;
   int *error_flag;
+  // chunk intermediates
+  uint32_t *counts;      // [chunk_rows + 1] matches per row (last = 0)
+  uint32_t *offsets;     // [chunk_rows + 1] exclusive scan of counts
+  uint64_t *q_rep;       // [capacity] representative of every matrix element, CSR order
+  uint8_t *q_cidx;       // [capacity] index of the minimising character
 };
-
-struct MvSmem {
-  // all offsets in bytes from the dynamic shared memory base
-  int off_m, off_l, off_x, off_s, off_w;      // off-diagonal terms
-  int diag_m, diag_r, diag_s, diag_v;         // diagonal terms
-  int chars;                                  // double2[|G|]
-  int row_alpha, row_off, row_acc, row_diag;  // per-row arrays
-  int queue, meta, cidx, values_im, planes;
-  int total;
-};
-
-static MvSmem mv_layout(int T_off, int T_diag, int number_chars, int np, bool complex_vectors, bool group) {
-  MvSmem L{};
-  int p = 0;
-  auto take = [&](int bytes) {
-    int const at = p;
-    p += (bytes + 15) & ~15;
-    return at;
-  };
-  L.off_m = take(8 * T_off);
-  L.off_l = take(8 * T_off);
-  L.off_x = take(8 * T_off);
-  L.off_s = take(8 * T_off);
-  L.off_w = take(16 * T_off);
-  L.diag_m = take(8 * T_diag);
-  L.diag_r = take(8 * T_diag);
-  L.diag_s = take(8 * T_diag);
-  L.diag_v = take(16 * T_diag);
-  L.chars = take(16 * number_chars);
-  L.row_alpha = take(8 * kMvMaxRows);
-  L.row_off = take(4 * (kMvMaxRows + 1));
-  L.row_acc = take(16 * kMvMaxRows);
-  L.row_diag = take(16 * kMvMaxRows);
-  L.queue = take(8 * kMvCap);  // betas in, real parts of the contributions out
-  L.meta = take(2 * kMvCap);
-  L.cidx = take(kMvCap);
-  L.values_im = take(complex_vectors ? 8 * kMvCap : 0);
-  L.planes = take(group ? 4 * np * kMvThreads : 0);
-  L.total = p;
-  return L;
-}
-
-// Queue slot of entry q: lane k = q % 32 of word w = q / 32 lives at k * 128 + w,
-// so that the thread owning word w touches bank w % 32 only (conflict-free).
-__device__ __forceinline__ int queue_slot(int q) { return (q & 31) * kMvThreads + (q >> 5); }
 
 // Stabiliser character sum of x read straight from the global tables; used on
 // the (rare) path that decides whether a missing index is an error.
-__device__ __noinline__ double stabiliser_sum_global(GroupView const &g, uint64_t x) {
+__device__ __noinline__ double stabiliser_sum_global(GroupView g, uint64_t x) {
   double acc = 0.0;
   for (int j = 0; j < g.number_masks; ++j) {
     uint64_t y = x;
@@ -211,7 +177,7 @@ __device__ __noinline__ double stabiliser_sum_global(GroupView const &g, uint64_
 
 // Scalar orbit minimum from the global tables (kModeGroupScalar: groups that
 // do not fit the bit-sliced path, and A/B validation via LS_B200_MATVEC=scalar).
-__device__ __noinline__ void orbit_min_global(GroupView const &g, uint64_t x, uint64_t &rep, int &element, int &flipped) {
+__device__ __noinline__ void orbit_min_global(GroupView g, uint64_t x, uint64_t &rep, int &element, int &flipped) {
   uint64_t r = x;
   int best = -1, fl = 0;
   for (int j = 0; j < g.number_masks; ++j) {
@@ -229,357 +195,356 @@ __device__ __noinline__ void orbit_min_global(GroupView const &g, uint64_t x, ui
   flipped = fl;
 }
 
-template <int NP, bool INV>
-__global__ void __launch_bounds__(kMvThreads)
-matvec_kernel(MatvecArgs const a, MvSmem const L) {
+// Shared-memory copy of the adjoint off-diagonal terms: match on l, weight
+// w = v (-1)^{|x&s|}.
+struct AdjointTerms {
+  uint64_t *m, *l, *x, *s;
+  double2 *w;
+  int T;
+  static __host__ __device__ size_t bytes(int T, bool with_weights) { return (size_t)T * (with_weights ? 48 : 24); }
+  __device__ void stage(unsigned char *base, TermsView const &off, bool with_weights) {
+    T = off.number_terms;
+    m = reinterpret_cast<uint64_t *>(base);
+    l = m + T;
+    x = l + T;
+    s = x + T;
+    w = reinterpret_cast<double2 *>(s + T);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      uint64_t const xt = off.x[t];
+      m[t] = off.m[t];
+      l[t] = off.l[t];
+      x[t] = xt;
+      if (with_weights) {
+        uint64_t const st = off.s[t];
+        double2 v = off.v[t];
+        if (__popcll(xt & st) & 1) { v.x = -v.x; v.y = -v.y; }
+        s[t] = st;
+        w[t] = v;
+      }
+    }
+  }
+};
+
+// counts[r] = number of adjoint terms matching row chunk_begin + r; counts[chunk_rows] = 0.
+__global__ void __launch_bounds__(256)
+row_count_kernel(MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint64_t *t_m = reinterpret_cast<uint64_t *>(smem + L.off_m);
-  uint64_t *t_l = reinterpret_cast<uint64_t *>(smem + L.off_l);
-  uint64_t *t_x = reinterpret_cast<uint64_t *>(smem + L.off_x);
-  uint64_t *t_s = reinterpret_cast<uint64_t *>(smem + L.off_s);
-  double2 *t_w = reinterpret_cast<double2 *>(smem + L.off_w);
-  uint64_t *d_m = reinterpret_cast<uint64_t *>(smem + L.diag_m);
-  uint64_t *d_r = reinterpret_cast<uint64_t *>(smem + L.diag_r);
-  uint64_t *d_s = reinterpret_cast<uint64_t *>(smem + L.diag_s);
-  double2 *d_v = reinterpret_cast<double2 *>(smem + L.diag_v);
-  double2 *chars = reinterpret_cast<double2 *>(smem + L.chars);
-  uint64_t *row_alpha = reinterpret_cast<uint64_t *>(smem + L.row_alpha);
-  uint32_t *row_off = reinterpret_cast<uint32_t *>(smem + L.row_off);
-  double2 *row_acc = reinterpret_cast<double2 *>(smem + L.row_acc);
-  double2 *row_diag = reinterpret_cast<double2 *>(smem + L.row_diag);
-  uint64_t *queue = reinterpret_cast<uint64_t *>(smem + L.queue);
-  double *values_re = reinterpret_cast<double *>(smem + L.queue);  // aliases the queue (same owner per slot)
-  uint16_t *meta = reinterpret_cast<uint16_t *>(smem + L.meta);
-  uint8_t *cidx = reinterpret_cast<uint8_t *>(smem + L.cidx);
-  double *values_im = reinterpret_cast<double *>(smem + L.values_im);
-  uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.planes);
-  __shared__ uint32_t s_total;
-  using BlockScan = cub::BlockScan<uint32_t, kMvThreads>;
-  __shared__ typename BlockScan::TempStorage scan_storage;
+  AdjointTerms terms;
+  terms.stage(smem, a.off, false);
+  __syncthreads();
+  int const r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > a.chunk_rows) return;
+  uint32_t c = 0;
+  if (r < a.chunk_rows) {
+    uint64_t const alpha = __ldg(a.ix.reps + a.chunk_begin + r);
+    for (int t = 0; t < terms.T; ++t) c += ((alpha & terms.m[t]) == terms.l[t]) ? 1u : 0u;
+  }
+  a.counts[r] = c;
+}
+
+// One thread canonicalises 32 consecutive matrix elements of the chunk; a warp
+// owns 1024 consecutive elements and a private 8 KB slab of shared memory that
+// first stages its betas and then holds its bit planes.
+constexpr int kWarpSlabBytes = 32 * 32 * 8;
+template <int NP, bool INV>
+__global__ void __launch_bounds__(kOrbitThreads)
+orbit_kernel(MatvecArgs const a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  AdjointTerms terms;
+  terms.stage(smem, a.off, false);
+  size_t const terms_bytes = (AdjointTerms::bytes(a.off.number_terms, false) + 15) & ~size_t(15);
+  __syncthreads();
 
   int const tid = threadIdx.x;
-  int const T = a.off.number_terms;
-  int const TD = a.diag.number_terms;
-  int const G = a.g.number_masks;
-  bool const cplx = a.complex_vectors != 0;
+  int const lane = tid & 31;
+  unsigned char *slab = smem + terms_bytes + (size_t)(tid >> 5) * kWarpSlabBytes;
+  uint64_t *stage = reinterpret_cast<uint64_t *>(slab);   // [k][lane]: element 32 * lane + k of the warp
+  uint32_t *planes = reinterpret_cast<uint32_t *>(slab);  // [plane][lane], after the betas have been read
+  uint32_t const total = a.offsets[a.chunk_rows];
+  uint64_t const warp_q0 = ((uint64_t)blockIdx.x * (kOrbitThreads / 32) + (tid >> 5)) * 1024;
+  if (warp_q0 >= total) return;  // whole warps leave: everything below runs converged
+  uint64_t const warp_q1 = min((uint64_t)total, warp_q0 + 1024);
+  uint64_t const q0 = warp_q0 + 32 * (uint64_t)lane;
+  int const lanes = q0 < total ? (int)min((uint64_t)32, total - q0) : 0;
 
-  // Stage the tables: adjoint off-diagonal terms (match on l, w = v (-1)^{|x&s|}).
-  for (int t = tid; t < T; t += kMvThreads) {
-    uint64_t const x = a.off.x[t], s = a.off.s[t];
-    double2 v = a.off.v[t];
-    if (__popcll(x & s) & 1) { v.x = -v.x; v.y = -v.y; }
-    t_m[t] = a.off.m[t];
-    t_l[t] = a.off.l[t];
-    t_x[t] = x;
-    t_s[t] = s;
-    t_w[t] = v;
+  // ---- regenerate the warp's betas: lane = row, CSR positions from the offsets -------
+  {
+    // first row with elements in [warp_q0, warp_q1): offsets[row] <= warp_q0 < offsets[row + 1]
+    int lo_r = 0, hi_r = a.chunk_rows;
+    while (hi_r - lo_r > 1) {
+      int const mid = (lo_r + hi_r) >> 1;
+      if (__ldg(a.offsets + mid) <= (uint32_t)warp_q0) lo_r = mid; else hi_r = mid;
+    }
+    int const T = terms.T;
+    for (int base = lo_r;; base += 32) {
+      int const row = base + lane;
+      uint32_t q = row < a.chunk_rows ? __ldg(a.offsets + row) : 0xffffffffu;
+      bool const mine = row < a.chunk_rows && q < warp_q1;
+      if (!__any_sync(0xffffffffu, mine)) break;
+      if (mine) {
+        uint64_t const alpha = __ldg(a.ix.reps + a.chunk_begin + row);
+        for (int t = 0; t < T; ++t)
+          if ((alpha & terms.m[t]) == terms.l[t]) {
+            if (q >= warp_q0 && q < warp_q1) {
+              unsigned const e = (unsigned)(q - warp_q0);
+              stage[(e & 31u) * 32 + (e >> 5)] = alpha ^ terms.x[t];
+            }
+            ++q;
+          }
+      }
+    }
   }
-  for (int t = tid; t < TD; t += kMvThreads) {
+  __syncwarp();
+  uint32_t r[NP];
+  {
+    uint32_t lo[32], hi[32];
+    uint64_t beta = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < lanes) beta = stage[k * 32 + lane];
+      lo[k] = (uint32_t)beta;  // lanes past the end repeat the last element (or carry zeros)
+      hi[k] = (uint32_t)(beta >> 32);
+    }
+    __syncwarp();  // every lane holds its betas: the slab may now be overwritten by the planes
+    transpose32(lo);
+    if (NP > 32) transpose32(hi);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      r[i] = (i < 32) ? lo[(i < 32) ? i : 0] : hi[(i < 32) ? 0 : i - 32];
+      planes[i * 32 + lane] = r[i];
+    }
+  }
+  __syncwarp();  // all 32 lanes are here (see above); a thread only reads back its own column
+  unsigned char const *column = reinterpret_cast<unsigned char const *>(planes + lane);
+  uint32_t idx[kMvIdxPlanes];
+#pragma unroll
+  for (int p = 0; p < kMvIdxPlanes; ++p) idx[p] = 0;  // character 0 == 1+0i: the input itself (generator.cpp:105-106)
+  int const nbits = a.g.number_bits;
+  int const nidx = a.number_idx_planes;
+  int const G = (a.debug_skip & 1) ? 0 : a.g.number_masks;
+#pragma unroll 1
+  for (int j = 0; j < G; ++j) {
+    uint16_t const *po = c_plane_offset + j * (NP + kPlaneRowExtra);
+    // z = min(y, ~y) = y ^ top(y) when spin inversion is present (see basis_build.cu)
+    uint32_t top = 0;
+    if (INV) top = *reinterpret_cast<uint32_t const *>(column + po[NP]);
+    uint32_t z[NP];
+    uint32_t lt = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      z[i] = *reinterpret_cast<uint32_t const *>(column + po[i]);
+      if (INV) z[i] ^= (i < NP - 3 || i < nbits) ? top : 0u;  // padding planes stay zero
+      lt = ((z[i] ^ r[i]) & r[i]) | (~(z[i] ^ r[i]) & lt);   // one LOP3: z < r, most significant plane last
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) r[i] = (lt & z[i]) | (~lt & r[i]);
+    if (nidx > 0) {
+      unsigned const ci = po[NP + 1];
+      auto update = [&](int p) {
+        uint32_t const c = 0u - ((ci >> p) & 1u);          // chi_j
+        uint32_t const cf = 0u - ((ci >> (8 + p)) & 1u);   // inversion * chi_j
+        uint32_t const nb = INV ? ((top & cf) | (~top & c)) : c;
+        idx[p] = (lt & nb) | (~lt & idx[p]);
+      };
+      update(0);
+      if (nidx > 1) update(1);
+      if (nidx > 2) { update(2); update(3); }
+      if (nidx > 4) { update(4); update(5); update(6); update(7); }
+    }
+  }
+  // back to one state per word, CSR order in global memory
+  {
+    uint32_t lo[32], hi[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      lo[i] = (i < NP) ? r[(i < NP) ? i : 0] : 0u;
+      hi[i] = (i + 32 < NP) ? r[(i + 32 < NP) ? i + 32 : 0] : 0u;
+    }
+    transpose32(lo);
+    if (NP > 32) transpose32(hi);
+    uint64_t *out = a.q_rep + q0;
+    if (lanes == 32) {
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        ulonglong2 v;
+        v.x = (NP > 32) ? (((uint64_t)hi[k] << 32) | lo[k]) : (uint64_t)lo[k];
+        v.y = (NP > 32) ? (((uint64_t)hi[k + 1] << 32) | lo[k + 1]) : (uint64_t)lo[k + 1];
+        *reinterpret_cast<ulonglong2 *>(out + k) = v;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < lanes) out[k] = (NP > 32) ? (((uint64_t)hi[k] << 32) | lo[k]) : (uint64_t)lo[k];
+    }
+  }
+  if (nidx > 0) {
+    uint32_t info[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) info[i] = (i < kMvIdxPlanes) ? idx[(i < kMvIdxPlanes) ? i : 0] : 0u;
+    transpose32(info);
+    uint8_t *out = a.q_cidx + q0;
+    if (lanes == 32) {
+#pragma unroll
+      for (int k = 0; k < 32; k += 4)
+        *reinterpret_cast<uint32_t *>(out + k) =
+            (info[k] & 0xffu) | ((info[k + 1] & 0xffu) << 8) | ((info[k + 2] & 0xffu) << 16) | (info[k + 3] << 24);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < lanes) out[k] = (uint8_t)info[k];
+    }
+  }
+}
+
+// Scalar fallback of orbit_kernel: thread per row, Benes walk per element.
+__global__ void __launch_bounds__(128)
+orbit_scalar_kernel(MatvecArgs const a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  AdjointTerms terms;
+  terms.stage(smem, a.off, false);
+  __syncthreads();
+  int const r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.chunk_rows) return;
+  uint64_t const alpha = __ldg(a.ix.reps + a.chunk_begin + r);
+  uint32_t q = a.offsets[r];
+  for (int t = 0; t < terms.T; ++t)
+    if ((alpha & terms.m[t]) == terms.l[t]) {
+      uint64_t rep;
+      int e, flipped;
+      orbit_min_global(a.g, alpha ^ terms.x[t], rep, e, flipped);
+      unsigned c = 0;
+      if (e >= 0) {
+        unsigned const ci = __ldg(a.g.cinfo + e);
+        c = flipped ? (ci >> 8) : (ci & 0xffu);
+      }
+      a.q_rep[q] = rep;
+      a.q_cidx[q] = (uint8_t)c;
+      ++q;
+    }
+}
+
+// Thread per row: rank, gather, sum in term order, write y.
+//   QUEUED: representatives / character indices come from the orbit kernel;
+//   otherwise they are computed inline (no symmetries, or spin inversion only).
+template <bool QUEUED, bool CPLX>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_kernel(MatvecArgs const a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  AdjointTerms terms;
+  terms.stage(smem, a.off, true);
+  size_t p = (AdjointTerms::bytes(a.off.number_terms, true) + 15) & ~size_t(15);
+  int const TD = a.diag.number_terms;
+  // 16-byte items first so that every array stays naturally aligned for any TD
+  double2 *d_v = reinterpret_cast<double2 *>(smem + p);
+  double2 *chars = d_v + TD;
+  uint64_t *d_m = reinterpret_cast<uint64_t *>(chars + a.number_chars);
+  uint64_t *d_r = d_m + TD;
+  uint64_t *d_s = d_r + TD;
+  for (int t = threadIdx.x; t < TD; t += blockDim.x) {
     d_m[t] = a.diag.m[t];
     d_r[t] = a.diag.r[t];
     d_s[t] = a.diag.s[t];
     d_v[t] = a.diag.v[t];
   }
-  for (int j = tid; j < a.number_chars; j += kMvThreads) chars[j] = a.cvals[j];
+  for (int j = threadIdx.x; j < a.number_chars; j += blockDim.x) chars[j] = a.cvals[j];
   __syncthreads();
 
-  int64_t const rows_total = a.row_end - a.row_begin;
-  int const R = a.rows_per_tile;
-  int64_t const tiles = (rows_total + R - 1) / R;
+  int const r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.chunk_rows) return;
+  int64_t const row = a.chunk_begin + r;
+  uint64_t const alpha = __ldg(a.ix.reps + row);
+  IndexView const ix = a.ix;
+  int const T = terms.T;
+  double acc_r = 0.0, acc_i = 0.0;
+  uint32_t q = QUEUED ? __ldg(a.offsets + r) : 0u;
+  bool const skip_gather = (a.debug_skip & 2) != 0;
 
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    int64_t const row0 = a.row_begin + tile * R;
-    int const nrows = (int)min((int64_t)R, a.row_end - row0);
-
-    // ---- phase 1: matches per row, diagonal ------------------------------------
-    uint32_t counts[kMvRowsPerThread];
+  int t = 0;
+  while (t < T && !skip_gather) {
+    // collect up to kGatherBatch matching terms
+    uint64_t needle[kGatherBatch];
+    double fr[kGatherBatch], fi[kGatherBatch];
+    bool live[kGatherBatch];
 #pragma unroll
-    for (int u = 0; u < kMvRowsPerThread; ++u) {
-      int const r = tid * kMvRowsPerThread + u;
-      uint32_t c = 0;
-      if (r < nrows) {
-        uint64_t const alpha = __ldg(a.ix.reps + row0 + r);
-        row_alpha[r] = alpha;
-        for (int t = 0; t < T; ++t) c += ((alpha & t_m[t]) == t_l[t]) ? 1u : 0u;
-        double dr = 0.0, di = 0.0;
-        for (int t = 0; t < TD; ++t)
-          if ((alpha & d_m[t]) == d_r[t]) {
-            double const sign = (__popcll(alpha & d_s[t]) & 1) ? -1.0 : 1.0;
-            dr += sign * d_v[t].x;
-            di += sign * d_v[t].y;
-          }
-        row_diag[r] = make_double2(dr, di);
-        row_acc[r] = make_double2(0.0, 0.0);
-      }
-      counts[u] = c;
-    }
-    uint32_t offsets[kMvRowsPerThread];
-    uint32_t total;
-    BlockScan(scan_storage).ExclusiveSum(counts, offsets, total);
-#pragma unroll
-    for (int u = 0; u < kMvRowsPerThread; ++u) {
-      int const r = tid * kMvRowsPerThread + u;
-      if (r < nrows) row_off[r] = offsets[u];
-    }
-    if (tid == 0) {
-      row_off[nrows] = total;
-      s_total = total;
-    }
-    __syncthreads();
-    total = s_total;
-
-    for (uint32_t base = 0; base < total; base += kMvCap) {
-      int const nwin = (int)min((uint32_t)kMvCap, total - base);
-
-      // ---- phase 2: fill the queue window [base, base + nwin) -------------------
-#pragma unroll
-      for (int u = 0; u < kMvRowsPerThread; ++u) {
-        int const r = tid * kMvRowsPerThread + u;
-        if (r < nrows && row_off[r + 1] > base && row_off[r] < base + (uint32_t)nwin) {
-          uint64_t const alpha = row_alpha[r];
-          uint32_t q = row_off[r];
-          for (int t = 0; t < T; ++t)
-            if ((alpha & t_m[t]) == t_l[t]) {
-              if (q >= base && q < base + (uint32_t)nwin) {
-                int const slot = queue_slot((int)(q - base));
-                queue[slot] = alpha ^ t_x[t];
-                meta[slot] = (uint16_t)(t | ((__popcll(alpha & t_s[t]) & 1) << 15));
-              }
-              ++q;
-            }
-        }
-      }
-      __syncthreads();
-
-      // ---- phase 3a: canonicalise (thread per 32 entries) ---------------------------
-      // In:  queue[slot] = beta.  Out: queue[slot] = representative, cidx[slot] =
-      // index (into chars[]) of the character of the minimising image.
-      int const nwords = (nwin + 31) >> 5;
-      // Whole warps enter (a warp-uniform condition) so that the group loop runs
-      // converged and its per-element table reads use the uniform datapath; threads
-      // past the last word carry lane 0 of word 0 and store nothing.
-      if ((tid & ~31) < nwords) {
-        int const lanes = max(0, min(32, nwin - 32 * tid));
-        if (a.mode == kModeGroup) {
-          uint32_t r[NP];
-          {
-            uint32_t lo[32], hi[32];
-            uint64_t const pad = queue[lanes > 0 ? tid : 0];  // lane 0 of a live word is always valid
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              uint64_t const b = (k < lanes) ? queue[k * kMvThreads + tid] : pad;
-              lo[k] = (uint32_t)b;
-              hi[k] = (uint32_t)(b >> 32);
-            }
-            transpose32(lo);
-            if (NP > 32) transpose32(hi);
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-              r[i] = (i < 32) ? lo[i] : hi[(i < 32) ? 0 : i - 32];
-              planes[i * kMvThreads + tid] = r[i];
-            }
-          }
-          __syncwarp();  // all 32 lanes are here (see above); a thread only reads back its own column
-          unsigned char const *column = reinterpret_cast<unsigned char const *>(planes + tid);
-          uint32_t idx[kMvIdxPlanes];
-#pragma unroll
-          for (int p = 0; p < kMvIdxPlanes; ++p) idx[p] = 0;  // character 0 == 1+0i: the input itself (generator.cpp:105-106)
-          int const nbits = a.g.number_bits;
-          int const nidx = a.number_idx_planes;
-#pragma unroll 1
-          for (int j = 0; j < ((a.debug_skip & 1) ? 0 : G); ++j) {
-            uint16_t const *po = c_plane_offset + j * (NP + kPlaneRowExtra);
-            // z = min(y, ~y) = y ^ top(y) when spin inversion is present (see basis_build.cu)
-            uint32_t top = 0;
-            if (INV) top = *reinterpret_cast<uint32_t const *>(column + po[NP]);
-            uint32_t z[NP];
-            uint32_t lt = 0;
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-              z[i] = *reinterpret_cast<uint32_t const *>(column + po[i]);
-              if (INV) z[i] ^= (i < NP - 3 || i < nbits) ? top : 0u;  // padding planes stay zero
-              lt = ((z[i] ^ r[i]) & r[i]) | (~(z[i] ^ r[i]) & lt);   // one LOP3: z < r, most significant plane last
-            }
-#pragma unroll
-            for (int i = 0; i < NP; ++i) r[i] = (lt & z[i]) | (~lt & r[i]);
-            if (nidx > 0) {
-              unsigned const ci = po[NP + 1];
-              auto update = [&](int p) {
-                uint32_t const c = 0u - ((ci >> p) & 1u);          // chi_j
-                uint32_t const cf = 0u - ((ci >> (8 + p)) & 1u);   // inversion * chi_j
-                uint32_t const nb = INV ? ((top & cf) | (~top & c)) : c;
-                idx[p] = (lt & nb) | (~lt & idx[p]);
-              };
-              update(0);
-              if (nidx > 1) update(1);
-              if (nidx > 2) { update(2); update(3); }
-              if (nidx > 4) { update(4); update(5); update(6); update(7); }
-            }
-          }
-          // back to one state per word
-          {
-            uint32_t lo[32], hi[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              lo[i] = (i < NP) ? r[(i < NP) ? i : 0] : 0u;
-              hi[i] = (i + 32 < NP) ? r[(i + 32 < NP) ? i + 32 : 0] : 0u;
-            }
-            transpose32(lo);
-            if (NP > 32) transpose32(hi);
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (k < lanes) queue[k * kMvThreads + tid] = (NP > 32) ? (((uint64_t)hi[k] << 32) | lo[k]) : (uint64_t)lo[k];
-          }
-          {
-            uint32_t info[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) info[i] = (i < kMvIdxPlanes) ? idx[(i < kMvIdxPlanes) ? i : 0] : 0u;
-            if (nidx > 0) transpose32(info);
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (k < lanes) cidx[k * kMvThreads + tid] = (uint8_t)info[k];
-          }
+    for (int u = 0; u < kGatherBatch; ++u) {
+      while (t < T && (alpha & terms.m[t]) != terms.l[t]) ++t;
+      live[u] = t < T;
+      needle[u] = 0;
+      fr[u] = fi[u] = 0.0;
+      if (live[u]) {
+        double2 w = terms.w[t];
+        if (__popcll(alpha & terms.s[t]) & 1) { w.x = -w.x; w.y = -w.y; }
+        uint64_t rep;
+        unsigned c;
+        if (QUEUED) {
+          rep = __ldg(a.q_rep + q);
+          c = a.number_idx_planes > 0 ? __ldg(a.q_cidx + q) : 0u;
+          ++q;
         } else {
-#pragma unroll 1
-          for (int k = 0; k < lanes; ++k) {
-            int const slot = k * kMvThreads + tid;
-            uint64_t rep = queue[slot];
-            unsigned c = 0;
-            if (a.mode == kModeGroupScalar) {
-              int e, flipped;
-              uint64_t r2;
-              orbit_min_global(a.g, rep, r2, e, flipped);
-              rep = r2;
-              if (e >= 0) {
-                unsigned const ci = __ldg(a.g.cinfo + e);
-                c = flipped ? (ci >> 8) : (ci & 0xffu);
-              }
-            } else if (a.mode == kModeInversion) {
-              // BatchedOperator.chpl:187-199
-              uint64_t const inverted = rep ^ a.inversion_mask;
-              if (inverted < rep) {
-                rep = inverted;
-                c = 1;
-              }
+          rep = alpha ^ terms.x[t];
+          c = 0;
+          if (a.mode == kModeInversion) {
+            // BatchedOperator.chpl:187-199
+            uint64_t const inverted = rep ^ a.inversion_mask;
+            if (inverted < rep) {
+              rep = inverted;
+              c = 1;
             }
-            queue[slot] = rep;
-            cidx[slot] = (uint8_t)c;
           }
         }
-      }
-      __syncthreads();
-
-      // ---- phase 3b: rank + gather, eight independent searches in flight per thread ----
-      if (tid < nwords && !(a.debug_skip & 2)) {
-        int const lanes = min(32, nwin - 32 * tid);
-        constexpr int B = 8;
-#pragma unroll 1
-        for (int k0 = 0; k0 < 32; k0 += B) {
-          uint64_t needle[B];
-          int64_t lo[B], n[B];
-#pragma unroll
-          for (int u = 0; u < B; ++u) {
-            bool const live = k0 + u < lanes;
-            needle[u] = live ? queue[(k0 + u) * kMvThreads + tid] : 0;
-            index_window(a.ix, needle[u], live, lo[u], n[u]);
-          }
-          if (!a.ix.identity) {
-#pragma unroll 1
-            for (int s = 0; s < a.ix.steps; ++s) {
-#pragma unroll
-              for (int u = 0; u < B; ++u) {
-                int64_t const half = n[u] >> 1;
-                int64_t const mid = lo[u] + half;
-                uint64_t const v = n[u] > 0 ? __ldg(a.ix.reps + mid) : ~uint64_t(0);
-                bool const less = v < needle[u];
-                lo[u] = less ? mid + 1 : lo[u];
-                n[u] = less ? n[u] - half - 1 : half;
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < B; ++u) {
-            int const slot = (k0 + u) * kMvThreads + tid;
-            bool const live = k0 + u < lanes;
-            int64_t j = -1;
-            if (live) {
-              if (a.ix.identity) j = (int64_t)needle[u];
-              else if (lo[u] < a.ix.number_states && __ldg(a.ix.reps + lo[u]) == needle[u]) j = lo[u];
-            }
-            double vr = 0.0, vi = 0.0;
-            if (live) {
-              unsigned const mt = meta[slot];
-              double2 w = t_w[mt & 0x7fffu];
-              if (mt & 0x8000u) { w.x = -w.x; w.y = -w.y; }
-              if (j >= 0) {
-                double2 const c = chars[cidx[slot]];
-                // conj(chi) * w * xs[j]
-                double const fr = c.x * w.x + c.y * w.y;
-                double const fi = c.x * w.y - c.y * w.x;
-                if (cplx) {
-                  double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.xs) + j);
-                  vr = fr * xv.x - fi * xv.y;
-                  vi = fr * xv.y + fi * xv.x;
-                } else {
-                  vr = fr * __ldg(a.xs + j);
-                }
-              } else if (w.x != 0.0 || w.y != 0.0) {
-                // Not in the basis: fine when its norm vanishes (the reference
-                // multiplies by n_beta = 0), an error otherwise
-                // (DistributedMatrixVector.chpl:127-135).
-                bool bad = true;
-                if (a.mode == kModeGroup || a.mode == kModeGroupScalar)
-                  bad = stabiliser_sum_global(a.g, needle[u]) > kNormThreshold;
-                if (bad) atomicOr(a.error_flag, 1);
-              }
-            }
-            values_re[slot] = vr;
-            if (cplx) values_im[slot] = vi;
-          }
-        }
-      }
-      __syncthreads();
-
-      // ---- phase 4: per-row sums in term order -----------------------------------
-#pragma unroll
-      for (int u = 0; u < kMvRowsPerThread; ++u) {
-        int const r = tid * kMvRowsPerThread + u;
-        if (r < nrows) {
-          uint32_t const q0 = max(row_off[r], base);
-          uint32_t const q1 = min(row_off[r + 1], base + (uint32_t)nwin);
-          if (q0 < q1) {
-            double sr = row_acc[r].x, si = row_acc[r].y;
-            for (uint32_t q = q0; q < q1; ++q) {
-              int const slot = queue_slot((int)(q - base));
-              sr += values_re[slot];
-              if (cplx) si += values_im[slot];
-            }
-            row_acc[r] = make_double2(sr, si);
-          }
-        }
-      }
-      __syncthreads();
-    }
-
-    // ---- write y -------------------------------------------------------------------
-    for (int r = tid; r < nrows; r += kMvThreads) {
-      int64_t const row = row0 + r;
-      double const ni = a.norms != nullptr ? __ldg(a.norms + row) : 1.0;
-      double2 const acc = row_acc[r];
-      double2 const dg = row_diag[r];
-      int64_t const out = row - a.row_begin;
-      if (cplx) {
-        double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.x) + row);
-        double2 res;
-        res.x = acc.x / ni + (dg.x * xv.x - dg.y * xv.y);
-        res.y = acc.y / ni + (dg.x * xv.y + dg.y * xv.x);
-        reinterpret_cast<double2 *>(a.y)[out] = res;
-      } else {
-        // kernels/reference.c:84-91 uses creal(v) only
-        a.y[out] = acc.x / ni + dg.x * __ldg(a.x + row);
+        double2 const ch = chars[c];
+        // conj(chi) * w
+        fr[u] = ch.x * w.x + ch.y * w.y;
+        fi[u] = ch.x * w.y - ch.y * w.x;
+        needle[u] = rep;
+        ++t;
       }
     }
-    __syncthreads();
+    // rank: kGatherBatch independent branchless searches in lockstep
+    int64_t j[kGatherBatch];
+    index_find<kGatherBatch>(ix, needle, live, j);
+#pragma unroll
+    for (int u = 0; u < kGatherBatch; ++u) {
+      if (!live[u]) continue;
+      if (j[u] >= 0) {
+        if (CPLX) {
+          double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.xs) + j[u]);
+          acc_r += fr[u] * xv.x - fi[u] * xv.y;
+          acc_i += fr[u] * xv.y + fi[u] * xv.x;
+        } else {
+          acc_r += fr[u] * __ldg(a.xs + j[u]);
+        }
+      } else if (fr[u] != 0.0 || fi[u] != 0.0) {
+        // Not in the basis: fine when its norm vanishes (the reference
+        // multiplies by n_beta = 0), an error otherwise
+        // (DistributedMatrixVector.chpl:127-135).
+        bool bad = true;
+        if (a.mode == kModeGroup || a.mode == kModeGroupScalar)
+          bad = stabiliser_sum_global(a.g, needle[u]) > kNormThreshold;
+        if (bad) atomicOr(a.error_flag, 1);
+      }
+    }
+  }
+
+  // diagonal + write
+  double dr = 0.0, di = 0.0;
+  for (int k = 0; k < TD; ++k)
+    if ((alpha & d_m[k]) == d_r[k]) {
+      double const sign = (__popcll(alpha & d_s[k]) & 1) ? -1.0 : 1.0;
+      dr += sign * d_v[k].x;
+      di += sign * d_v[k].y;
+    }
+  double const ni = a.norms != nullptr ? __ldg(a.norms + row) : 1.0;
+  int64_t const out = row - a.row_begin;
+  if (CPLX) {
+    double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.x) + row);
+    double2 res;
+    res.x = acc_r / ni + (dr * xv.x - di * xv.y);
+    res.y = acc_i / ni + (dr * xv.y + di * xv.x);
+    reinterpret_cast<double2 *>(a.y)[out] = res;
+  } else {
+    // kernels/reference.c:84-91 uses creal(v) only
+    a.y[out] = acc_r / ni + dr * __ldg(a.x + row);
   }
 }
 
@@ -618,29 +583,29 @@ count_elements_kernel(TermsView off, uint64_t const *__restrict__ reps, int64_t 
 
 void ensure_norms(IndexData &ix, GroupData const &g);
 
-using MatvecKernel = void (*)(MatvecArgs, MvSmem);
+using OrbitKernel = void (*)(MatvecArgs);
 template <int NP>
-static MatvecKernel pick_mv_inv(bool inv) {
-  return inv ? matvec_kernel<NP, true> : matvec_kernel<NP, false>;
+static OrbitKernel pick_orbit_inv(bool inv) {
+  return inv ? orbit_kernel<NP, true> : orbit_kernel<NP, false>;
 }
-static MatvecKernel pick_matvec_kernel(int np, bool inv) {
+static OrbitKernel pick_orbit_kernel(int np, bool inv) {
   switch (np) {
-    case 4: return pick_mv_inv<4>(inv);
-    case 8: return pick_mv_inv<8>(inv);
-    case 12: return pick_mv_inv<12>(inv);
-    case 16: return pick_mv_inv<16>(inv);
-    case 20: return pick_mv_inv<20>(inv);
-    case 24: return pick_mv_inv<24>(inv);
-    case 28: return pick_mv_inv<28>(inv);
-    case 32: return pick_mv_inv<32>(inv);
-    case 36: return pick_mv_inv<36>(inv);
-    case 40: return pick_mv_inv<40>(inv);
-    case 44: return pick_mv_inv<44>(inv);
-    case 48: return pick_mv_inv<48>(inv);
-    case 52: return pick_mv_inv<52>(inv);
-    case 56: return pick_mv_inv<56>(inv);
-    case 60: return pick_mv_inv<60>(inv);
-    case 64: return pick_mv_inv<64>(inv);
+    case 4: return pick_orbit_inv<4>(inv);
+    case 8: return pick_orbit_inv<8>(inv);
+    case 12: return pick_orbit_inv<12>(inv);
+    case 16: return pick_orbit_inv<16>(inv);
+    case 20: return pick_orbit_inv<20>(inv);
+    case 24: return pick_orbit_inv<24>(inv);
+    case 28: return pick_orbit_inv<28>(inv);
+    case 32: return pick_orbit_inv<32>(inv);
+    case 36: return pick_orbit_inv<36>(inv);
+    case 40: return pick_orbit_inv<40>(inv);
+    case 44: return pick_orbit_inv<44>(inv);
+    case 48: return pick_orbit_inv<48>(inv);
+    case 52: return pick_orbit_inv<52>(inv);
+    case 56: return pick_orbit_inv<56>(inv);
+    case 60: return pick_orbit_inv<60>(inv);
+    case 64: return pick_orbit_inv<64>(inv);
   }
   return nullptr;
 }
@@ -664,12 +629,36 @@ static int64_t count_elements(OperatorDev &od, IndexData const &ix, int64_t row_
 
 struct MatvecScratch {
   DeviceBuffer<double> x, xs, y;
+  DeviceBuffer<uint32_t> counts, offsets;
+  DeviceBuffer<uint64_t> q_rep;
+  DeviceBuffer<uint8_t> q_cidx;
+  DeviceBuffer<unsigned char> scan_tmp;
+  size_t scan_tmp_bytes = 0;
   int *d_error = nullptr;
   double2 *d_plain_chars = nullptr;  // {1, +1, -1}: character table of the unprojected / inversion-only modes
+  // per-kernel device time of the last matvec (LS_B200_PROFILE=1): events around every orbit / gather launch
+  std::vector<cudaEvent_t> events;
+  size_t events_used = 0;
+  std::vector<std::pair<size_t, int>> spans;  // (index of start event, kind: 0 orbit, 1 gather)
 };
 static MatvecScratch &mv_scratch() {
   static MatvecScratch s;
   return s;
+}
+
+template <class K>
+static void allow_dynamic_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+static cudaEvent_t next_event(MatvecScratch &sc) {
+  if (sc.events_used == sc.events.size()) {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    sc.events.push_back(e);
+  }
+  return sc.events[sc.events_used++];
 }
 
 // y[row_begin:row_end] = (H x)[row_begin:row_end]; x, y in device memory.
@@ -692,6 +681,10 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     CUDA_CHECK(cudaMalloc(&sc.d_plain_chars, sizeof plain));
     CUDA_CHECK(cudaMemcpy(sc.d_plain_chars, plain, sizeof plain, cudaMemcpyHostToDevice));
   }
+  static bool const profile = getenv("LS_B200_PROFILE") != nullptr;
+  sc.events_used = 0;
+  sc.spans.clear();
+  CUDA_CHECK(cudaEventRecord(rt.ev0, rt.stream));
 
   MatvecArgs a{};
   a.ix = ix->view();
@@ -699,7 +692,6 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   a.diag = od.diag.view();
   a.complex_vectors = complex_vectors ? 1 : 0;
   a.row_begin = row_begin;
-  a.row_end = row_end;
   a.x = d_x;
   a.xs = d_x;
   a.y = d_y;
@@ -712,7 +704,6 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   a.number_chars = 1;
   int np = 4;
   bool inv = false;
-  bool bitsliced = false;
   if (info.has_permutation_symmetries) {
     GroupData const &g = *info.group;
     ensure_norms(*ix, g);
@@ -726,8 +717,9 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     a.cvals = g.d_cvals;
     a.number_chars = (int)(g.cvals.size() / 2);
     while ((1 << a.number_idx_planes) < a.number_chars) ++a.number_idx_planes;
-    bitsliced = !want_scalar && upload_plane_offsets(g, np, kMvThreads);
+    bool const bitsliced = !want_scalar && upload_plane_offsets(g, np, 32);
     a.mode = bitsliced ? kModeGroup : kModeGroupScalar;
+    if (!bitsliced) a.number_idx_planes = std::max(a.number_idx_planes, 1);  // the scalar kernel always writes q_cidx
     // pre-scaled copy of x
     size_t const words = (size_t)dim * (complex_vectors ? 2 : 1);
     double *xs = sc.xs.reserve(words);
@@ -742,34 +734,83 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     a.cvals = sc.d_plain_chars + (basis->spin_inversion < 0 ? 1 : 0);
     a.number_chars = 2;
   }
-
-  // tile size from the average number of matrix elements per row
-  if (od.stats_index != (void const *)ix || od.stats_rows != dim) {
-    od.stats_elements = count_elements(od, *ix, 0, dim);
-    od.stats_index = ix;
-    od.stats_rows = dim;
-  }
-  double const avg = dim > 0 ? (double)od.stats_elements / (double)dim : 0.0;
-  int rows = kMvMaxRows;
-  if (avg > 0.0) rows = (int)std::min<double>(kMvMaxRows, std::max(1.0, 0.94 * kMvCap / avg));
-  a.rows_per_tile = rows;
-
-  bool const group_planes = a.mode == kModeGroup;
-  MvSmem const L = mv_layout(a.off.number_terms, a.diag.number_terms, a.number_chars, np, complex_vectors, group_planes);
-  LSB_CHECK((size_t)L.total <= rt.smem_optin, "operator / symmetry tables do not fit in shared memory");
   LSB_CHECK(a.off.number_terms < 0x8000, "too many off-diagonal terms");
-  MatvecKernel kernel = group_planes ? pick_matvec_kernel(np, inv) : matvec_kernel<4, false>;
-  LSB_CHECK(kernel != nullptr, "unsupported number of bits");
-  CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  int per_sm = 1;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kMvThreads, (size_t)L.total));
-  per_sm = std::max(per_sm, 1);
-  int64_t const tiles = (row_end - row_begin + rows - 1) / rows;
-  unsigned const blocks = (unsigned)std::min<int64_t>(tiles, (int64_t)rt.sm_count * per_sm);
-  CUDA_CHECK(cudaEventRecord(rt.ev0, rt.stream));
-  kernel<<<blocks, kMvThreads, (size_t)L.total, rt.stream>>>(a, L);
-  count_launch();
-  CUDA_CHECK(cudaGetLastError());
+
+  int const T = a.off.number_terms;
+  bool const queued = (a.mode == kModeGroup || a.mode == kModeGroupScalar) && T > 0;
+  size_t const gather_smem = ((AdjointTerms::bytes(T, true) + 15) & ~size_t(15)) + (size_t)a.diag.number_terms * 40 +
+                             (size_t)a.number_chars * 16;
+  size_t const count_smem = AdjointTerms::bytes(T, false);
+  size_t const orbit_smem = ((count_smem + 15) & ~size_t(15)) + (size_t)(kOrbitThreads / 32) * kWarpSlabBytes;
+  LSB_CHECK(gather_smem <= rt.smem_optin && orbit_smem <= rt.smem_optin,
+            "operator / symmetry tables do not fit in shared memory");
+
+  // Chunk of rows: its intermediates (8 + 1 bytes per matrix element) must fit the
+  // scratch capacity even if every term matched every row.
+  int64_t capacity = int64_t(1) << 27;
+  if (char const *env = getenv("LS_B200_MV_CHUNK")) capacity = std::max<int64_t>(4096, atoll(env));
+  int64_t chunk_rows = row_end - row_begin;
+  OrbitKernel orbit = nullptr;
+  if (queued) {
+    chunk_rows = std::max<int64_t>(1, std::min<int64_t>(chunk_rows, capacity / T));
+    capacity = chunk_rows * T;
+    a.counts = sc.counts.reserve((size_t)chunk_rows + 1);
+    a.offsets = sc.offsets.reserve((size_t)chunk_rows + 1);
+    a.q_rep = sc.q_rep.reserve((size_t)capacity + 32);
+    a.q_cidx = sc.q_cidx.reserve((size_t)capacity + 32);
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, a.counts, a.offsets, (int)(chunk_rows + 1), rt.stream);
+    if (tmp > sc.scan_tmp_bytes) {
+      sc.scan_tmp.reserve(tmp);
+      sc.scan_tmp_bytes = sc.scan_tmp.capacity;
+    }
+    if (a.mode == kModeGroup) {
+      orbit = pick_orbit_kernel(np, inv);
+      LSB_CHECK(orbit != nullptr, "unsupported number of bits");
+      allow_dynamic_smem(orbit, orbit_smem);
+    } else {
+      allow_dynamic_smem(orbit_scalar_kernel, count_smem);
+    }
+    allow_dynamic_smem(row_count_kernel, count_smem);
+  } else {
+    chunk_rows = std::min<int64_t>(chunk_rows, int64_t(1) << 30);
+  }
+  auto gather = queued ? (complex_vectors ? gather_kernel<true, true> : gather_kernel<true, false>)
+                       : (complex_vectors ? gather_kernel<false, true> : gather_kernel<false, false>);
+  allow_dynamic_smem(gather, gather_smem);
+
+  for (int64_t begin = row_begin; begin < row_end; begin += chunk_rows) {
+    int64_t const nrows = std::min(chunk_rows, row_end - begin);
+    a.chunk_begin = begin;
+    a.chunk_rows = (int)nrows;
+    if (queued) {
+      row_count_kernel<<<ceil_div((size_t)nrows + 1, 256), 256, count_smem, rt.stream>>>(a);
+      size_t tmp = sc.scan_tmp_bytes;
+      cub::DeviceScan::ExclusiveSum(sc.scan_tmp.ptr, tmp, a.counts, a.offsets, (int)(nrows + 1), rt.stream);
+      count_launch(2);
+      if (profile) {
+        sc.spans.emplace_back(sc.events_used, 0);
+        CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+      }
+      if (a.mode == kModeGroup) {
+        // grid for the worst case (every term matches); words past the chunk's total exit at once
+        size_t const max_words = (((size_t)nrows * (size_t)T + 1023) / 1024) * 32;
+        orbit<<<ceil_div(max_words, kOrbitThreads), kOrbitThreads, orbit_smem, rt.stream>>>(a);
+      } else {
+        orbit_scalar_kernel<<<ceil_div((size_t)nrows, 128), 128, count_smem, rt.stream>>>(a);
+      }
+      count_launch();
+      if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+    }
+    if (profile) {
+      sc.spans.emplace_back(sc.events_used, 1);
+      CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+    }
+    gather<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
+    count_launch();
+    if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+    CUDA_CHECK(cudaGetLastError());
+  }
   CUDA_CHECK(cudaEventRecord(rt.ev1, rt.stream));
 }
 
@@ -782,6 +823,14 @@ static bool matvec_finish() {
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
   float ms = 0;
   if (cudaEventElapsedTime(&ms, rt.ev0, rt.ev1) == cudaSuccess) rt.last_matvec_ms = ms;
+  rt.last_orbit_ms = rt.last_gather_ms = 0;
+  rt.last_orbit_launches = rt.last_gather_launches = 0;
+  for (auto const &span : sc.spans) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, sc.events[span.first], sc.events[span.first + 1]) != cudaSuccess) continue;
+    if (span.second == 0) { rt.last_orbit_ms += t; ++rt.last_orbit_launches; }
+    else { rt.last_gather_ms += t; ++rt.last_gather_launches; }
+  }
   if (flag != 0) {
     CUDA_CHECK(cudaMemsetAsync(sc.d_error, 0, sizeof(int), rt.stream));
     return false;

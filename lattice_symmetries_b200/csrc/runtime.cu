@@ -127,6 +127,10 @@ uint64_t ls_b200_kernel_launch_count(void) { return runtime().launches.load(); }
 double ls_b200_last_kernel_ms(char const *name) {
   Runtime &rt = runtime();
   if (name != nullptr && strcmp(name, "build") == 0) return rt.last_build_ms;
+  if (name != nullptr && strcmp(name, "orbit") == 0) return rt.last_orbit_ms;
+  if (name != nullptr && strcmp(name, "gather") == 0) return rt.last_gather_ms;
+  if (name != nullptr && strcmp(name, "orbit_launches") == 0) return (double)rt.last_orbit_launches;
+  if (name != nullptr && strcmp(name, "gather_launches") == 0) return (double)rt.last_gather_launches;
   return rt.last_matvec_ms;
 }
 

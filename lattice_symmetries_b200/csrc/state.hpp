@@ -55,6 +55,8 @@ struct IndexData {
   bool owns_d_reps = true;
   uint32_t *d_offsets32 = nullptr;
   int64_t *d_offsets64 = nullptr;
+  uint16_t *d_lows16 = nullptr;  // low `shift` bits of every representative (shift <= 16)
+  uint32_t *d_lows32 = nullptr;  // (16 < shift <= 32)
   double *d_norms = nullptr;  // state_info norms of the representatives (lazy)
 
   IndexView view() const;

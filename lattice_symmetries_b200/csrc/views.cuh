@@ -29,12 +29,19 @@ struct GroupView {
 };
 
 // Sorted representatives + prefix bucket table (replaces
-// ls_hs_state_index_binary_search_data, kernels/indexing.c:10-18).
+// ls_hs_state_index_binary_search_data, kernels/indexing.c:10-18).  Within a
+// bucket all representatives share their top prefix bits, so the search only
+// compares the low `shift` bits, kept in a compact side array (2 or 4 bytes per
+// state instead of 8): the whole index of a 3e7-state basis is ~80 MB and
+// stays L2-resident while x is gathered from HBM.
 struct IndexView {
   uint64_t const *reps;
   int64_t number_states;
   uint32_t const *offsets32;  // [2^prefix + 1] when number_states < 2^32
   int64_t const *offsets64;   // otherwise
+  uint16_t const *lows16;     // [number_states] low bits when shift <= 16
+  uint32_t const *lows32;     // [number_states] low bits when 16 < shift <= 32
+  uint64_t low_mask;          // (1 << shift) - 1
   int shift;                  // number_bits - prefix_bits
   int identity;               // state_index_is_identity: index == state
   uint64_t number_buckets;    // 2^prefix
@@ -60,37 +67,8 @@ struct TermsView {
 // out as +-1e-16 noise.  Anything below 0.5 is treated as exactly zero.
 constexpr double kNormThreshold = 0.5;
 
-// lower_bound-style bucketed search; returns index or -1
-// (kernels/indexing.c:196-215, :273-325).
-__device__ __forceinline__ int64_t state_index(IndexView const &ix, uint64_t needle) {
-  if (ix.identity) return (int64_t)needle;
-  uint64_t const p = needle >> ix.shift;
-  int64_t lo, hi;
-  if (ix.offsets32 != nullptr) {
-    if (p >= ix.number_buckets) return -1;
-    lo = (int64_t)__ldg(ix.offsets32 + p);
-    hi = (int64_t)__ldg(ix.offsets32 + p + 1);
-  } else if (ix.offsets64 != nullptr) {
-    if (p >= ix.number_buckets) return -1;
-    lo = __ldg(ix.offsets64 + p);
-    hi = __ldg(ix.offsets64 + p + 1);
-  } else {
-    lo = 0;
-    hi = ix.number_states;
-  }
-  while (lo < hi) {
-    int64_t const mid = (lo + hi) >> 1;
-    uint64_t const v = __ldg(ix.reps + mid);
-    if (v < needle) lo = mid + 1; else hi = mid;
-  }
-  return (lo < ix.number_states && __ldg(ix.reps + lo) == needle) ? lo : (int64_t)-1;
-}
-
 // Search window of `needle`: [lo, lo + n) is its prefix bucket (empty when the
-// needle cannot be in the basis or `live` is false).  Followed by ix.steps
-// rounds of  half = n >> 1; mid = lo + half; reps[mid] < needle ? (lo = mid + 1,
-// n -= half + 1) : (n = half)  -- the fixed-length branchless lower bound of
-// kernels/indexing.c:196-215 -- after which reps[lo] == needle decides.
+// needle cannot be in the basis or `live` is false).
 __device__ __forceinline__ void index_window(IndexView const &ix, uint64_t needle, bool live, int64_t &lo, int64_t &n) {
   lo = 0;
   n = 0;
@@ -109,6 +87,60 @@ __device__ __forceinline__ void index_window(IndexView const &ix, uint64_t needl
   } else {
     n = ix.number_states;
   }
+}
+
+__device__ __forceinline__ uint64_t index_key_at(IndexView const &ix, int64_t i) {
+  if (ix.lows16 != nullptr) return (uint64_t)__ldg(ix.lows16 + i);
+  if (ix.lows32 != nullptr) return (uint64_t)__ldg(ix.lows32 + i);
+  return __ldg(ix.reps + i);
+}
+
+// B independent lookups in lockstep (their loads overlap): index of needle[u]
+// among the sorted representatives, or -1 (kernels/indexing.c:196-215, 273-325:
+// prefix bucket, then a fixed-length branchless lower bound).
+template <int B>
+__device__ __forceinline__ void index_find(IndexView const &ix, uint64_t const (&needle)[B], bool const (&live)[B],
+                                           int64_t (&found)[B]) {
+  if (ix.identity) {
+#pragma unroll
+    for (int u = 0; u < B; ++u) found[u] = live[u] ? (int64_t)needle[u] : (int64_t)-1;
+    return;
+  }
+  bool const compact = ix.lows16 != nullptr || ix.lows32 != nullptr;
+  int64_t lo[B], n[B], end[B];
+  uint64_t key[B];
+#pragma unroll
+  for (int u = 0; u < B; ++u) {
+    index_window(ix, needle[u], live[u], lo[u], n[u]);
+    end[u] = lo[u] + n[u];
+    key[u] = compact ? (needle[u] & ix.low_mask) : needle[u];
+  }
+#pragma unroll 1
+  for (int s = 0; s < ix.steps; ++s) {
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      int64_t const half = n[u] >> 1;
+      int64_t const mid = lo[u] + half;
+      bool less = false;
+      if (n[u] > 0) less = index_key_at(ix, mid) < key[u];
+      lo[u] = less ? mid + 1 : lo[u];
+      n[u] = less ? n[u] - half - 1 : half;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < B; ++u) {
+    found[u] = -1;
+    // lo[u] is the lower bound inside the needle's bucket; it may sit at the bucket's end
+    if (live[u] && lo[u] < end[u] && index_key_at(ix, lo[u]) == key[u]) found[u] = lo[u];
+  }
+}
+
+__device__ __forceinline__ int64_t state_index(IndexView const &ix, uint64_t needle) {
+  uint64_t const needles[1] = {needle};
+  bool const live[1] = {true};
+  int64_t found[1];
+  index_find<1>(ix, needles, live, found);
+  return found[0];
 }
 
 // Scalar orbit walk: apply every group element's Benes network to x

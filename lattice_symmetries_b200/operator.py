@@ -231,6 +231,16 @@ class Operator(_Base):
         return n
 
     @property
+    def _xp(self):
+        """Array namespace newer scipy (>= 1.17) expects LinearOperator.__init__ to have
+        set; like the reference class we never call it (shape is only known after build)."""
+        try:
+            from scipy._lib._array_api import np_compat
+        except ImportError:  # older scipy never asks
+            return np
+        return np_compat
+
+    @property
     def dtype(self):
         self._check_basis_is_built("dtype")
         return np.dtype("float64")

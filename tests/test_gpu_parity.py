@@ -343,7 +343,8 @@ def test_matvec_invalid_sector_raises(oracle):
     m = L.heisenberg_chain(12)
     basis = m.basis()
     basis.build()
-    bad = ls.Operator(basis, ls.Expr("σ⁺₀ σ⁻₁ + σ⁻₀ σ⁺₁ + 0.3 σᶻ₀ σᶻ₅"))  # not translation invariant
+    # sigma^x changes the Hamming weight: every image leaves the Sz = 0 basis
+    bad = ls.Operator(basis, ls.Expr("σˣ₀", sites=[[i] for i in range(12)]))
     x = np.ones(basis.number_states)
     with pytest.raises(RuntimeError, match="invalid index"):
         bad.apply_to_state_vector(x)

@@ -21,4 +21,6 @@ x = _lib.DeviceArray.from_numpy(np.random.default_rng(0).standard_normal(dim))
 y = _lib.DeviceArray(dim, np.float64)
 for _ in range(reps):
     op.matvec_device(x.ptr, y.ptr, sync=True)
-print(name, "dim", dim, "matvec ms", _lib.lib.ls_b200_last_kernel_ms(b"matvec"), "build ms", _lib.lib.ls_b200_last_kernel_ms(b"build"))
+ms = _lib.lib.ls_b200_last_kernel_ms
+print(name, "dim", dim, "matvec ms %.2f" % ms(b"matvec"), "orbit ms %.2f x%d" % (ms(b"orbit"), ms(b"orbit_launches")),
+      "gather ms %.2f x%d" % (ms(b"gather"), ms(b"gather_launches")), "build ms %.2f" % ms(b"build"))
