@@ -274,6 +274,14 @@ int ls_b200_basis_device_view(ls_hs_basis const *basis,
                               uint64_t const **representatives,
                               double const **norms, uint64_t *count);
 
+/* Shape of the state -> index structure that replaces
+ * ls_hs_state_index_binary_search_data (kernels/indexing.c:10-18):
+ * out[0] = prefix bits of the first-level table, out[1] = trip count of the
+ * final branchless search (bit length of the widest window), out[2] = 1 when
+ * crowded buckets carry second-level tables, out[3] = number of states.
+ * Returns 0, or -1 when the basis is not built. */
+int ls_b200_index_info(ls_hs_basis const *basis, int64_t out[4]);
+
 /* y[row_begin:row_end] = (H x)[row_begin:row_end] with x (full length dim)
  * and y (length row_end-row_begin) in DEVICE memory; asynchronous on
  * ls_b200_stream().  Returns 0 on success.  The rows are the contiguous

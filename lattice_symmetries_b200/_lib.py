@@ -169,6 +169,7 @@ PROTOTYPES = {
     "ls_b200_measure_lop3_peak": (C.c_double, []),
     "ls_b200_basis_device_view": (
         C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "ls_b200_index_info": (C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_int64)]),
     "ls_b200_matvec_device": (C.c_int, [C.POINTER(ls_hs_operator), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ls_b200_matvec_device_c128": (C.c_int, [C.POINTER(ls_hs_operator), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ls_b200_matvec_sync": (C.c_int, []),

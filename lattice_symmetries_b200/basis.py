@@ -267,6 +267,14 @@ class Basis:
         return int(indices[0]) if is_scalar else indices
 
     # -- device-resident extensions ------------------------------------------------
+    def index_info(self) -> dict:
+        """Shape of the device index: prefix bits, search trip count, second-level tables."""
+        self.check_is_built()
+        out = (C.c_int64 * 4)()
+        if lib.ls_b200_index_info(C.byref(self._payload), out) != 0:
+            raise RuntimeError("basis has no device index")
+        return {"prefix_bits": int(out[0]), "steps": int(out[1]), "two_level": bool(out[2]), "states": int(out[3])}
+
     @property
     def number_candidates(self) -> int:
         """Size of the enumeration range scanned by ``build`` (combinadic index space)."""

@@ -2,6 +2,8 @@
 // Replaces kernels/indexing.c: the prefix-bucket table (:45-117) is built on
 // the device by one lower_bound per prefix, and the search kernel (:273-325)
 // runs one needle per thread.  Results (index or -1) are identical.
+#include <cub/device/device_scan.cuh>
+
 #include "state.hpp"
 
 namespace lsb {
@@ -19,6 +21,8 @@ IndexView IndexData::view() const {
   v.identity = identity ? 1 : 0;
   v.number_buckets = uint64_t(1) << prefix_bits;
   v.steps = steps;
+  v.sub_info = d_sub_info;
+  v.subtab = d_subtab;
   return v;
 }
 
@@ -28,6 +32,8 @@ IndexData::~IndexData() {
   cudaFree(d_offsets64);
   cudaFree(d_lows16);
   cudaFree(d_lows32);
+  cudaFree(d_sub_info);
+  cudaFree(d_subtab);
   cudaFree(d_norms);
   magic = 0;
 }
@@ -76,6 +82,75 @@ max_bucket_kernel(T const *__restrict__ offsets, int64_t number_buckets, unsigne
     local = other > local ? other : local;
   }
   if ((threadIdx.x & 31) == 0 && local != 0) atomicMax(out, local);
+}
+
+// ---- second level for crowded buckets ---------------------------------------------
+constexpr int kDenseBucket = 32;  // buckets with more entries get a sub-table ...
+constexpr int kSubTargetLog2 = 4; // ... of about 2^4 entries per slot
+constexpr int kMaxSubBits = 24;
+
+__device__ __forceinline__ int sub_bits(uint32_t n, int shift) {
+  if (n <= (uint32_t)kDenseBucket || shift <= 0) return 0;
+  int const len = 32 - __clz(n - 1);  // ceil(log2 n)
+  return max(1, min(min(shift, kMaxSubBits), len - kSubTargetLog2));
+}
+
+// units[p] = size of bucket p's sub-table in units of 8 entries (0: none)
+__global__ void __launch_bounds__(256)
+sub_sizes_kernel(uint32_t const *__restrict__ offsets, int64_t number_buckets, int shift,
+                 uint32_t *__restrict__ units) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < number_buckets;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    int const p2 = sub_bits(offsets[p + 1] - offsets[p], shift);
+    units[p] = p2 == 0 ? 0u : (((1u << p2) + 1u + 7u) >> 3);
+  }
+}
+
+// Warp per bucket: sub_info[p] and the lower bounds of its 2^p2 + 1 slot boundaries;
+// also the largest window any lookup can end up with.  `units` is overwritten in
+// place by sub_info (first[p] is read before).
+__global__ void __launch_bounds__(256)
+sub_fill_kernel(IndexView ix, uint32_t const *__restrict__ first, uint32_t *__restrict__ units_then_info,
+                uint32_t *__restrict__ subtab, unsigned long long *__restrict__ max_window) {
+  int const lane = threadIdx.x & 31;
+  int64_t const warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t const warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  bool const compact = ix.lows16 != nullptr || ix.lows32 != nullptr;
+  uint32_t widest = 0;
+  for (int64_t p = warp; p < (int64_t)ix.number_buckets; p += warps) {
+    uint32_t const lo = ix.offsets32[p];
+    uint32_t const n = ix.offsets32[p + 1] - lo;
+    int const p2 = sub_bits(n, ix.shift);
+    if (p2 == 0) {
+      widest = max(widest, n);
+      if (lane == 0) units_then_info[p] = 0;
+      continue;
+    }
+    uint32_t const t = first[p];
+    uint32_t *tab = subtab + (size_t)t * 8;
+    uint32_t const slots = 1u << p2;
+    uint64_t const high = compact ? 0 : ((uint64_t)p << ix.shift);
+    for (uint32_t e = lane; e <= slots; e += 32) {
+      uint32_t pos = n;
+      if (e < slots) {
+        uint64_t const key = high | ((uint64_t)e << (ix.shift - p2));
+        uint32_t a = 0, b = n;
+        while (a < b) {
+          uint32_t const mid = (a + b) >> 1;
+          if (index_key_at(ix, (int64_t)lo + mid) < key) a = mid + 1; else b = mid;
+        }
+        pos = a;
+      }
+      tab[e] = pos;
+    }
+    __syncwarp();
+    for (uint32_t e = lane; e < slots; e += 32) widest = max(widest, tab[e + 1] - tab[e]);
+    __syncwarp();
+    if (lane == 0) units_then_info[p] = ((uint32_t)p2 << 27) | t;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) widest = max(widest, __shfl_xor_sync(0xffffffffu, widest, o));
+  if (lane == 0 && widest != 0) atomicMax(max_window, (unsigned long long)widest);
 }
 
 __global__ void __launch_bounds__(256)
@@ -133,11 +208,50 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
   unsigned long long *d_max = nullptr, h_max = 0;
   CUDA_CHECK(cudaMalloc(&d_max, sizeof h_max));
   CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof h_max, rt.stream));
-  if (ix.d_offsets32 != nullptr)
+  static bool const no_sub = getenv("LS_B200_INDEX_FLAT") != nullptr;  // A/B knob: first level only
+  bool have_sub = false;
+  if (ix.d_offsets32 != nullptr && ix.shift > 0 && !no_sub) {
+    // second level: sizes -> exclusive scan -> fill; dropped when nothing is crowded
+    int64_t const nb = number_offsets - 1;
+    uint32_t *d_units = nullptr, *d_first = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_units, sizeof(uint32_t) * (size_t)(nb + 1)));
+    CUDA_CHECK(cudaMalloc(&d_first, sizeof(uint32_t) * (size_t)(nb + 1)));
+    CUDA_CHECK(cudaMemsetAsync(d_units + nb, 0, sizeof(uint32_t), rt.stream));
+    sub_sizes_kernel<<<blocks, 256, 0, rt.stream>>>(ix.d_offsets32, nb, ix.shift, d_units);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_units, d_first, (int)(nb + 1), rt.stream);
+    void *d_tmp = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_units, d_first, (int)(nb + 1), rt.stream);
+    count_launch(2);
+    uint32_t total_units = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&total_units, d_first + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    cudaFree(d_tmp);
+    // (no 32-bit wrap: a crowded bucket of n states adds at most n / 64 + 1 units and n sums to < 2^32)
+    if (total_units > 0 && total_units < (1u << 27)) {
+      CUDA_CHECK(cudaMalloc(&ix.d_subtab, sizeof(uint32_t) * (size_t)total_units * 8));
+      IndexView v = ix.view();
+      v.sub_info = nullptr;
+      sub_fill_kernel<<<blocks, 256, 0, rt.stream>>>(v, d_first, d_units, ix.d_subtab, d_max);
+      count_launch();
+      ix.d_sub_info = d_units;
+      d_units = nullptr;
+      have_sub = true;
+    }
+    cudaFree(d_units);
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    cudaFree(d_first);
+  }
+  if (have_sub) {
+    // sub_fill_kernel has folded every final window into d_max
+  } else if (ix.d_offsets32 != nullptr) {
     max_bucket_kernel<uint32_t><<<blocks, 256, 0, rt.stream>>>(ix.d_offsets32, number_offsets - 1, d_max);
-  else
+    count_launch();
+  } else {
     max_bucket_kernel<int64_t><<<blocks, 256, 0, rt.stream>>>(ix.d_offsets64, number_offsets - 1, d_max);
-  count_launch();
+    count_launch();
+  }
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof h_max, cudaMemcpyDeviceToHost, rt.stream));
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
@@ -211,6 +325,16 @@ void ls_hs_destroy_state_index_binary_search_kernel_data(ls_hs_state_index_binar
   LSB_CHECK(ix->magic == kIndexMagic, "not an index object of this library");
   std::lock_guard<std::mutex> lock(runtime().mutex);
   delete ix;
+}
+
+int ls_b200_index_info(ls_hs_basis const *basis, int64_t out[4]) {
+  IndexData const *ix = index_of(basis);
+  if (ix == nullptr || out == nullptr) return -1;
+  out[0] = ix->prefix_bits;
+  out[1] = ix->steps;
+  out[2] = ix->d_sub_info != nullptr ? 1 : 0;
+  out[3] = ix->number_states;
+  return 0;
 }
 
 void ls_hs_state_index_binary_search_kernel(ptrdiff_t const batch_size, uint64_t const *spins,

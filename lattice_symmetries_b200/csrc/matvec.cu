@@ -159,6 +159,7 @@ struct MatvecArgs {
   uint32_t *offsets;     // [chunk_rows + 1] exclusive scan of counts
   uint64_t *q_rep;       // [capacity] representative of every matrix element, CSR order
   uint8_t *q_cidx;       // [capacity] index of the minimising character
+  double *vals;          // [capacity] (x2 when complex) fused path: conj(chi) w sign n_j x_j of every matrix element
 };
 
 // Stabiliser character sum of x read straight from the global tables; used on
@@ -396,6 +397,265 @@ orbit_kernel(MatvecArgs const a) {
   }
 }
 
+// ---- fused path: canonicalise, rank and gather in one kernel ------------------------
+// Same walk as orbit_kernel, but the representatives never leave the SM: after the
+// group loop they are transposed back into the warp's slab and every lane ranks and
+// gathers one element per step (kFusedBatch searches in flight per lane), so the
+// memory latency of the lookups hides behind the integer work of the other warps.
+// Output: one value per matrix element, CSR order, summed per row by row_sum_kernel
+// (deterministic order, no atomics).
+constexpr int kFusedBatch = 4;
+constexpr int kOutPitch = 33;                          // u64 words per row of the [k][owner] output slab
+constexpr int kCidxPitch = 36;                         // bytes per row of the [k][owner] character-index slab
+constexpr int kFusedSlabBytes = 32 * kOutPitch * 8;    // >= kWarpSlabBytes
+constexpr int kFusedTsignBytes = 1024 * 2;             // term | sign << 15 per element
+constexpr int kFusedCidxBytes = 32 * kCidxPitch;
+constexpr int kFusedWarpBytes = kFusedSlabBytes + kFusedTsignBytes + kFusedCidxBytes;
+static_assert(kFusedSlabBytes >= kWarpSlabBytes && kFusedWarpBytes % 16 == 0, "slab layout");
+
+template <int NP, bool INV>
+__global__ void __launch_bounds__(kOrbitThreads, 4)
+orbit_gather_kernel(MatvecArgs const a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  AdjointTerms terms;
+  terms.stage(smem, a.off, true);
+  size_t const terms_bytes = (AdjointTerms::bytes(a.off.number_terms, true) + 15) & ~size_t(15);
+  double2 *chars = reinterpret_cast<double2 *>(smem + terms_bytes);
+  for (int j = threadIdx.x; j < a.number_chars; j += blockDim.x) chars[j] = a.cvals[j];
+  __syncthreads();
+
+  int const tid = threadIdx.x;
+  int const lane = tid & 31;
+  unsigned char *slab = smem + terms_bytes + (size_t)a.number_chars * 16 + (size_t)(tid >> 5) * kFusedWarpBytes;
+  uint64_t *stage = reinterpret_cast<uint64_t *>(slab);   // [k][lane]: element 32 * lane + k of the warp
+  uint32_t *planes = reinterpret_cast<uint32_t *>(slab);  // [plane][lane], after the betas have been read
+  uint16_t *tsign = reinterpret_cast<uint16_t *>(slab + kFusedSlabBytes);
+  uint8_t *cslab = slab + kFusedSlabBytes + kFusedTsignBytes;
+  uint32_t const total = a.offsets[a.chunk_rows];
+  uint64_t const warp_q0 = ((uint64_t)blockIdx.x * (kOrbitThreads / 32) + (tid >> 5)) * 1024;
+  if (warp_q0 >= total) return;  // whole warps leave: everything below runs converged
+  uint64_t const warp_q1 = min((uint64_t)total, warp_q0 + 1024);
+  uint64_t const q0 = warp_q0 + 32 * (uint64_t)lane;
+  int const lanes = q0 < total ? (int)min((uint64_t)32, total - q0) : 0;
+
+  // ---- regenerate the warp's betas: lane = row, CSR positions from the offsets -------
+  {
+    int lo_r = 0, hi_r = a.chunk_rows;
+    while (hi_r - lo_r > 1) {
+      int const mid = (lo_r + hi_r) >> 1;
+      if (__ldg(a.offsets + mid) <= (uint32_t)warp_q0) lo_r = mid; else hi_r = mid;
+    }
+    int const T = terms.T;
+    for (int base = lo_r;; base += 32) {
+      int const row = base + lane;
+      uint32_t q = row < a.chunk_rows ? __ldg(a.offsets + row) : 0xffffffffu;
+      bool const mine = row < a.chunk_rows && q < warp_q1;
+      if (!__any_sync(0xffffffffu, mine)) break;
+      if (mine) {
+        uint64_t const alpha = __ldg(a.ix.reps + a.chunk_begin + row);
+        for (int t = 0; t < T; ++t)
+          if ((alpha & terms.m[t]) == terms.l[t]) {
+            if (q >= warp_q0 && q < warp_q1) {
+              unsigned const e = (unsigned)(q - warp_q0);
+              stage[(e & 31u) * 32 + (e >> 5)] = alpha ^ terms.x[t];
+              tsign[e] = (uint16_t)((unsigned)t | ((unsigned)(__popcll(alpha & terms.s[t]) & 1) << 15));
+            }
+            ++q;
+          }
+      }
+    }
+  }
+  __syncwarp();
+  uint32_t r[NP];
+  {
+    uint32_t lo[32], hi[32];
+    uint64_t beta = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < lanes) beta = stage[k * 32 + lane];
+      lo[k] = (uint32_t)beta;  // lanes past the end repeat the last element (or carry zeros)
+      hi[k] = (uint32_t)(beta >> 32);
+    }
+    __syncwarp();  // every lane holds its betas: the slab may now be overwritten by the planes
+    transpose32(lo);
+    if (NP > 32) transpose32(hi);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      r[i] = (i < 32) ? lo[(i < 32) ? i : 0] : hi[(i < 32) ? 0 : i - 32];
+      planes[i * 32 + lane] = r[i];
+    }
+  }
+  __syncwarp();
+  unsigned char const *column = reinterpret_cast<unsigned char const *>(planes + lane);
+  uint32_t idx[kMvIdxPlanes];
+#pragma unroll
+  for (int p = 0; p < kMvIdxPlanes; ++p) idx[p] = 0;
+  int const nbits = a.g.number_bits;
+  int const nidx = a.number_idx_planes;
+  int const G = (a.debug_skip & 1) ? 0 : a.g.number_masks;
+#pragma unroll 1
+  for (int j = 0; j < G; ++j) {
+    uint16_t const *po = c_plane_offset + j * (NP + kPlaneRowExtra);
+    uint32_t top = 0;
+    if (INV) top = *reinterpret_cast<uint32_t const *>(column + po[NP]);
+    uint32_t z[NP];
+    uint32_t lt = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      z[i] = *reinterpret_cast<uint32_t const *>(column + po[i]);
+      if (INV) z[i] ^= (i < NP - 3 || i < nbits) ? top : 0u;  // padding planes stay zero
+      lt = ((z[i] ^ r[i]) & r[i]) | (~(z[i] ^ r[i]) & lt);   // one LOP3: z < r, most significant plane last
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) r[i] = (lt & z[i]) | (~lt & r[i]);
+    if (nidx > 0) {
+      unsigned const ci = po[NP + 1];
+      auto update = [&](int p) {
+        uint32_t const c = 0u - ((ci >> p) & 1u);
+        uint32_t const cf = 0u - ((ci >> (8 + p)) & 1u);
+        uint32_t const nb = INV ? ((top & cf) | (~top & c)) : c;
+        idx[p] = (lt & nb) | (~lt & idx[p]);
+      };
+      update(0);
+      if (nidx > 1) update(1);
+      if (nidx > 2) { update(2); update(3); }
+      if (nidx > 4) { update(4); update(5); update(6); update(7); }
+    }
+  }
+  __syncwarp();  // every lane is done with its plane column: the slab becomes the output slab
+  // back to one state per word: out[k][owner lane] (pitch 33: conflict-free both ways)
+  {
+    uint32_t lo[32], hi[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      lo[i] = (i < NP) ? r[(i < NP) ? i : 0] : 0u;
+      hi[i] = (i + 32 < NP) ? r[(i + 32 < NP) ? i + 32 : 0] : 0u;
+    }
+    transpose32(lo);
+    if (NP > 32) transpose32(hi);
+    uint64_t *out = reinterpret_cast<uint64_t *>(slab);
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      out[k * kOutPitch + lane] = (NP > 32) ? (((uint64_t)hi[k] << 32) | lo[k]) : (uint64_t)lo[k];
+  }
+  if (nidx > 0) {
+    uint32_t info[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) info[i] = (i < kMvIdxPlanes) ? idx[(i < kMvIdxPlanes) ? i : 0] : 0u;
+    transpose32(info);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) cslab[k * kCidxPitch + lane] = (uint8_t)info[k];
+  }
+  __syncwarp();
+
+  // ---- rank + gather: step `it` handles elements it * 32 + lane (coalesced stores) -----
+  uint64_t const *out = reinterpret_cast<uint64_t const *>(slab);
+  int const count = (int)(warp_q1 - warp_q0);
+  IndexView const ix = a.ix;
+  bool const skip_gather = (a.debug_skip & 2) != 0;
+  bool const CPLX = a.complex_vectors != 0;
+#pragma unroll 1
+  for (int it = 0; it < 32 && it * 32 < count; it += kFusedBatch) {
+    uint64_t needle[kFusedBatch];
+    double fr[kFusedBatch], fi[kFusedBatch];
+    bool live[kFusedBatch];
+#pragma unroll
+    for (int u = 0; u < kFusedBatch; ++u) {
+      int const e = (it + u) * 32 + lane;
+      live[u] = e < count && !skip_gather;
+      needle[u] = 0;
+      fr[u] = fi[u] = 0.0;
+      if (live[u]) {
+        needle[u] = out[lane * kOutPitch + it + u];
+        unsigned const ts = tsign[e];
+        double2 w = terms.w[ts & 0x7fffu];
+        if (ts & 0x8000u) { w.x = -w.x; w.y = -w.y; }
+        unsigned const c = nidx > 0 ? cslab[lane * kCidxPitch + it + u] : 0u;
+        double2 const ch = chars[c];
+        fr[u] = ch.x * w.x + ch.y * w.y;  // conj(chi) * w
+        fi[u] = ch.x * w.y - ch.y * w.x;
+      }
+    }
+    int64_t j[kFusedBatch];
+    index_find<kFusedBatch>(ix, needle, live, j);
+#pragma unroll
+    for (int u = 0; u < kFusedBatch; ++u) {
+      int const e = (it + u) * 32 + lane;
+      if (e >= count) continue;
+      double vr = 0.0, vi = 0.0;
+      if (live[u]) {
+        if (j[u] >= 0) {
+          if (CPLX) {
+            double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.xs) + j[u]);
+            vr = fr[u] * xv.x - fi[u] * xv.y;
+            vi = fr[u] * xv.y + fi[u] * xv.x;
+          } else {
+            vr = fr[u] * __ldg(a.xs + j[u]);
+          }
+        } else if (fr[u] != 0.0 || fi[u] != 0.0) {
+          // not in the basis: fine when its norm vanishes, an error otherwise
+          // (DistributedMatrixVector.chpl:127-135)
+          if (stabiliser_sum_global(a.g, needle[u]) > kNormThreshold) atomicOr(a.error_flag, 1);
+        }
+      }
+      if (CPLX) reinterpret_cast<double2 *>(a.vals)[warp_q0 + e] = make_double2(vr, vi);
+      else a.vals[warp_q0 + e] = vr;
+    }
+  }
+}
+
+// Thread per row: sum the row's values in term order, add the diagonal, write y once.
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+row_sum_kernel(MatvecArgs const a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int const TD = a.diag.number_terms;
+  double2 *d_v = reinterpret_cast<double2 *>(smem);
+  uint64_t *d_m = reinterpret_cast<uint64_t *>(d_v + TD);
+  uint64_t *d_r = d_m + TD;
+  uint64_t *d_s = d_r + TD;
+  for (int t = threadIdx.x; t < TD; t += blockDim.x) {
+    d_m[t] = a.diag.m[t];
+    d_r[t] = a.diag.r[t];
+    d_s[t] = a.diag.s[t];
+    d_v[t] = a.diag.v[t];
+  }
+  __syncthreads();
+  int const r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.chunk_rows) return;
+  int64_t const row = a.chunk_begin + r;
+  uint64_t const alpha = __ldg(a.ix.reps + row);
+  uint32_t const qa = __ldg(a.offsets + r), qb = __ldg(a.offsets + r + 1);
+  double acc_r = 0.0, acc_i = 0.0;
+  for (uint32_t q = qa; q < qb; ++q) {
+    if (CPLX) {
+      double2 const v = __ldcs(reinterpret_cast<double2 const *>(a.vals) + q);
+      acc_r += v.x;
+      acc_i += v.y;
+    } else {
+      acc_r += __ldcs(a.vals + q);
+    }
+  }
+  double dr = 0.0, di = 0.0;
+  for (int k = 0; k < TD; ++k)
+    if ((alpha & d_m[k]) == d_r[k]) {
+      double const sign = (__popcll(alpha & d_s[k]) & 1) ? -1.0 : 1.0;
+      dr += sign * d_v[k].x;
+      di += sign * d_v[k].y;
+    }
+  double const ni = a.norms != nullptr ? __ldg(a.norms + row) : 1.0;
+  int64_t const out = row - a.row_begin;
+  if (CPLX) {
+    double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.x) + row);
+    double2 res;
+    res.x = acc_r / ni + (dr * xv.x - di * xv.y);
+    res.y = acc_i / ni + (dr * xv.y + di * xv.x);
+    reinterpret_cast<double2 *>(a.y)[out] = res;
+  } else {
+    a.y[out] = acc_r / ni + dr * __ldg(a.x + row);  // kernels/reference.c:84-91 uses creal(v) only
+  }
+}
+
 // Scalar fallback of orbit_kernel: thread per row, Benes walk per element.
 __global__ void __launch_bounds__(128)
 orbit_scalar_kernel(MatvecArgs const a) {
@@ -585,27 +845,28 @@ void ensure_norms(IndexData &ix, GroupData const &g);
 
 using OrbitKernel = void (*)(MatvecArgs);
 template <int NP>
-static OrbitKernel pick_orbit_inv(bool inv) {
+static OrbitKernel pick_orbit_inv(bool inv, bool fused) {
+  if (fused) return inv ? orbit_gather_kernel<NP, true> : orbit_gather_kernel<NP, false>;
   return inv ? orbit_kernel<NP, true> : orbit_kernel<NP, false>;
 }
-static OrbitKernel pick_orbit_kernel(int np, bool inv) {
+static OrbitKernel pick_orbit_kernel(int np, bool inv, bool fused) {
   switch (np) {
-    case 4: return pick_orbit_inv<4>(inv);
-    case 8: return pick_orbit_inv<8>(inv);
-    case 12: return pick_orbit_inv<12>(inv);
-    case 16: return pick_orbit_inv<16>(inv);
-    case 20: return pick_orbit_inv<20>(inv);
-    case 24: return pick_orbit_inv<24>(inv);
-    case 28: return pick_orbit_inv<28>(inv);
-    case 32: return pick_orbit_inv<32>(inv);
-    case 36: return pick_orbit_inv<36>(inv);
-    case 40: return pick_orbit_inv<40>(inv);
-    case 44: return pick_orbit_inv<44>(inv);
-    case 48: return pick_orbit_inv<48>(inv);
-    case 52: return pick_orbit_inv<52>(inv);
-    case 56: return pick_orbit_inv<56>(inv);
-    case 60: return pick_orbit_inv<60>(inv);
-    case 64: return pick_orbit_inv<64>(inv);
+    case 4: return pick_orbit_inv<4>(inv, fused);
+    case 8: return pick_orbit_inv<8>(inv, fused);
+    case 12: return pick_orbit_inv<12>(inv, fused);
+    case 16: return pick_orbit_inv<16>(inv, fused);
+    case 20: return pick_orbit_inv<20>(inv, fused);
+    case 24: return pick_orbit_inv<24>(inv, fused);
+    case 28: return pick_orbit_inv<28>(inv, fused);
+    case 32: return pick_orbit_inv<32>(inv, fused);
+    case 36: return pick_orbit_inv<36>(inv, fused);
+    case 40: return pick_orbit_inv<40>(inv, fused);
+    case 44: return pick_orbit_inv<44>(inv, fused);
+    case 48: return pick_orbit_inv<48>(inv, fused);
+    case 52: return pick_orbit_inv<52>(inv, fused);
+    case 56: return pick_orbit_inv<56>(inv, fused);
+    case 60: return pick_orbit_inv<60>(inv, fused);
+    case 64: return pick_orbit_inv<64>(inv, fused);
   }
   return nullptr;
 }
@@ -632,6 +893,7 @@ struct MatvecScratch {
   DeviceBuffer<uint32_t> counts, offsets;
   DeviceBuffer<uint64_t> q_rep;
   DeviceBuffer<uint8_t> q_cidx;
+  DeviceBuffer<double> vals;
   DeviceBuffer<unsigned char> scan_tmp;
   size_t scan_tmp_bytes = 0;
   int *d_error = nullptr;
@@ -741,7 +1003,15 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   size_t const gather_smem = ((AdjointTerms::bytes(T, true) + 15) & ~size_t(15)) + (size_t)a.diag.number_terms * 40 +
                              (size_t)a.number_chars * 16;
   size_t const count_smem = AdjointTerms::bytes(T, false);
-  size_t const orbit_smem = ((count_smem + 15) & ~size_t(15)) + (size_t)(kOrbitThreads / 32) * kWarpSlabBytes;
+  size_t orbit_smem = ((count_smem + 15) & ~size_t(15)) + (size_t)(kOrbitThreads / 32) * kWarpSlabBytes;
+  size_t const fused_smem = ((AdjointTerms::bytes(T, true) + 15) & ~size_t(15)) + (size_t)a.number_chars * 16 +
+                            (size_t)(kOrbitThreads / 32) * kFusedWarpBytes;
+  size_t const sum_smem = (size_t)a.diag.number_terms * 40;
+  // fused = canonicalise + rank + gather in one kernel, then a row sum; LS_B200_MATVEC=unfused keeps the
+  // three-kernel pipeline (orbit -> q_rep/q_cidx -> gather) for A/B measurements
+  bool fused = a.mode == kModeGroup && fused_smem <= rt.smem_optin && sum_smem <= rt.smem_optin;
+  if (char const *env = getenv("LS_B200_MATVEC")) fused = fused && strcmp(env, "unfused") != 0;
+  if (fused) orbit_smem = fused_smem;
   LSB_CHECK(gather_smem <= rt.smem_optin && orbit_smem <= rt.smem_optin,
             "operator / symmetry tables do not fit in shared memory");
 
@@ -756,8 +1026,12 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     capacity = chunk_rows * T;
     a.counts = sc.counts.reserve((size_t)chunk_rows + 1);
     a.offsets = sc.offsets.reserve((size_t)chunk_rows + 1);
-    a.q_rep = sc.q_rep.reserve((size_t)capacity + 32);
-    a.q_cidx = sc.q_cidx.reserve((size_t)capacity + 32);
+    if (fused) {
+      a.vals = sc.vals.reserve(((size_t)capacity + 32) * (complex_vectors ? 2 : 1));
+    } else {
+      a.q_rep = sc.q_rep.reserve((size_t)capacity + 32);
+      a.q_cidx = sc.q_cidx.reserve((size_t)capacity + 32);
+    }
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, a.counts, a.offsets, (int)(chunk_rows + 1), rt.stream);
     if (tmp > sc.scan_tmp_bytes) {
@@ -765,7 +1039,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
       sc.scan_tmp_bytes = sc.scan_tmp.capacity;
     }
     if (a.mode == kModeGroup) {
-      orbit = pick_orbit_kernel(np, inv);
+      orbit = pick_orbit_kernel(np, inv, fused);
       LSB_CHECK(orbit != nullptr, "unsupported number of bits");
       allow_dynamic_smem(orbit, orbit_smem);
     } else {
@@ -778,6 +1052,8 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   auto gather = queued ? (complex_vectors ? gather_kernel<true, true> : gather_kernel<true, false>)
                        : (complex_vectors ? gather_kernel<false, true> : gather_kernel<false, false>);
   allow_dynamic_smem(gather, gather_smem);
+  auto row_sum = complex_vectors ? row_sum_kernel<true> : row_sum_kernel<false>;
+  if (fused) allow_dynamic_smem(row_sum, sum_smem);
 
   for (int64_t begin = row_begin; begin < row_end; begin += chunk_rows) {
     int64_t const nrows = std::min(chunk_rows, row_end - begin);
@@ -806,7 +1082,10 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
       sc.spans.emplace_back(sc.events_used, 1);
       CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
     }
-    gather<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
+    if (fused && queued)
+      row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, rt.stream>>>(a);
+    else
+      gather<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
     count_launch();
     if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
     CUDA_CHECK(cudaGetLastError());

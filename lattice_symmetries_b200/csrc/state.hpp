@@ -57,6 +57,8 @@ struct IndexData {
   int64_t *d_offsets64 = nullptr;
   uint16_t *d_lows16 = nullptr;  // low `shift` bits of every representative (shift <= 16)
   uint32_t *d_lows32 = nullptr;  // (16 < shift <= 32)
+  uint32_t *d_sub_info = nullptr;  // second-level tables of the crowded buckets (IndexView)
+  uint32_t *d_subtab = nullptr;
   double *d_norms = nullptr;  // state_info norms of the representatives (lazy)
 
   IndexView view() const;

@@ -45,7 +45,15 @@ struct IndexView {
   int shift;                  // number_bits - prefix_bits
   int identity;               // state_index_is_identity: index == state
   uint64_t number_buckets;    // 2^prefix
-  int steps;                  // bit_length(largest bucket): trip count of the branchless search
+  int steps;                  // bit_length(largest final window): trip count of the branchless search
+  // Second level for crowded buckets (fixed-Hamming-weight representatives pile up
+  // behind long runs of leading zeros: a few prefix buckets hold thousands of states
+  // while the average holds eight).  sub_info[p] == 0: bucket p is searched directly;
+  // otherwise (p2 << 27 | t): the next p2 bits below the prefix select entry k2 of the
+  // table at subtab + 8 t, whose entries k2, k2 + 1 bracket the window relative to the
+  // bucket's start.
+  uint32_t const *sub_info;   // [2^prefix] or nullptr
+  uint32_t const *subtab;
 };
 
 // Operator terms, structure-of-arrays on the device
@@ -86,6 +94,17 @@ __device__ __forceinline__ void index_window(IndexView const &ix, uint64_t needl
     }
   } else {
     n = ix.number_states;
+  }
+  if (ix.sub_info != nullptr && p < ix.number_buckets) {
+    uint32_t const s = __ldg(ix.sub_info + p);
+    if (s != 0) {
+      int const p2 = (int)(s >> 27);
+      uint64_t const k2 = (needle >> (ix.shift - p2)) & ((uint64_t(1) << p2) - 1);
+      uint32_t const *t = ix.subtab + (size_t)(s & 0x7ffffffu) * 8 + k2;
+      uint32_t const r0 = __ldg(t);
+      lo += (int64_t)r0;
+      n = (int64_t)(__ldg(t + 1) - r0);
+    }
   }
 }
 

@@ -222,6 +222,33 @@ def test_state_index(oracle, built, name):
         assert np.array_equal(got, ref)
 
 
+def test_state_index_crowded_buckets(oracle):
+    """Fixed-Hamming-weight representatives pile up behind leading zeros: a basis large
+    enough for the prefix table to grow a second level (index.cu sub-tables)."""
+    from lattice_symmetries_b200 import lattices as L
+    p = _model_problem(L.heisenberg_chain(26))
+    basis = p.product_basis()
+    basis.build()
+    reps = np.asarray(basis.states)
+    info = basis.index_info()
+    assert info["two_level"] and info["states"] == reps.shape[0] and info["steps"] <= 9, info
+    assert np.all(reps[1:] > reps[:-1])
+    assert np.array_equal(basis.index(reps), np.arange(reps.shape[0]))
+    rng = np.random.default_rng(17)
+    absent = reps[rng.integers(0, reps.shape[0], size=20000)] ^ np.uint64(2)
+    got = basis.index(absent)
+    pos = np.searchsorted(reps, absent)
+    pos[pos == reps.shape[0]] = 0
+    want = np.where(reps[pos] == absent, pos, -1)
+    assert np.array_equal(got, want)
+    # an unprojected fixed-weight basis is the extreme case: every candidate is present
+    full = H.Problem("chain22_full", 22, L.heisenberg_chain(22).expression, hamming_weight=11).product_basis()
+    full.build()
+    states = np.asarray(full.states)
+    assert np.array_equal(full.index(states), np.arange(states.shape[0]))
+    assert np.all(full.index(states[:5000] ^ np.uint64(1)) == -1)
+
+
 # ---- (a-5, a-6) rows of H ---------------------------------------------------------------------
 @pytest.mark.parametrize("name", ALL)
 def test_operator_apply(oracle, built, name):
@@ -279,6 +306,39 @@ def test_matvec_scalar_variant_agrees(oracle, built, name, monkeypatch):
     monkeypatch.setenv("LS_B200_MATVEC", "scalar")
     y1 = op.apply_to_state_vector(x)
     assert _rel_err(y1, y0) < MATVEC_RTOL
+
+
+@pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome24_c2v_inv", "kagome18_c2"])
+@pytest.mark.parametrize("chunk", [None, "4096"])
+def test_matvec_pipeline_variants_agree(oracle, built, name, chunk, monkeypatch):
+    """Fused (canonicalise + rank + gather in one kernel, default) vs the three-kernel
+    pipeline, also with tiny row chunks so that warps straddle chunk ends."""
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal(reps.shape[0])
+    y0 = op.apply_to_state_vector(x)
+    if chunk is not None:
+        monkeypatch.setenv("LS_B200_MV_CHUNK", chunk)
+        y1 = op.apply_to_state_vector(x)
+        assert np.array_equal(y1, y0)  # chunking never changes the summation order
+    monkeypatch.setenv("LS_B200_MATVEC", "unfused")
+    y2 = op.apply_to_state_vector(x)
+    assert _rel_err(y2, y0) < MATVEC_RTOL
+
+
+@pytest.mark.parametrize("name", ["ladder_2x8_dm", "kagome12_complex"])
+def test_matvec_complex_pipeline_variants_agree(oracle, built, name, monkeypatch):
+    from lattice_symmetries_b200 import _lib
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    dim = reps.shape[0]
+    rng = np.random.default_rng(8)
+    d_x = _lib.DeviceArray.from_numpy(rng.standard_normal(dim) + 1j * rng.standard_normal(dim))
+    d_y = _lib.DeviceArray(dim, np.complex128)
+    op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
+    y0 = d_y.numpy().copy()
+    monkeypatch.setenv("LS_B200_MATVEC", "unfused")
+    op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
+    assert _rel_err(d_y.numpy(), y0) < MATVEC_RTOL
 
 
 @pytest.mark.parametrize("name", ["chain16_symm", "kagome18_c2", "hubbard_2x4"])
