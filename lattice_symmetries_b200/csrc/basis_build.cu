@@ -317,7 +317,7 @@ build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint6
   int const nbits = g.number_bits;
 #pragma unroll 1
   for (int j = 0; j < G; ++j) {
-    uint16_t const *off = c_plane_offset + j * (NP + kPlaneRowExtra);
+    PlaneRow<NP> const off(j);
     // With spin inversion both y and ~y must be >= x; the smaller of the two is
     // z = y ^ top(y) (top = the most significant live bit decides their order),
     // so one comparison per plane covers both images.

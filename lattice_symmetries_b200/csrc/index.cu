@@ -85,8 +85,8 @@ max_bucket_kernel(T const *__restrict__ offsets, int64_t number_buckets, unsigne
 }
 
 // ---- second level for crowded buckets ---------------------------------------------
-constexpr int kDenseBucket = 32;  // buckets with more entries get a sub-table ...
-constexpr int kSubTargetLog2 = 4; // ... of about 2^4 entries per slot
+constexpr int kDenseBucket = 15;  // buckets with more entries get a sub-table ...
+constexpr int kSubTargetLog2 = 3; // ... of about 2^3 entries per slot
 constexpr int kMaxSubBits = 24;
 
 __device__ __forceinline__ int sub_bits(uint32_t n, int shift) {

@@ -44,6 +44,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <type_traits>
 
 #include "bitslice.cuh"
 #include "plane_table.cuh"
@@ -325,7 +326,7 @@ orbit_kernel(MatvecArgs const a) {
   int const G = (a.debug_skip & 1) ? 0 : a.g.number_masks;
 #pragma unroll 1
   for (int j = 0; j < G; ++j) {
-    uint16_t const *po = c_plane_offset + j * (NP + kPlaneRowExtra);
+    PlaneRow<NP> const po(j);
     // z = min(y, ~y) = y ^ top(y) when spin inversion is present (see basis_build.cu)
     uint32_t top = 0;
     if (INV) top = *reinterpret_cast<uint32_t const *>(column + po[NP]);
@@ -404,7 +405,7 @@ orbit_kernel(MatvecArgs const a) {
 // memory latency of the lookups hides behind the integer work of the other warps.
 // Output: one value per matrix element, CSR order, summed per row by row_sum_kernel
 // (deterministic order, no atomics).
-constexpr int kFusedBatch = 4;
+constexpr int kFusedBatch = 8;
 constexpr int kOutPitch = 33;                          // u64 words per row of the [k][owner] output slab
 constexpr int kCidxPitch = 36;                         // bytes per row of the [k][owner] character-index slab
 constexpr int kFusedSlabBytes = 32 * kOutPitch * 8;    // >= kWarpSlabBytes
@@ -413,9 +414,79 @@ constexpr int kFusedCidxBytes = 32 * kCidxPitch;
 constexpr int kFusedWarpBytes = kFusedSlabBytes + kFusedTsignBytes + kFusedCidxBytes;
 static_assert(kFusedSlabBytes >= kWarpSlabBytes && kFusedWarpBytes % 16 == 0, "slab layout");
 
+// Last phase of orbit_gather_kernel: every lane ranks kFusedBatch representatives at a
+// time (independent searches in flight), gathers n_j x_j, applies conj(chi) w sign and
+// stores the values in CSR order.  Low = void: the generic 64-bit index path.
+struct FusedLookup {
+  MatvecArgs const &a;
+  unsigned char const *slab;
+  uint16_t const *tsign;
+  uint8_t const *cslab;
+  double2 const *chars;
+  double2 const *tw;
+  uint64_t warp_q0;
+  int count;
+  int lane;
+
+  template <class Low>
+  __device__ __forceinline__ void run() const {
+    uint64_t const *out = reinterpret_cast<uint64_t const *>(slab);
+    bool const skip_gather = (a.debug_skip & 2) != 0;
+    bool const cplx = a.complex_vectors != 0;
+    int const nidx = a.number_idx_planes;
+#pragma unroll 1
+    for (int it = 0; it * 32 < count; it += kFusedBatch) {
+      uint64_t needle[kFusedBatch];
+      bool live[kFusedBatch];
+#pragma unroll
+      for (int u = 0; u < kFusedBatch; ++u) {
+        live[u] = (it + u) * 32 + lane < count && !skip_gather;
+        needle[u] = live[u] ? out[lane * kOutPitch + it + u] : 0;
+      }
+      int64_t j[kFusedBatch];
+      if constexpr (std::is_void<Low>::value) index_find<kFusedBatch>(a.ix, needle, live, j);
+      else index_find32<Low, kFusedBatch>(a.ix, needle, live, j);
+      double2 xv[kFusedBatch];
+#pragma unroll
+      for (int u = 0; u < kFusedBatch; ++u) {
+        xv[u] = make_double2(0.0, 0.0);
+        if (j[u] >= 0) {
+          if (cplx) xv[u] = __ldg(reinterpret_cast<double2 const *>(a.xs) + j[u]);
+          else xv[u].x = __ldg(a.xs + j[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kFusedBatch; ++u) {
+        int const e = (it + u) * 32 + lane;
+        if (e >= count) continue;
+        double vr = 0.0, vi = 0.0;
+        if (live[u]) {
+          unsigned const ts = tsign[e];
+          double2 w = tw[ts & 0x7fffu];
+          if (ts & 0x8000u) { w.x = -w.x; w.y = -w.y; }
+          unsigned const c = nidx > 0 ? cslab[lane * kCidxPitch + it + u] : 0u;
+          double2 const ch = chars[c];
+          double const fr = ch.x * w.x + ch.y * w.y;  // conj(chi) * w
+          double const fi = ch.x * w.y - ch.y * w.x;
+          if (j[u] >= 0) {
+            vr = fr * xv[u].x - fi * xv[u].y;
+            vi = fr * xv[u].y + fi * xv[u].x;
+          } else if (fr != 0.0 || fi != 0.0) {
+            // not in the basis: fine when its norm vanishes, an error otherwise
+            // (DistributedMatrixVector.chpl:127-135)
+            if (stabiliser_sum_global(a.g, needle[u]) > kNormThreshold) atomicOr(a.error_flag, 1);
+          }
+        }
+        if (cplx) reinterpret_cast<double2 *>(a.vals)[warp_q0 + e] = make_double2(vr, vi);
+        else a.vals[warp_q0 + e] = vr;
+      }
+    }
+  }
+};
+
 template <int NP, bool INV>
 __global__ void __launch_bounds__(kOrbitThreads, 4)
-orbit_gather_kernel(MatvecArgs const a) {
+orbit_gather_kernel(__grid_constant__ MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
   AdjointTerms terms;
   terms.stage(smem, a.off, true);
@@ -495,7 +566,7 @@ orbit_gather_kernel(MatvecArgs const a) {
   int const G = (a.debug_skip & 1) ? 0 : a.g.number_masks;
 #pragma unroll 1
   for (int j = 0; j < G; ++j) {
-    uint16_t const *po = c_plane_offset + j * (NP + kPlaneRowExtra);
+    PlaneRow<NP> const po(j);
     uint32_t top = 0;
     if (INV) top = *reinterpret_cast<uint32_t const *>(column + po[NP]);
     uint32_t z[NP];
@@ -549,58 +620,13 @@ orbit_gather_kernel(MatvecArgs const a) {
   __syncwarp();
 
   // ---- rank + gather: step `it` handles elements it * 32 + lane (coalesced stores) -----
-  uint64_t const *out = reinterpret_cast<uint64_t const *>(slab);
-  int const count = (int)(warp_q1 - warp_q0);
-  IndexView const ix = a.ix;
-  bool const skip_gather = (a.debug_skip & 2) != 0;
-  bool const CPLX = a.complex_vectors != 0;
-#pragma unroll 1
-  for (int it = 0; it < 32 && it * 32 < count; it += kFusedBatch) {
-    uint64_t needle[kFusedBatch];
-    double fr[kFusedBatch], fi[kFusedBatch];
-    bool live[kFusedBatch];
-#pragma unroll
-    for (int u = 0; u < kFusedBatch; ++u) {
-      int const e = (it + u) * 32 + lane;
-      live[u] = e < count && !skip_gather;
-      needle[u] = 0;
-      fr[u] = fi[u] = 0.0;
-      if (live[u]) {
-        needle[u] = out[lane * kOutPitch + it + u];
-        unsigned const ts = tsign[e];
-        double2 w = terms.w[ts & 0x7fffu];
-        if (ts & 0x8000u) { w.x = -w.x; w.y = -w.y; }
-        unsigned const c = nidx > 0 ? cslab[lane * kCidxPitch + it + u] : 0u;
-        double2 const ch = chars[c];
-        fr[u] = ch.x * w.x + ch.y * w.y;  // conj(chi) * w
-        fi[u] = ch.x * w.y - ch.y * w.x;
-      }
-    }
-    int64_t j[kFusedBatch];
-    index_find<kFusedBatch>(ix, needle, live, j);
-#pragma unroll
-    for (int u = 0; u < kFusedBatch; ++u) {
-      int const e = (it + u) * 32 + lane;
-      if (e >= count) continue;
-      double vr = 0.0, vi = 0.0;
-      if (live[u]) {
-        if (j[u] >= 0) {
-          if (CPLX) {
-            double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.xs) + j[u]);
-            vr = fr[u] * xv.x - fi[u] * xv.y;
-            vi = fr[u] * xv.y + fi[u] * xv.x;
-          } else {
-            vr = fr[u] * __ldg(a.xs + j[u]);
-          }
-        } else if (fr[u] != 0.0 || fi[u] != 0.0) {
-          // not in the basis: fine when its norm vanishes, an error otherwise
-          // (DistributedMatrixVector.chpl:127-135)
-          if (stabiliser_sum_global(a.g, needle[u]) > kNormThreshold) atomicOr(a.error_flag, 1);
-        }
-      }
-      if (CPLX) reinterpret_cast<double2 *>(a.vals)[warp_q0 + e] = make_double2(vr, vi);
-      else a.vals[warp_q0 + e] = vr;
-    }
+  FusedLookup const L{a, slab, tsign, cslab, chars, terms.w, warp_q0, (int)(warp_q1 - warp_q0), lane};
+  if (a.ix.offsets32 != nullptr && !a.ix.identity) {
+    if (a.ix.lows16 != nullptr) L.template run<uint16_t>();
+    else if (a.ix.lows32 != nullptr) L.template run<uint32_t>();
+    else L.template run<uint64_t>();
+  } else {
+    L.template run<void>();
   }
 }
 

@@ -19,41 +19,63 @@
 
 namespace lsb {
 
-constexpr int kMaxPermTable = 24576;  // uint16 entries (48 KB of constant memory)
-static __constant__ uint16_t c_plane_offset[kMaxPermTable];
+constexpr int kMaxPermTable = 15360;  // uint32 entries (60 KB of constant memory), read as uint4 (LDCU.128)
+static __constant__ uint4 c_plane_rows[kMaxPermTable / 4];
 static uint64_t g_plane_table_owner = 0;  // GroupData::id, NP and block size currently resident
 
-// Row j of the table (kPlaneRowExtra + np entries):
+// Row j of the table (kPlaneRowExtra + np 32-bit entries, 16-byte aligned):
 //   [0, np)   byte offset of the source plane of output plane i
 //   [np]      byte offset of the source plane of the TOP live bit (number_bits - 1):
 //             the spin-flipped image ~y is smaller than y iff that bit of y is set
 //   [np + 1]  character indices of element j (GroupData::cinfo)
+//   [np + 2], [np + 3]  padding
 // Planes are padded to a multiple of four (np >= number_bits); padding planes
 // map onto themselves.  Returns false when the table does not fit.
-constexpr int kPlaneRowExtra = 2;
+constexpr int kPlaneRowExtra = 4;
 static inline bool upload_plane_offsets(GroupData const &g, int np, int threads_per_block) {
   size_t const stride = (size_t)np + kPlaneRowExtra;
   size_t const entries = (size_t)g.number_masks * stride;
   if (entries > (size_t)kMaxPermTable) return false;
-  if ((size_t)(np - 1) * (size_t)threads_per_block * 4 > 0xffffu) return false;
+  if ((np & 3) != 0) return false;
   uint64_t const tag = (g.id << 20) | ((uint64_t)np << 12) | (uint64_t)threads_per_block;
   if (g_plane_table_owner == tag) return true;
-  std::vector<uint16_t> table(entries);
+  std::vector<uint32_t> table(entries, 0u);
   for (int j = 0; j < g.number_masks; ++j) {
     for (int i = 0; i < np; ++i) {
       int const src = i < g.number_bits ? g.perm[(size_t)j * g.number_bits + i] : i;
-      table[(size_t)j * stride + i] = (uint16_t)(src * threads_per_block * 4);
+      table[(size_t)j * stride + i] = (uint32_t)(src * threads_per_block * 4);
     }
     int const top = g.number_bits > 0 ? g.perm[(size_t)j * g.number_bits + (g.number_bits - 1)] : 0;
-    table[(size_t)j * stride + np] = (uint16_t)(top * threads_per_block * 4);
-    table[(size_t)j * stride + np + 1] = g.cinfo.empty() ? (uint16_t)0 : g.cinfo[(size_t)j];
+    table[(size_t)j * stride + np] = (uint32_t)(top * threads_per_block * 4);
+    table[(size_t)j * stride + np + 1] = g.cinfo.empty() ? 0u : (uint32_t)g.cinfo[(size_t)j];
   }
-  CUDA_CHECK(cudaMemcpyToSymbolAsync(c_plane_offset, table.data(), entries * sizeof(uint16_t), 0,
+  CUDA_CHECK(cudaMemcpyToSymbolAsync(c_plane_rows, table.data(), entries * sizeof(uint32_t), 0,
                                      cudaMemcpyHostToDevice, runtime().stream));
   CUDA_CHECK(cudaStreamSynchronize(runtime().stream));  // table is a stack temporary
   g_plane_table_owner = tag;
   return true;
 }
+
+#if defined(__CUDACC__)
+// Row j of the table in (uniform) registers: NP + kPlaneRowExtra offsets, fetched
+// four at a time.  j must be warp-uniform.
+template <int NP>
+struct PlaneRow {
+  uint32_t off[NP + kPlaneRowExtra];
+  __device__ __forceinline__ explicit PlaneRow(int j) {
+    uint4 const *row = c_plane_rows + (size_t)j * ((NP + kPlaneRowExtra) / 4);
+#pragma unroll
+    for (int q = 0; q < (NP + kPlaneRowExtra) / 4; ++q) {
+      uint4 const v = row[q];
+      off[4 * q] = v.x;
+      off[4 * q + 1] = v.y;
+      off[4 * q + 2] = v.z;
+      off[4 * q + 3] = v.w;
+    }
+  }
+  __device__ __forceinline__ uint32_t operator[](int i) const { return off[i]; }
+};
+#endif
 
 // True when element 0 is the identity with character exactly 1 (always the
 // case for groups built by Group.hs:174-183, whose ascending order puts the

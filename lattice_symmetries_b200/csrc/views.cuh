@@ -154,6 +154,61 @@ __device__ __forceinline__ void index_find(IndexView const &ix, uint64_t const (
   }
 }
 
+// Lean variant for the hot kernels: 32-bit positions (offsets32 tables), keys of a
+// fixed type Low (uint16_t / uint32_t low bits, or uint64_t full states).  Upper-bound
+// search by descending powers of two that carries the last key <= needle along, so the
+// membership test needs no extra load; `steps` probes, each a predicated load.
+template <class Low> __device__ __forceinline__ Low const *index_keys(IndexView const &ix);
+template <> __device__ __forceinline__ uint16_t const *index_keys<uint16_t>(IndexView const &ix) { return ix.lows16; }
+template <> __device__ __forceinline__ uint32_t const *index_keys<uint32_t>(IndexView const &ix) { return ix.lows32; }
+template <> __device__ __forceinline__ uint64_t const *index_keys<uint64_t>(IndexView const &ix) { return ix.reps; }
+
+template <class Low, int B>
+__device__ __forceinline__ void index_find32(IndexView const &ix, uint64_t const (&needle)[B], bool const (&live)[B],
+                                             int64_t (&found)[B]) {
+  Low const *__restrict__ keys = index_keys<Low>(ix);
+  uint32_t lo[B], pos[B], end[B];
+  Low key[B], val[B];
+#pragma unroll
+  for (int u = 0; u < B; ++u) {
+    uint64_t const p = needle[u] >> ix.shift;
+    uint32_t l = 0, n = 0;
+    if (live[u] && p < ix.number_buckets) {
+      l = __ldg(ix.offsets32 + p);
+      n = __ldg(ix.offsets32 + p + 1) - l;
+      uint32_t const s = ix.sub_info != nullptr ? __ldg(ix.sub_info + p) : 0u;
+      if (s != 0) {
+        int const p2 = (int)(s >> 27);
+        uint32_t const k2 = (uint32_t)(needle[u] >> (ix.shift - p2)) & ((1u << p2) - 1u);
+        uint32_t const *t = ix.subtab + (size_t)(s & 0x7ffffffu) * 8 + k2;
+        uint32_t const r0 = __ldg(t);
+        l += r0;
+        n = __ldg(t + 1) - r0;
+      }
+    }
+    lo[u] = pos[u] = l;
+    end[u] = l + n;
+    key[u] = sizeof(Low) < 8 ? (Low)(needle[u] & ix.low_mask) : (Low)needle[u];
+    val[u] = 0;
+  }
+#pragma unroll 1
+  for (uint32_t s = ix.steps > 0 ? (1u << (ix.steps - 1)) : 0u; s != 0; s >>= 1) {
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      uint32_t const cand = pos[u] + s;
+      if (cand <= end[u]) {
+        Low const v = __ldg(keys + (cand - 1));
+        if (v <= key[u]) {
+          pos[u] = cand;
+          val[u] = v;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < B; ++u) found[u] = (pos[u] > lo[u] && val[u] == key[u]) ? (int64_t)(pos[u] - 1) : (int64_t)-1;
+}
+
 __device__ __forceinline__ int64_t state_index(IndexView const &ix, uint64_t needle) {
   uint64_t const needles[1] = {needle};
   bool const live[1] = {true};

@@ -17,9 +17,7 @@ run() { echo "== $1"; shift; env "$@" timeout 300 python tools/profile_workload.
 run "default (fused, two-level index)" A=1
 run "fused, flat index" LS_B200_INDEX_FLAT=1
 run "fused, no gather (orbit only)" LS_B200_MV_SKIP=2
-run "fused, no orbit (gather only)" LS_B200_MV_SKIP=1
 run "unfused, two-level index" LS_B200_MATVEC=unfused
-run "unfused, flat index" LS_B200_MATVEC=unfused LS_B200_INDEX_FLAT=1
 } > $OUT/ab_$WL.txt 2>&1
 cat $OUT/ab_$WL.txt
 unset LS_B200_PROFILE
