@@ -320,14 +320,23 @@ build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint6
     PlaneRow<NP> const off(j);
     // With spin inversion both y and ~y must be >= x; the smaller of the two is
     // z = y ^ top(y) (top = the most significant live bit decides their order),
-    // so one comparison per plane covers both images.
-    uint32_t top = 0;
-    if (INV) top = *reinterpret_cast<uint32_t const *>(column + off[NP]);
+    // so one comparison per plane covers both images.  The table rows are sorted
+    // by the source of that top bit (plane_table.cuh): the thread's column holds
+    // the planes already XOR-ed with the current flip plane and is re-targeted in
+    // place only when the class changes (every |G| / number_bits rows).
+    if (INV) {
+      uint32_t const ro = off[NP + 2];
+      if (ro != kNoRetarget) {
+        uint32_t const d = *reinterpret_cast<uint32_t const *>(column + ro);
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+          if (i < NP - 3 || i < nbits) planes[i * kBuildThreads + tid] ^= d;  // padding planes stay zero
+      }
+    }
     uint32_t lt = 0, eq = 0xffffffffu;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      uint32_t z = *reinterpret_cast<uint32_t const *>(column + off[i]);
-      if (INV) z ^= (i < NP - 3 || i < nbits) ? top : 0u;  // padding planes stay zero
+      uint32_t const z = *reinterpret_cast<uint32_t const *>(column + off[i]);
       cmp_step(z, xr[i], lt, eq);
     }
     alive &= ~lt;

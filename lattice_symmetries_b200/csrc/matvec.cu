@@ -405,7 +405,10 @@ orbit_kernel(MatvecArgs const a) {
 // memory latency of the lookups hides behind the integer work of the other warps.
 // Output: one value per matrix element, CSR order, summed per row by row_sum_kernel
 // (deterministic order, no atomics).
-constexpr int kFusedBatch = 8;
+#ifndef LS_FUSED_BATCH
+#define LS_FUSED_BATCH 8
+#endif
+constexpr int kFusedBatch = LS_FUSED_BATCH;  // independent searches in flight per lane
 constexpr int kOutPitch = 33;                          // u64 words per row of the [k][owner] output slab
 constexpr int kCidxPitch = 36;                         // bytes per row of the [k][owner] character-index slab
 constexpr int kFusedSlabBytes = 32 * kOutPitch * 8;    // >= kWarpSlabBytes
@@ -564,17 +567,28 @@ orbit_gather_kernel(__grid_constant__ MatvecArgs const a) {
   int const nbits = a.g.number_bits;
   int const nidx = a.number_idx_planes;
   int const G = (a.debug_skip & 1) ? 0 : a.g.number_masks;
+  uint32_t top = 0;  // flip plane of the current class of elements: bit (number_bits - 1) of their images
 #pragma unroll 1
   for (int j = 0; j < G; ++j) {
     PlaneRow<NP> const po(j);
-    uint32_t top = 0;
-    if (INV) top = *reinterpret_cast<uint32_t const *>(column + po[NP]);
+    // z = min(y, ~y) = y ^ top(y) when spin inversion is present (see basis_build.cu).  The
+    // slab holds the planes already XOR-ed with the flip plane of the current class; when the
+    // class changes (every |G| / number_bits rows) the copy is re-targeted in place.
+    if (INV) {
+      uint32_t const ro = po[NP + 2];
+      if (ro != kNoRetarget) {
+        uint32_t const d = *reinterpret_cast<uint32_t const *>(column + ro);
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+          if (i < NP - 3 || i < nbits) planes[i * 32 + lane] ^= d;  // padding planes stay zero
+        top ^= d;
+      }
+    }
     uint32_t z[NP];
     uint32_t lt = 0;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       z[i] = *reinterpret_cast<uint32_t const *>(column + po[i]);
-      if (INV) z[i] ^= (i < NP - 3 || i < nbits) ? top : 0u;  // padding planes stay zero
       lt = ((z[i] ^ r[i]) & r[i]) | (~(z[i] ^ r[i]) & lt);   // one LOP3: z < r, most significant plane last
     }
 #pragma unroll

@@ -13,6 +13,7 @@
 // owns a private copy and uploads it on demand.
 #pragma once
 
+#include <algorithm>
 #include <vector>
 
 #include "state.hpp"
@@ -28,10 +29,12 @@ static uint64_t g_plane_table_owner = 0;  // GroupData::id, NP and block size cu
 //   [np]      byte offset of the source plane of the TOP live bit (number_bits - 1):
 //             the spin-flipped image ~y is smaller than y iff that bit of y is set
 //   [np + 1]  character indices of element j (GroupData::cinfo)
-//   [np + 2], [np + 3]  padding
+//   [np + 2]  same as [np] when the flip plane differs from the previous row's, else kNoRetarget
+//   [np + 3]  padding
 // Planes are padded to a multiple of four (np >= number_bits); padding planes
 // map onto themselves.  Returns false when the table does not fit.
 constexpr int kPlaneRowExtra = 4;
+constexpr uint32_t kNoRetarget = 0xffffffffu;
 static inline bool upload_plane_offsets(GroupData const &g, int np, int threads_per_block) {
   size_t const stride = (size_t)np + kPlaneRowExtra;
   size_t const entries = (size_t)g.number_masks * stride;
@@ -40,14 +43,30 @@ static inline bool upload_plane_offsets(GroupData const &g, int np, int threads_
   uint64_t const tag = (g.id << 20) | ((uint64_t)np << 12) | (uint64_t)threads_per_block;
   if (g_plane_table_owner == tag) return true;
   std::vector<uint32_t> table(entries, 0u);
-  for (int j = 0; j < g.number_masks; ++j) {
+  // Rows are ordered by the source of the top bit (the identity's class first, so that an
+  // identity element stays in row 0): consecutive rows then share their flip plane and the
+  // kernels re-target the flipped copy of the planes only when it changes.  The orbit
+  // minimum / stabiliser sums do not depend on the order of the elements.
+  auto top_of = [&](int j) { return g.number_bits > 0 ? (int)g.perm[(size_t)j * g.number_bits + (g.number_bits - 1)] : 0; };
+  std::vector<int> order((size_t)g.number_masks);
+  for (int j = 0; j < g.number_masks; ++j) order[(size_t)j] = j;
+  int const first_top = g.number_masks > 0 ? top_of(0) : 0;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    int const ka = top_of(a) == first_top ? -1 : top_of(a), kb = top_of(b) == first_top ? -1 : top_of(b);
+    return ka < kb;
+  });
+  int previous_top = -1;
+  for (int row = 0; row < g.number_masks; ++row) {
+    int const j = order[(size_t)row];
     for (int i = 0; i < np; ++i) {
       int const src = i < g.number_bits ? g.perm[(size_t)j * g.number_bits + i] : i;
-      table[(size_t)j * stride + i] = (uint32_t)(src * threads_per_block * 4);
+      table[(size_t)row * stride + i] = (uint32_t)(src * threads_per_block * 4);
     }
-    int const top = g.number_bits > 0 ? g.perm[(size_t)j * g.number_bits + (g.number_bits - 1)] : 0;
-    table[(size_t)j * stride + np] = (uint32_t)(top * threads_per_block * 4);
-    table[(size_t)j * stride + np + 1] = g.cinfo.empty() ? 0u : (uint32_t)g.cinfo[(size_t)j];
+    int const top = top_of(j);
+    table[(size_t)row * stride + np] = (uint32_t)(top * threads_per_block * 4);
+    table[(size_t)row * stride + np + 1] = g.cinfo.empty() ? 0u : (uint32_t)g.cinfo[(size_t)j];
+    table[(size_t)row * stride + np + 2] = top != previous_top ? (uint32_t)(top * threads_per_block * 4) : kNoRetarget;
+    previous_top = top;
   }
   CUDA_CHECK(cudaMemcpyToSymbolAsync(c_plane_rows, table.data(), entries * sizeof(uint32_t), 0,
                                      cudaMemcpyHostToDevice, runtime().stream));
