@@ -127,6 +127,9 @@ OperatorDev &operator_dev(ls_hs_operator const *op) {
 }
 
 // ---- kernels ---------------------------------------------------------------------
+#ifndef LS_ORBIT_RETARGET
+#define LS_ORBIT_RETARGET 0  // orbit_kernel: re-target the flipped planes in place instead of one XOR per plane
+#endif
 constexpr int kOrbitThreads = 128;   // one thread = one word of 32 matrix elements
 constexpr int kGatherThreads = 128;  // one thread = one row
 constexpr int kMvIdxPlanes = 8;      // bit-sliced path: at most 256 distinct character values
@@ -324,18 +327,36 @@ orbit_kernel(MatvecArgs const a) {
   int const nbits = a.g.number_bits;
   int const nidx = a.number_idx_planes;
   int const G = (a.debug_skip & 1) ? 0 : a.g.number_masks;
+#if LS_ORBIT_RETARGET
+  uint32_t top = 0;
+#endif
 #pragma unroll 1
   for (int j = 0; j < G; ++j) {
     PlaneRow<NP> const po(j);
     // z = min(y, ~y) = y ^ top(y) when spin inversion is present (see basis_build.cu)
+#if LS_ORBIT_RETARGET
+    if (INV) {
+      uint32_t const ro = po[NP + 2];
+      if (ro != kNoRetarget) {
+        uint32_t const d = *reinterpret_cast<uint32_t const *>(column + ro);
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+          if (i < NP - 3 || i < nbits) planes[i * 32 + lane] ^= d;
+        top ^= d;
+      }
+    }
+#else
     uint32_t top = 0;
     if (INV) top = *reinterpret_cast<uint32_t const *>(column + po[NP]);
+#endif
     uint32_t z[NP];
     uint32_t lt = 0;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       z[i] = *reinterpret_cast<uint32_t const *>(column + po[i]);
+#if !LS_ORBIT_RETARGET
       if (INV) z[i] ^= (i < NP - 3 || i < nbits) ? top : 0u;  // padding planes stay zero
+#endif
       lt = ((z[i] ^ r[i]) & r[i]) | (~(z[i] ^ r[i]) & lt);   // one LOP3: z < r, most significant plane last
     }
 #pragma unroll
@@ -674,6 +695,130 @@ row_sum_kernel(MatvecArgs const a) {
       acc_i += v.y;
     } else {
       acc_r += __ldcs(a.vals + q);
+    }
+  }
+  double dr = 0.0, di = 0.0;
+  for (int k = 0; k < TD; ++k)
+    if ((alpha & d_m[k]) == d_r[k]) {
+      double const sign = (__popcll(alpha & d_s[k]) & 1) ? -1.0 : 1.0;
+      dr += sign * d_v[k].x;
+      di += sign * d_v[k].y;
+    }
+  double const ni = a.norms != nullptr ? __ldg(a.norms + row) : 1.0;
+  int64_t const out = row - a.row_begin;
+  if (CPLX) {
+    double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.x) + row);
+    double2 res;
+    res.x = acc_r / ni + (dr * xv.x - di * xv.y);
+    res.y = acc_i / ni + (dr * xv.y + di * xv.x);
+    reinterpret_cast<double2 *>(a.y)[out] = res;
+  } else {
+    a.y[out] = acc_r / ni + dr * __ldg(a.x + row);  // kernels/reference.c:84-91 uses creal(v) only
+  }
+}
+
+// ---- split path: orbit_kernel -> rank_gather_kernel -> row_combine_kernel ------------
+// The ranking + gather is pure memory latency; on its own it runs at full occupancy
+// (thread per matrix element, kRankBatch independent searches per thread, few registers,
+// no shared memory) instead of sharing the register-heavy orbit kernel's 16-20 warps.
+//   gathered[q] = n_j x_j of the representative of matrix element q (0 when the state has
+//   no index; kMissBits when it has none although its norm is positive -- an error unless
+//   the term's coefficient vanishes, which row_combine_kernel decides).
+constexpr int kRankThreads = 256;
+constexpr int kRankBatch = 4;
+constexpr unsigned long long kMissBits = 0x7ff8dead00000001ull;  // a quiet NaN no computation produces
+
+template <class Low>
+__global__ void __launch_bounds__(kRankThreads)
+rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
+  uint32_t const total = a.offsets[a.chunk_rows];
+  uint64_t const warp_q0 = ((uint64_t)blockIdx.x * (kRankThreads / 32) + (threadIdx.x >> 5)) * (32 * kRankBatch);
+  if (warp_q0 >= total) return;
+  int const lane = threadIdx.x & 31;
+  bool const cplx = a.complex_vectors != 0;
+  uint64_t needle[kRankBatch];
+  bool live[kRankBatch];
+#pragma unroll
+  for (int u = 0; u < kRankBatch; ++u) {
+    uint64_t const q = warp_q0 + (uint64_t)u * 32 + lane;
+    live[u] = q < total;
+    needle[u] = live[u] ? __ldcs(a.q_rep + q) : 0;
+  }
+  int64_t j[kRankBatch];
+  if constexpr (std::is_void<Low>::value) index_find<kRankBatch>(a.ix, needle, live, j);
+  else index_find32<Low, kRankBatch>(a.ix, needle, live, j);
+  double2 xv[kRankBatch];
+#pragma unroll
+  for (int u = 0; u < kRankBatch; ++u) {
+    xv[u] = make_double2(0.0, 0.0);
+    if (j[u] >= 0) {
+      if (cplx) xv[u] = __ldg(reinterpret_cast<double2 const *>(a.xs) + j[u]);
+      else xv[u].x = __ldg(a.xs + j[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kRankBatch; ++u) {
+    if (!live[u]) continue;
+    uint64_t const q = warp_q0 + (uint64_t)u * 32 + lane;
+    if (j[u] < 0 && stabiliser_sum_global(a.g, needle[u]) > kNormThreshold) xv[u].x = __longlong_as_double((long long)kMissBits);
+    if (cplx) reinterpret_cast<double2 *>(a.vals)[q] = xv[u];
+    else a.vals[q] = xv[u].x;
+  }
+}
+
+// Thread per row: conj(chi) w sign times the gathered values in term order, the
+// diagonal, one write of y.
+template <bool CPLX>
+__global__ void __launch_bounds__(kGatherThreads)
+row_combine_kernel(__grid_constant__ MatvecArgs const a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  AdjointTerms terms;
+  terms.stage(smem, a.off, true);
+  size_t p = (AdjointTerms::bytes(a.off.number_terms, true) + 15) & ~size_t(15);
+  int const TD = a.diag.number_terms;
+  double2 *d_v = reinterpret_cast<double2 *>(smem + p);
+  double2 *chars = d_v + TD;
+  uint64_t *d_m = reinterpret_cast<uint64_t *>(chars + a.number_chars);
+  uint64_t *d_r = d_m + TD;
+  uint64_t *d_s = d_r + TD;
+  for (int t = threadIdx.x; t < TD; t += blockDim.x) {
+    d_m[t] = a.diag.m[t];
+    d_r[t] = a.diag.r[t];
+    d_s[t] = a.diag.s[t];
+    d_v[t] = a.diag.v[t];
+  }
+  for (int j = threadIdx.x; j < a.number_chars; j += blockDim.x) chars[j] = a.cvals[j];
+  __syncthreads();
+
+  int const r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.chunk_rows) return;
+  int64_t const row = a.chunk_begin + r;
+  uint64_t const alpha = __ldg(a.ix.reps + row);
+  int const T = terms.T;
+  bool const have_cidx = a.number_idx_planes > 0;
+  double acc_r = 0.0, acc_i = 0.0;
+  uint32_t q = __ldg(a.offsets + r);
+  for (int t = 0; t < T; ++t) {
+    if ((alpha & terms.m[t]) != terms.l[t]) continue;
+    double2 w = terms.w[t];
+    if (__popcll(alpha & terms.s[t]) & 1) { w.x = -w.x; w.y = -w.y; }
+    double2 const ch = chars[have_cidx ? __ldcs(a.q_cidx + q) : 0];
+    double const fr = ch.x * w.x + ch.y * w.y;  // conj(chi) * w
+    double const fi = ch.x * w.y - ch.y * w.x;
+    double2 xv = make_double2(0.0, 0.0);
+    if (CPLX) xv = __ldcs(reinterpret_cast<double2 const *>(a.vals) + q);
+    else xv.x = __ldcs(a.vals + q);
+    ++q;
+    if ((unsigned long long)__double_as_longlong(xv.x) == kMissBits) {
+      // not in the basis although its norm is positive (DistributedMatrixVector.chpl:127-135)
+      if (fr != 0.0 || fi != 0.0) atomicOr(a.error_flag, 1);
+      continue;
+    }
+    if (CPLX) {
+      acc_r += fr * xv.x - fi * xv.y;
+      acc_i += fr * xv.y + fi * xv.x;
+    } else {
+      acc_r += fr * xv.x;
     }
   }
   double dr = 0.0, di = 0.0;
@@ -1049,8 +1194,12 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   size_t const sum_smem = (size_t)a.diag.number_terms * 40;
   // fused = canonicalise + rank + gather in one kernel, then a row sum; LS_B200_MATVEC=unfused keeps the
   // three-kernel pipeline (orbit -> q_rep/q_cidx -> gather) for A/B measurements
-  bool fused = a.mode == kModeGroup && fused_smem <= rt.smem_optin && sum_smem <= rt.smem_optin;
-  if (char const *env = getenv("LS_B200_MATVEC")) fused = fused && strcmp(env, "unfused") != 0;
+  // split = orbit kernel -> full-occupancy rank + gather kernel -> per-row combine (LS_B200_MATVEC=split)
+  char const *variant = getenv("LS_B200_MATVEC");
+  bool const is_group = a.mode == kModeGroup || a.mode == kModeGroupScalar;
+  bool split = is_group && variant != nullptr && strcmp(variant, "split") == 0;
+  bool fused = a.mode == kModeGroup && !split && fused_smem <= rt.smem_optin && sum_smem <= rt.smem_optin;
+  if (variant != nullptr) fused = fused && strcmp(variant, "unfused") != 0;
   if (fused) orbit_smem = fused_smem;
   LSB_CHECK(gather_smem <= rt.smem_optin && orbit_smem <= rt.smem_optin,
             "operator / symmetry tables do not fit in shared memory");
@@ -1066,6 +1215,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     capacity = chunk_rows * T;
     a.counts = sc.counts.reserve((size_t)chunk_rows + 1);
     a.offsets = sc.offsets.reserve((size_t)chunk_rows + 1);
+    if (split) a.vals = sc.vals.reserve(((size_t)capacity + 32) * (complex_vectors ? 2 : 1));
     if (fused) {
       a.vals = sc.vals.reserve(((size_t)capacity + 32) * (complex_vectors ? 2 : 1));
     } else {
@@ -1094,6 +1244,13 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   allow_dynamic_smem(gather, gather_smem);
   auto row_sum = complex_vectors ? row_sum_kernel<true> : row_sum_kernel<false>;
   if (fused) allow_dynamic_smem(row_sum, sum_smem);
+  auto row_combine = complex_vectors ? row_combine_kernel<true> : row_combine_kernel<false>;
+  if (split) allow_dynamic_smem(row_combine, gather_smem);
+  void (*rank_gather)(MatvecArgs) = rank_gather_kernel<void>;
+  if (a.ix.offsets32 != nullptr && !a.ix.identity)
+    rank_gather = a.ix.lows16 != nullptr   ? rank_gather_kernel<uint16_t>
+                  : a.ix.lows32 != nullptr ? rank_gather_kernel<uint32_t>
+                                           : rank_gather_kernel<uint64_t>;
 
   for (int64_t begin = row_begin; begin < row_end; begin += chunk_rows) {
     int64_t const nrows = std::min(chunk_rows, row_end - begin);
@@ -1122,9 +1279,19 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
       sc.spans.emplace_back(sc.events_used, 1);
       CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
     }
-    if (fused && queued)
+    if (fused && queued) {
       row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, rt.stream>>>(a);
-    else
+    } else if (split && queued) {
+      size_t const max_tiles = ceil_div((size_t)nrows * (size_t)T, 32 * kRankBatch);
+      rank_gather<<<ceil_div(max_tiles, kRankThreads / 32), kRankThreads, 0, rt.stream>>>(a);
+      count_launch();
+      if (profile) {
+        CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+        sc.spans.emplace_back(sc.events_used, 2);
+        CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+      }
+      row_combine<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
+    } else
       gather<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
     count_launch();
     if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
@@ -1142,12 +1309,13 @@ static bool matvec_finish() {
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
   float ms = 0;
   if (cudaEventElapsedTime(&ms, rt.ev0, rt.ev1) == cudaSuccess) rt.last_matvec_ms = ms;
-  rt.last_orbit_ms = rt.last_gather_ms = 0;
+  rt.last_orbit_ms = rt.last_gather_ms = rt.last_combine_ms = 0;
   rt.last_orbit_launches = rt.last_gather_launches = 0;
   for (auto const &span : sc.spans) {
     float t = 0;
     if (cudaEventElapsedTime(&t, sc.events[span.first], sc.events[span.first + 1]) != cudaSuccess) continue;
     if (span.second == 0) { rt.last_orbit_ms += t; ++rt.last_orbit_launches; }
+    else if (span.second == 2) { rt.last_combine_ms += t; }
     else { rt.last_gather_ms += t; ++rt.last_gather_launches; }
   }
   if (flag != 0) {

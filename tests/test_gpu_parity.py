@@ -321,9 +321,10 @@ def test_matvec_pipeline_variants_agree(oracle, built, name, chunk, monkeypatch)
         monkeypatch.setenv("LS_B200_MV_CHUNK", chunk)
         y1 = op.apply_to_state_vector(x)
         assert np.array_equal(y1, y0)  # chunking never changes the summation order
-    monkeypatch.setenv("LS_B200_MATVEC", "unfused")
-    y2 = op.apply_to_state_vector(x)
-    assert _rel_err(y2, y0) < MATVEC_RTOL
+    for variant in ("unfused", "split", "fused"):
+        monkeypatch.setenv("LS_B200_MATVEC", variant)
+        y2 = op.apply_to_state_vector(x)
+        assert _rel_err(y2, y0) < MATVEC_RTOL, variant
 
 
 @pytest.mark.parametrize("name", ["ladder_2x8_dm", "kagome12_complex"])
@@ -336,9 +337,10 @@ def test_matvec_complex_pipeline_variants_agree(oracle, built, name, monkeypatch
     d_y = _lib.DeviceArray(dim, np.complex128)
     op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
     y0 = d_y.numpy().copy()
-    monkeypatch.setenv("LS_B200_MATVEC", "unfused")
-    op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
-    assert _rel_err(d_y.numpy(), y0) < MATVEC_RTOL
+    for variant in ("unfused", "split", "fused"):
+        monkeypatch.setenv("LS_B200_MATVEC", variant)
+        op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
+        assert _rel_err(d_y.numpy(), y0) < MATVEC_RTOL, variant
 
 
 @pytest.mark.parametrize("name", ["chain16_symm", "kagome18_c2", "hubbard_2x4"])
@@ -408,6 +410,11 @@ def test_matvec_invalid_sector_raises(oracle):
     x = np.ones(basis.number_states)
     with pytest.raises(RuntimeError, match="invalid index"):
         bad.apply_to_state_vector(x)
+    for variant in ("unfused", "split", "fused"):
+        with pytest.MonkeyPatch.context() as mp:
+            mp.setenv("LS_B200_MATVEC", variant)
+            with pytest.raises(RuntimeError, match="invalid index"):
+                bad.apply_to_state_vector(x)
     # the library stays usable afterwards
     good = m.operator(basis)
     assert np.isfinite(good.apply_to_state_vector(x)).all()

@@ -18,7 +18,9 @@ run "default (fused, two-level index)" A=1
 run "fused, flat index" LS_B200_INDEX_FLAT=1
 run "fused, no gather (orbit only)" LS_B200_MV_SKIP=2
 run "unfused, two-level index" LS_B200_MATVEC=unfused
-for v in lattice_symmetries_b200/variants/*.so; do [ -f "$v" ] && run "variant $v" LS_B200_LIBRARY=$PWD/$v; done
+run "split" LS_B200_MATVEC=split
+run "split, flat index" LS_B200_MATVEC=split LS_B200_INDEX_FLAT=1
+for v in lattice_symmetries_b200/variants/*.so; do [ -f "$v" ] && run "variant $v split" LS_B200_LIBRARY=$PWD/$v LS_B200_MATVEC=split; done
 } > $OUT/ab_$WL.txt 2>&1
 cat $OUT/ab_$WL.txt
 unset LS_B200_PROFILE

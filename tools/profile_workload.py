@@ -23,4 +23,5 @@ for _ in range(reps):
     op.matvec_device(x.ptr, y.ptr, sync=True)
 ms = _lib.lib.ls_b200_last_kernel_ms
 print(name, "dim", dim, "matvec ms %.2f" % ms(b"matvec"), "orbit ms %.2f x%d" % (ms(b"orbit"), ms(b"orbit_launches")),
-      "gather ms %.2f x%d" % (ms(b"gather"), ms(b"gather_launches")), "build ms %.2f" % ms(b"build"))
+      "gather ms %.2f x%d" % (ms(b"gather"), ms(b"gather_launches")), "combine ms %.2f" % ms(b"combine"),
+      "build ms %.2f" % ms(b"build"))
