@@ -729,7 +729,7 @@ constexpr int kRankBatch = 4;
 constexpr unsigned long long kMissBits = 0x7ff8dead00000001ull;  // a quiet NaN no computation produces
 
 template <class Low>
-__global__ void __launch_bounds__(kRankThreads)
+__global__ void __launch_bounds__(kRankThreads, 5)  // <= 48 registers, also for the (rare) noinline norm check
 rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
   uint32_t const total = a.offsets[a.chunk_rows];
   uint64_t const warp_q0 = ((uint64_t)blockIdx.x * (kRankThreads / 32) + (threadIdx.x >> 5)) * (32 * kRankBatch);
@@ -872,7 +872,7 @@ orbit_scalar_kernel(MatvecArgs const a) {
 //   QUEUED: representatives / character indices come from the orbit kernel;
 //   otherwise they are computed inline (no symmetries, or spin inversion only).
 template <bool QUEUED, bool CPLX>
-__global__ void __launch_bounds__(kGatherThreads)
+__global__ void __launch_bounds__(kGatherThreads, 8)  // <= 64 registers (the noinline norm check would take 128)
 gather_kernel(MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
   AdjointTerms terms;
