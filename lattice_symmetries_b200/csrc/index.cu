@@ -168,6 +168,7 @@ state_index_kernel(IndexView ix, int64_t n, uint64_t const *__restrict__ needles
 // only affects speed, never results, so we are free to choose.
 static int choose_prefix_bits(int64_t n, int number_bits, int requested) {
   (void)requested;
+  if (char const *env = getenv("LS_B200_INDEX_PREFIX")) return std::max(0, std::min(atoi(env), number_bits));  // A/B knob
   int want = 1;
   while (want < 40 && (int64_t(1) << want) < n / 8) ++want;
   int const cap = 28;

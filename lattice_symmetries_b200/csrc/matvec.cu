@@ -128,7 +128,7 @@ OperatorDev &operator_dev(ls_hs_operator const *op) {
 
 // ---- kernels ---------------------------------------------------------------------
 #ifndef LS_ORBIT_RETARGET
-#define LS_ORBIT_RETARGET 0  // orbit_kernel: re-target the flipped planes in place instead of one XOR per plane
+#define LS_ORBIT_RETARGET 1  // orbit_kernel: re-target the flipped planes in place instead of one XOR per plane
 #endif
 constexpr int kOrbitThreads = 128;   // one thread = one word of 32 matrix elements
 constexpr int kGatherThreads = 128;  // one thread = one row
@@ -798,27 +798,35 @@ row_combine_kernel(__grid_constant__ MatvecArgs const a) {
   bool const have_cidx = a.number_idx_planes > 0;
   double acc_r = 0.0, acc_i = 0.0;
   uint32_t q = __ldg(a.offsets + r);
-  for (int t = 0; t < T; ++t) {
-    if ((alpha & terms.m[t]) != terms.l[t]) continue;
-    double2 w = terms.w[t];
-    if (__popcll(alpha & terms.s[t]) & 1) { w.x = -w.x; w.y = -w.y; }
-    double2 const ch = chars[have_cidx ? __ldcs(a.q_cidx + q) : 0];
-    double const fr = ch.x * w.x + ch.y * w.y;  // conj(chi) * w
-    double const fi = ch.x * w.y - ch.y * w.x;
-    double2 xv = make_double2(0.0, 0.0);
-    if (CPLX) xv = __ldcs(reinterpret_cast<double2 const *>(a.vals) + q);
-    else xv.x = __ldcs(a.vals + q);
-    ++q;
-    if ((unsigned long long)__double_as_longlong(xv.x) == kMissBits) {
-      // not in the basis although its norm is positive (DistributedMatrixVector.chpl:127-135)
-      if (fr != 0.0 || fi != 0.0) atomicOr(a.error_flag, 1);
-      continue;
-    }
-    if (CPLX) {
-      acc_r += fr * xv.x - fi * xv.y;
-      acc_i += fr * xv.y + fi * xv.x;
-    } else {
-      acc_r += fr * xv.x;
+  // Terms are matched 64 at a time into a bit mask (no divergence: every lane tests every
+  // term), then each lane walks its own set bits -- the row's matrix elements in term order.
+  for (int t0 = 0; t0 < T; t0 += 64) {
+    int const tn = min(64, T - t0);
+    uint64_t mask = 0;
+    for (int k = 0; k < tn; ++k) mask |= (uint64_t)((alpha & terms.m[t0 + k]) == terms.l[t0 + k]) << k;
+    while (mask != 0) {
+      int const t = t0 + __ffsll((long long)mask) - 1;
+      mask &= mask - 1;
+      double2 w = terms.w[t];
+      if (__popcll(alpha & terms.s[t]) & 1) { w.x = -w.x; w.y = -w.y; }
+      double2 const ch = chars[have_cidx ? __ldcs(a.q_cidx + q) : 0];
+      double const fr = ch.x * w.x + ch.y * w.y;  // conj(chi) * w
+      double const fi = ch.x * w.y - ch.y * w.x;
+      double2 xv = make_double2(0.0, 0.0);
+      if (CPLX) xv = __ldcs(reinterpret_cast<double2 const *>(a.vals) + q);
+      else xv.x = __ldcs(a.vals + q);
+      ++q;
+      if ((unsigned long long)__double_as_longlong(xv.x) == kMissBits) {
+        // not in the basis although its norm is positive (DistributedMatrixVector.chpl:127-135)
+        if (fr != 0.0 || fi != 0.0) atomicOr(a.error_flag, 1);
+        continue;
+      }
+      if (CPLX) {
+        acc_r += fr * xv.x - fi * xv.y;
+        acc_i += fr * xv.y + fi * xv.x;
+      } else {
+        acc_r += fr * xv.x;
+      }
     }
   }
   double dr = 0.0, di = 0.0;
