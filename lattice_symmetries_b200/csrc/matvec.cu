@@ -163,6 +163,7 @@ struct MatvecArgs {
   uint32_t *offsets;     // [chunk_rows + 1] exclusive scan of counts
   uint64_t *q_rep;       // [capacity] representative of every matrix element, CSR order
   uint8_t *q_cidx;       // [capacity] index of the minimising character
+  uint16_t *q_tsign;     // [capacity] split path: term | sign << 15 of every matrix element (nullptr: not recorded)
   double *vals;          // [capacity] (x2 when complex) fused path: conj(chi) w sign n_j x_j of every matrix element
 };
 
@@ -255,9 +256,10 @@ template <int NP, bool INV>
 __global__ void __launch_bounds__(kOrbitThreads)
 orbit_kernel(MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
+  bool const pack_tsign = NP <= 48 && a.q_tsign != nullptr;
   AdjointTerms terms;
-  terms.stage(smem, a.off, false);
-  size_t const terms_bytes = (AdjointTerms::bytes(a.off.number_terms, false) + 15) & ~size_t(15);
+  terms.stage(smem, a.off, pack_tsign);
+  size_t const terms_bytes = (AdjointTerms::bytes(a.off.number_terms, pack_tsign) + 15) & ~size_t(15);
   __syncthreads();
 
   int const tid = threadIdx.x;
@@ -292,7 +294,11 @@ orbit_kernel(MatvecArgs const a) {
           if ((alpha & terms.m[t]) == terms.l[t]) {
             if (q >= warp_q0 && q < warp_q1) {
               unsigned const e = (unsigned)(q - warp_q0);
-              stage[(e & 31u) * 32 + (e >> 5)] = alpha ^ terms.x[t];
+              uint64_t beta = alpha ^ terms.x[t];
+              // the term and its sign ride in the 16 spare bits above the state (NP <= 48)
+              if (pack_tsign)
+                beta |= (uint64_t)((unsigned)t | ((unsigned)(__popcll(alpha & terms.s[t]) & 1) << 15)) << 48;
+              stage[(e & 31u) * 32 + (e >> 5)] = beta;
             }
             ++q;
           }
@@ -311,6 +317,26 @@ orbit_kernel(MatvecArgs const a) {
       hi[k] = (uint32_t)(beta >> 32);
     }
     __syncwarp();  // every lane holds its betas: the slab may now be overwritten by the planes
+    if (pack_tsign) {
+      uint16_t *ts_out = a.q_tsign + q0;
+      if (lanes == 32) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+          uint4 v;
+          v.x = (hi[k] >> 16) | (hi[k + 1] & 0xffff0000u);
+          v.y = (hi[k + 2] >> 16) | (hi[k + 3] & 0xffff0000u);
+          v.z = (hi[k + 4] >> 16) | (hi[k + 5] & 0xffff0000u);
+          v.w = (hi[k + 6] >> 16) | (hi[k + 7] & 0xffff0000u);
+          *reinterpret_cast<uint4 *>(ts_out + k) = v;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (k < lanes) ts_out[k] = (uint16_t)(hi[k] >> 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) hi[k] &= 0xffffu;
+    }
     transpose32(lo);
     if (NP > 32) transpose32(hi);
 #pragma unroll
@@ -731,6 +757,21 @@ constexpr unsigned long long kMissBits = 0x7ff8dead00000001ull;  // a quiet NaN 
 template <class Low>
 __global__ void __launch_bounds__(kRankThreads, 5)  // <= 48 registers, also for the (rare) noinline norm check
 rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  // product mode (q_tsign recorded): the values leave this kernel already multiplied by
+  // conj(chi) w sign, and a plain per-row sum finishes the job
+  bool const product = a.q_tsign != nullptr;
+  double2 *tw = reinterpret_cast<double2 *>(smem);
+  double2 *chars = tw + a.off.number_terms;
+  if (product) {
+    for (int t = threadIdx.x; t < a.off.number_terms; t += blockDim.x) {
+      double2 v = a.off.v[t];
+      if (__popcll(a.off.x[t] & a.off.s[t]) & 1) { v.x = -v.x; v.y = -v.y; }
+      tw[t] = v;
+    }
+    for (int j = threadIdx.x; j < a.number_chars; j += blockDim.x) chars[j] = a.cvals[j];
+    __syncthreads();
+  }
   uint32_t const total = a.offsets[a.chunk_rows];
   uint64_t const warp_q0 = ((uint64_t)blockIdx.x * (kRankThreads / 32) + (threadIdx.x >> 5)) * (32 * kRankBatch);
   if (warp_q0 >= total) return;
@@ -760,7 +801,21 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
   for (int u = 0; u < kRankBatch; ++u) {
     if (!live[u]) continue;
     uint64_t const q = warp_q0 + (uint64_t)u * 32 + lane;
-    if (j[u] < 0 && stabiliser_sum_global(a.g, needle[u]) > kNormThreshold) xv[u].x = __longlong_as_double((long long)kMissBits);
+    bool const missing = j[u] < 0;
+    if (product) {
+      unsigned const ts = __ldcs(a.q_tsign + q);
+      double2 w = tw[ts & 0x7fffu];
+      if (ts & 0x8000u) { w.x = -w.x; w.y = -w.y; }
+      double2 const ch = chars[a.number_idx_planes > 0 ? __ldcs(a.q_cidx + q) : 0];
+      double const fr = ch.x * w.x + ch.y * w.y;  // conj(chi) * w
+      double const fi = ch.x * w.y - ch.y * w.x;
+      // not in the basis: fine when its norm vanishes, an error otherwise (DistributedMatrixVector.chpl:127-135)
+      if (missing && (fr != 0.0 || fi != 0.0) && stabiliser_sum_global(a.g, needle[u]) > kNormThreshold)
+        atomicOr(a.error_flag, 1);
+      xv[u] = make_double2(fr * xv[u].x - fi * xv[u].y, fr * xv[u].y + fi * xv[u].x);
+    } else if (missing && stabiliser_sum_global(a.g, needle[u]) > kNormThreshold) {
+      xv[u].x = __longlong_as_double((long long)kMissBits);
+    }
     if (cplx) reinterpret_cast<double2 *>(a.vals)[q] = xv[u];
     else a.vals[q] = xv[u].x;
   }
@@ -1086,6 +1141,7 @@ struct MatvecScratch {
   DeviceBuffer<uint32_t> counts, offsets;
   DeviceBuffer<uint64_t> q_rep;
   DeviceBuffer<uint8_t> q_cidx;
+  DeviceBuffer<uint16_t> q_tsign;
   DeviceBuffer<double> vals;
   DeviceBuffer<unsigned char> scan_tmp;
   size_t scan_tmp_bytes = 0;
@@ -1209,6 +1265,10 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   bool fused = a.mode == kModeGroup && !split && fused_smem <= rt.smem_optin && sum_smem <= rt.smem_optin;
   if (variant != nullptr) fused = fused && strcmp(variant, "unfused") != 0;
   if (fused) orbit_smem = fused_smem;
+  // the orbit kernel can carry (term, sign) in the spare bits of the staged states only when NP <= 48
+  bool const want_tsign = split && a.mode == kModeGroup && np <= 48;
+  if (want_tsign)
+    orbit_smem = ((AdjointTerms::bytes(T, true) + 15) & ~size_t(15)) + (size_t)(kOrbitThreads / 32) * kWarpSlabBytes;
   LSB_CHECK(gather_smem <= rt.smem_optin && orbit_smem <= rt.smem_optin,
             "operator / symmetry tables do not fit in shared memory");
 
@@ -1229,6 +1289,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     } else {
       a.q_rep = sc.q_rep.reserve((size_t)capacity + 32);
       a.q_cidx = sc.q_cidx.reserve((size_t)capacity + 32);
+      if (want_tsign) a.q_tsign = sc.q_tsign.reserve((size_t)capacity + 32);
     }
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, a.counts, a.offsets, (int)(chunk_rows + 1), rt.stream);
@@ -1251,7 +1312,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
                        : (complex_vectors ? gather_kernel<false, true> : gather_kernel<false, false>);
   allow_dynamic_smem(gather, gather_smem);
   auto row_sum = complex_vectors ? row_sum_kernel<true> : row_sum_kernel<false>;
-  if (fused) allow_dynamic_smem(row_sum, sum_smem);
+  if (fused || split) allow_dynamic_smem(row_sum, sum_smem);
   auto row_combine = complex_vectors ? row_combine_kernel<true> : row_combine_kernel<false>;
   if (split) allow_dynamic_smem(row_combine, gather_smem);
   void (*rank_gather)(MatvecArgs) = rank_gather_kernel<void>;
@@ -1291,14 +1352,18 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
       row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, rt.stream>>>(a);
     } else if (split && queued) {
       size_t const max_tiles = ceil_div((size_t)nrows * (size_t)T, 32 * kRankBatch);
-      rank_gather<<<ceil_div(max_tiles, kRankThreads / 32), kRankThreads, 0, rt.stream>>>(a);
+      size_t const rank_smem = a.q_tsign != nullptr ? ((size_t)T + (size_t)a.number_chars) * 16 : 0;
+      rank_gather<<<ceil_div(max_tiles, kRankThreads / 32), kRankThreads, rank_smem, rt.stream>>>(a);
       count_launch();
       if (profile) {
         CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
         sc.spans.emplace_back(sc.events_used, 2);
         CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
       }
-      row_combine<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
+      if (a.q_tsign != nullptr)
+        row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, rt.stream>>>(a);
+      else
+        row_combine<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
     } else
       gather<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
     count_launch();
