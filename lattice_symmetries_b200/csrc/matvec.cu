@@ -253,7 +253,7 @@ row_count_kernel(MatvecArgs const a) {
 // first stages its betas and then holds its bit planes.
 constexpr int kWarpSlabBytes = 32 * 32 * 8;
 template <int NP, bool INV>
-__global__ void __launch_bounds__(kOrbitThreads)
+__global__ void __launch_bounds__(kOrbitThreads, 5)  // five CTAs per SM: <= 102 registers
 orbit_kernel(MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
   bool const pack_tsign = NP <= 48 && a.q_tsign != nullptr;
@@ -750,12 +750,15 @@ row_sum_kernel(MatvecArgs const a) {
 //   gathered[q] = n_j x_j of the representative of matrix element q (0 when the state has
 //   no index; kMissBits when it has none although its norm is positive -- an error unless
 //   the term's coefficient vanishes, which row_combine_kernel decides).
+#ifndef LS_RANK_MINBLOCKS
+#define LS_RANK_MINBLOCKS 5  // <= 48 registers
+#endif
 constexpr int kRankThreads = 256;
 constexpr int kRankBatch = 4;
 constexpr unsigned long long kMissBits = 0x7ff8dead00000001ull;  // a quiet NaN no computation produces
 
 template <class Low>
-__global__ void __launch_bounds__(kRankThreads, 5)  // <= 48 registers, also for the (rare) noinline norm check
+__global__ void __launch_bounds__(kRankThreads, LS_RANK_MINBLOCKS)  // register cap, also for the (rare) noinline norm check
 rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
   // product mode (q_tsign recorded): the values leave this kernel already multiplied by
@@ -1256,14 +1259,17 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   size_t const fused_smem = ((AdjointTerms::bytes(T, true) + 15) & ~size_t(15)) + (size_t)a.number_chars * 16 +
                             (size_t)(kOrbitThreads / 32) * kFusedWarpBytes;
   size_t const sum_smem = (size_t)a.diag.number_terms * 40;
-  // fused = canonicalise + rank + gather in one kernel, then a row sum; LS_B200_MATVEC=unfused keeps the
-  // three-kernel pipeline (orbit -> q_rep/q_cidx -> gather) for A/B measurements
-  // split = orbit kernel -> full-occupancy rank + gather kernel -> per-row combine (LS_B200_MATVEC=split)
+  // Pipeline variants (LS_B200_MATVEC, for A/B measurements; results agree to rounding):
+  //   split   (default) orbit kernel -> full-occupancy rank + gather kernel -> per-row sum
+  //   fused   canonicalise + rank + gather in one kernel, then a per-row sum
+  //   unfused orbit kernel -> thread-per-row rank + gather + sum (the first design)
+  //   scalar  split, with the scalar Benes walk instead of the bit-sliced orbit kernel (handled above)
   char const *variant = getenv("LS_B200_MATVEC");
   bool const is_group = a.mode == kModeGroup || a.mode == kModeGroupScalar;
-  bool split = is_group && variant != nullptr && strcmp(variant, "split") == 0;
-  bool fused = a.mode == kModeGroup && !split && fused_smem <= rt.smem_optin && sum_smem <= rt.smem_optin;
-  if (variant != nullptr) fused = fused && strcmp(variant, "unfused") != 0;
+  bool const want_fused = variant != nullptr && strcmp(variant, "fused") == 0;
+  bool const want_unfused = variant != nullptr && strcmp(variant, "unfused") == 0;
+  bool const fused = a.mode == kModeGroup && want_fused && fused_smem <= rt.smem_optin && sum_smem <= rt.smem_optin;
+  bool const split = is_group && !fused && !want_unfused && sum_smem <= rt.smem_optin;
   if (fused) orbit_smem = fused_smem;
   // the orbit kernel can carry (term, sign) in the spare bits of the staged states only when NP <= 48
   bool const want_tsign = split && a.mode == kModeGroup && np <= 48;

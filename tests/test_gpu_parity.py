@@ -321,7 +321,7 @@ def test_matvec_pipeline_variants_agree(oracle, built, name, chunk, monkeypatch)
         monkeypatch.setenv("LS_B200_MV_CHUNK", chunk)
         y1 = op.apply_to_state_vector(x)
         assert np.array_equal(y1, y0)  # chunking never changes the summation order
-    for variant in ("unfused", "split", "fused"):
+    for variant in ("unfused", "split", "fused", "scalar"):
         monkeypatch.setenv("LS_B200_MATVEC", variant)
         y2 = op.apply_to_state_vector(x)
         assert _rel_err(y2, y0) < MATVEC_RTOL, variant
@@ -337,7 +337,7 @@ def test_matvec_complex_pipeline_variants_agree(oracle, built, name, monkeypatch
     d_y = _lib.DeviceArray(dim, np.complex128)
     op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
     y0 = d_y.numpy().copy()
-    for variant in ("unfused", "split", "fused"):
+    for variant in ("unfused", "split", "fused", "scalar"):
         monkeypatch.setenv("LS_B200_MATVEC", variant)
         op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
         assert _rel_err(d_y.numpy(), y0) < MATVEC_RTOL, variant
@@ -410,7 +410,7 @@ def test_matvec_invalid_sector_raises(oracle):
     x = np.ones(basis.number_states)
     with pytest.raises(RuntimeError, match="invalid index"):
         bad.apply_to_state_vector(x)
-    for variant in ("unfused", "split", "fused"):
+    for variant in ("unfused", "split", "fused", "scalar"):
         with pytest.MonkeyPatch.context() as mp:
             mp.setenv("LS_B200_MATVEC", variant)
             with pytest.raises(RuntimeError, match="invalid index"):
