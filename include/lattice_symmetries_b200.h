@@ -314,8 +314,11 @@ int ls_b200_build_shard(ls_hs_basis const *basis, uint64_t index_begin,
                         double **norms_dev, uint64_t *count);
 uint64_t ls_b200_number_candidates(ls_hs_basis const *basis);
 /* Install an (all-gathered) device-resident representative list + norms as
- * the basis' representatives; the library takes ownership of both buffers and
- * mirrors the states to pinned host memory for basis->representatives. */
+ * the basis' representatives; the library takes ownership of both buffers.
+ * basis->representatives.elts (a host pointer in the reference) is served by a
+ * managed allocation that doubles as the device array (read-mostly: host reads
+ * fault in duplicates, nothing is copied up front); LS_B200_HOST_MIRROR=pinned
+ * keeps a separate pinned host copy instead. */
 int ls_b200_set_representatives_device(ls_hs_basis *basis,
                                        uint64_t *representatives_dev,
                                        double *norms_dev, uint64_t count,

@@ -21,6 +21,8 @@
 //     order, together with their norms sqrt(n/|G|).
 #include <cub/device/device_scan.cuh>
 
+#include <chrono>
+
 #include <algorithm>
 
 #include "bitslice.cuh"
@@ -271,7 +273,7 @@ __device__ __noinline__ double lane_norm_sum(GroupView const &g, uint64_t const 
 //   alive_out[w]  bit k: candidate 32w+k is a representative with norm > 0
 //   event_out[w]  bit k: ... and has a non-trivial stabiliser (norm != 1/sqrt|G|)
 template <int NP, bool INV>
-__global__ void __launch_bounds__(kBuildThreads)
+__global__ void __launch_bounds__(kBuildThreads, (NP <= 40 ? 5 : NP <= 52 ? 4 : 3))  // NP <= 40: five CTAs per SM (<= 102 registers)
 build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint64_t number_words,
                              int identity_first, uint32_t *__restrict__ alive_out,
                              uint32_t *__restrict__ event_out, uint32_t *__restrict__ block_counts) {
@@ -641,12 +643,54 @@ static void free_pinned(void *p) {
     auto &reg = built_registry();
     auto it = reg.find(p);
     if (it != reg.end()) {
-      cudaFree(it->second.d_reps);
+      if (it->second.d_reps != p) cudaFree(it->second.d_reps);
       cudaFree(it->second.d_norms);
       reg.erase(it);
     }
   }
-  cudaFreeHost(p);
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeManaged) cudaFree(p);
+  else cudaFreeHost(p);
+}
+
+// The reference hands the representatives to its callers as a HOST array
+// (chpl_external_array::elts, read directly by Python and Haskell).  Default:
+// one managed allocation serves as both the device array of the kernels and
+// that host view -- resident in HBM, advised read-mostly, so a host read
+// faults in a read-only duplicate of the touched pages and the device copy
+// stays put.  Nothing is copied at build time.  LS_B200_HOST_MIRROR=pinned
+// keeps a second, pinned host copy instead (cudaMallocHost of the whole array:
+// ~0.4 ms per MB, more than the build itself for large bases).
+// Takes ownership of d_reps; returns the host-visible pointer and updates d_reps.
+static uint64_t *make_host_view(uint64_t *&d_reps, uint64_t count) {
+  Runtime &rt = runtime();
+  size_t const bytes = sizeof(uint64_t) * count;
+  char const *mode = getenv("LS_B200_HOST_MIRROR");
+  bool managed = mode == nullptr || strcmp(mode, "pinned") != 0;
+  if (managed) {
+    int concurrent = 0;
+    cudaDeviceGetAttribute(&concurrent, cudaDevAttrConcurrentManagedAccess, rt.device);
+    managed = concurrent != 0;
+  }
+  if (managed) {
+    uint64_t *m = nullptr;
+    if (cudaMallocManaged(&m, bytes) == cudaSuccess) {
+      CUDA_CHECK(cudaMemAdvise(m, bytes, cudaMemAdviseSetPreferredLocation, rt.device));
+      CUDA_CHECK(cudaMemPrefetchAsync(m, bytes, rt.device, rt.stream));
+      CUDA_CHECK(cudaMemcpyAsync(m, d_reps, bytes, cudaMemcpyDeviceToDevice, rt.stream));
+      CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+      CUDA_CHECK(cudaMemAdvise(m, bytes, cudaMemAdviseSetReadMostly, rt.device));
+      cudaFree(d_reps);
+      d_reps = m;
+      return m;
+    }
+    (void)cudaGetLastError();
+  }
+  uint64_t *host = nullptr;
+  CUDA_CHECK(cudaMallocHost(&host, bytes));
+  CUDA_CHECK(cudaMemcpyAsync(host, d_reps, bytes, cudaMemcpyDeviceToHost, rt.stream));
+  CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+  return host;
 }
 
 IndexData *create_index(uint64_t const *host_reps, int64_t count, int number_bits, int prefix_bits);
@@ -707,12 +751,19 @@ void ls_chpl_enumerate_representatives(ls_hs_basis const *basis, uint64_t lower,
   dest->num_elts = 0;
   dest->freer = nullptr;
   guarded(__func__, [&] {
+    static bool const profile = getenv("LS_B200_PROFILE") != nullptr;
+    auto const t0 = std::chrono::steady_clock::now();
     BuildResult r = build_range(basis, 0, ~uint64_t(0));
+    auto const t1 = std::chrono::steady_clock::now();
     uint64_t *host = nullptr;
     if (r.count > 0) {
-      CUDA_CHECK(cudaMallocHost(&host, sizeof(uint64_t) * r.count));
-      CUDA_CHECK(cudaMemcpyAsync(host, r.d_reps, sizeof(uint64_t) * r.count, cudaMemcpyDeviceToHost, runtime().stream));
-      CUDA_CHECK(cudaStreamSynchronize(runtime().stream));
+      host = make_host_view(r.d_reps, r.count);
+      auto const t2 = std::chrono::steady_clock::now();
+      if (profile) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[ls_b200] enumerate: build_range %.2f ms, host view %.2f ms (%zu states, %s)\n", ms(t0, t1),
+                ms(t1, t2), (size_t)r.count, host == r.d_reps ? "managed" : "pinned copy");
+      }
       built_registry()[host] = BuiltReps{r.d_reps, r.d_norms, r.count};
     } else {
       cudaFree(r.d_reps);
@@ -730,7 +781,9 @@ void ls_hs_build_representatives(ls_hs_basis *basis, uint64_t const lower, uint6
   LSB_CHECK(kernels->enumerate_states != nullptr,
             "enumerate_states kernel is NULL, ls_chpl_init was supposed to initialize it");
   if (basis->representatives.num_elts > 0) return;  // already built
+  auto const t0 = std::chrono::steady_clock::now();
   (*kernels->enumerate_states)(basis, lower, upper, &basis->representatives);
+  auto const t1 = std::chrono::steady_clock::now();
   int const number_bits = (basis->particle_type == LS_HS_SPINFUL_FERMION ? 2 : 1) * basis->number_sites;
   int const default_cache_bits = 22;
   auto *ix = reinterpret_cast<IndexData *>(ls_hs_create_state_index_binary_search_kernel_data(
@@ -738,6 +791,11 @@ void ls_hs_build_representatives(ls_hs_basis *basis, uint64_t const lower, uint6
   if (ix != nullptr) ix->identity = basis->state_index_is_identity;
   basis->kernels->state_index_data = ix;
   basis->kernels->state_index_kernel = &ls_hs_state_index_binary_search_kernel;
+  if (getenv("LS_B200_PROFILE") != nullptr) {
+    auto const t2 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[ls_b200] build_representatives: enumerate %.2f ms, index %.2f ms\n", ms(t0, t1), ms(t1, t2));
+  }
 }
 
 // kernels/reference.c:196-211 (borrows the caller's array)
@@ -762,11 +820,7 @@ int ls_b200_set_representatives_device(ls_hs_basis *basis, uint64_t *representat
   guarded(__func__, [&] {
     uint64_t *host = nullptr;
     bool const mirror = getenv("LS_B200_NO_HOST_MIRROR") == nullptr;
-    if (mirror && count > 0) {
-      CUDA_CHECK(cudaMallocHost(&host, sizeof(uint64_t) * count));
-      CUDA_CHECK(cudaMemcpyAsync(host, representatives_dev, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost, runtime().stream));
-      CUDA_CHECK(cudaStreamSynchronize(runtime().stream));
-    }
+    if (mirror && count > 0) host = make_host_view(representatives_dev, count);
     void const *key = host != nullptr ? (void const *)host : (void const *)representatives_dev;
     built_registry()[key] = BuiltReps{representatives_dev, norms_dev, count};
     basis->representatives.elts = host;

@@ -280,6 +280,8 @@ IndexData *create_index(uint64_t const *host_reps, int64_t count, int number_bit
   if (it != reg.end() && (int64_t)it->second.count == count) {
     ix->d_reps = it->second.d_reps;
     ix->d_norms = it->second.d_norms;
+    // a managed array doubles as the caller's host view and is released by its freer
+    ix->owns_d_reps = static_cast<void const *>(ix->d_reps) != static_cast<void const *>(host_reps);
     reg.erase(it);
   } else if (count > 0) {
     CUDA_CHECK(cudaMalloc(&ix->d_reps, sizeof(uint64_t) * (size_t)count));

@@ -253,7 +253,7 @@ row_count_kernel(MatvecArgs const a) {
 // first stages its betas and then holds its bit planes.
 constexpr int kWarpSlabBytes = 32 * 32 * 8;
 template <int NP, bool INV>
-__global__ void __launch_bounds__(kOrbitThreads, 5)  // five CTAs per SM: <= 102 registers
+__global__ void __launch_bounds__(kOrbitThreads, (NP <= 40 ? 5 : NP <= 52 ? 4 : 3))  // NP <= 40: five CTAs per SM (<= 102 registers)
 orbit_kernel(MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
   bool const pack_tsign = NP <= 48 && a.q_tsign != nullptr;
