@@ -732,7 +732,13 @@ int ls_b200_build_shard(ls_hs_basis const *basis, uint64_t index_begin, uint64_t
                         uint64_t **representatives_dev, double **norms_dev, uint64_t *count) {
   int status = -1;
   guarded(__func__, [&] {
+    auto const t0 = std::chrono::steady_clock::now();
     BuildResult r = build_range(basis, index_begin, index_end);
+    if (getenv("LS_B200_PROFILE") != nullptr)
+      fprintf(stderr, "[ls_b200] build_shard [%llu, %llu): %llu states, device %.2f ms, wall %.2f ms\n",
+              (unsigned long long)index_begin, (unsigned long long)index_end, (unsigned long long)r.count,
+              runtime().last_build_ms,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     *representatives_dev = r.d_reps;
     if (norms_dev != nullptr) *norms_dev = r.d_norms; else cudaFree(r.d_norms);
     *count = r.count;

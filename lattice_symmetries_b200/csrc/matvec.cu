@@ -268,8 +268,12 @@ orbit_kernel(MatvecArgs const a) {
   uint64_t *stage = reinterpret_cast<uint64_t *>(slab);   // [k][lane]: element 32 * lane + k of the warp
   uint32_t *planes = reinterpret_cast<uint32_t *>(slab);  // [plane][lane], after the betas have been read
   uint32_t const total = a.offsets[a.chunk_rows];
-  uint64_t const warp_q0 = ((uint64_t)blockIdx.x * (kOrbitThreads / 32) + (tid >> 5)) * 1024;
-  if (warp_q0 >= total) return;  // whole warps leave: everything below runs converged
+  // persistent: the grid is sized to the machine, a warp strides over the chunk's 1024-element blocks
+  // (whole warps leave together: everything below runs converged)
+  uint64_t const warp_stride = (uint64_t)gridDim.x * (kOrbitThreads / 32) * 1024;
+  for (uint64_t warp_q0 = ((uint64_t)blockIdx.x * (kOrbitThreads / 32) + (tid >> 5)) * 1024; warp_q0 < total;
+       warp_q0 += warp_stride) {
+  __syncwarp();  // the previous block's planes are dead: the slab may be overwritten
   uint64_t const warp_q1 = min((uint64_t)total, warp_q0 + 1024);
   uint64_t const q0 = warp_q0 + 32 * (uint64_t)lane;
   int const lanes = q0 < total ? (int)min((uint64_t)32, total - q0) : 0;
@@ -443,6 +447,7 @@ orbit_kernel(MatvecArgs const a) {
         if (k < lanes) out[k] = (uint8_t)info[k];
     }
   }
+  }  // blocks of this warp
 }
 
 // ---- fused path: canonicalise, rank and gather in one kernel ------------------------
@@ -776,10 +781,12 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
     __syncthreads();
   }
   uint32_t const total = a.offsets[a.chunk_rows];
-  uint64_t const warp_q0 = ((uint64_t)blockIdx.x * (kRankThreads / 32) + (threadIdx.x >> 5)) * (32 * kRankBatch);
-  if (warp_q0 >= total) return;
   int const lane = threadIdx.x & 31;
   bool const cplx = a.complex_vectors != 0;
+  // persistent: the grid is sized to the machine, a warp strides over tiles of 32 * kRankBatch elements
+  uint64_t const warp_stride = (uint64_t)gridDim.x * (kRankThreads / 32) * (32 * kRankBatch);
+  for (uint64_t warp_q0 = ((uint64_t)blockIdx.x * (kRankThreads / 32) + (threadIdx.x >> 5)) * (32 * kRankBatch);
+       warp_q0 < total; warp_q0 += warp_stride) {
   uint64_t needle[kRankBatch];
   bool live[kRankBatch];
 #pragma unroll
@@ -789,8 +796,15 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
     needle[u] = live[u] ? __ldcs(a.q_rep + q) : 0;
   }
   int64_t j[kRankBatch];
-  if constexpr (std::is_void<Low>::value) index_find<kRankBatch>(a.ix, needle, live, j);
+  if (a.debug_skip & 8) {  // profiling only: no index search
+#pragma unroll
+    for (int u = 0; u < kRankBatch; ++u) j[u] = (int64_t)(needle[u] % (uint64_t)a.ix.number_states);
+  } else if constexpr (std::is_void<Low>::value) index_find<kRankBatch>(a.ix, needle, live, j);
   else index_find32<Low, kRankBatch>(a.ix, needle, live, j);
+  if (a.debug_skip & 4) {  // profiling only: no random gather
+#pragma unroll
+    for (int u = 0; u < kRankBatch; ++u) j[u] = j[u] >= 0 ? (j[u] & 1023) : j[u];
+  }
   double2 xv[kRankBatch];
 #pragma unroll
   for (int u = 0; u < kRankBatch; ++u) {
@@ -822,6 +836,7 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
     if (cplx) reinterpret_cast<double2 *>(a.vals)[q] = xv[u];
     else a.vals[q] = xv[u].x;
   }
+  }  // tiles of this warp
 }
 
 // Thread per row: conj(chi) w sign times the gathered values in term order, the
@@ -1139,13 +1154,21 @@ static int64_t count_elements(OperatorDev &od, IndexData const &ix, int64_t row_
   return (int64_t)h;
 }
 
-struct MatvecScratch {
-  DeviceBuffer<double> x, xs, y;
+// Intermediates of one row chunk.  Two slots: with the pipelined split path chunk c + 1 is
+// canonicalised (stream A) while chunk c is ranked and summed (stream B).
+struct ChunkSlot {
   DeviceBuffer<uint32_t> counts, offsets;
   DeviceBuffer<uint64_t> q_rep;
   DeviceBuffer<uint8_t> q_cidx;
   DeviceBuffer<uint16_t> q_tsign;
   DeviceBuffer<double> vals;
+  cudaEvent_t orbit_done = nullptr, released = nullptr;
+};
+struct MatvecScratch {
+  DeviceBuffer<double> x, xs, y;
+  ChunkSlot slot[2];
+  cudaStream_t stream_b = nullptr;
+  cudaEvent_t inputs_ready = nullptr;
   DeviceBuffer<unsigned char> scan_tmp;
   size_t scan_tmp_bytes = 0;
   int *d_error = nullptr;
@@ -1278,27 +1301,42 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   LSB_CHECK(gather_smem <= rt.smem_optin && orbit_smem <= rt.smem_optin,
             "operator / symmetry tables do not fit in shared memory");
 
-  // Chunk of rows: its intermediates (8 + 1 bytes per matrix element) must fit the
+  // Chunk of rows: its intermediates (up to 19 bytes per matrix element) must fit the
   // scratch capacity even if every term matched every row.
   int64_t capacity = int64_t(1) << 27;
   if (char const *env = getenv("LS_B200_MV_CHUNK")) capacity = std::max<int64_t>(4096, atoll(env));
+  // Pipelined split path (experimental): two half-size slots, rank + gather + row sum of
+  // chunk c on a second stream while the orbit kernel of chunk c + 1 runs on the first -- the two are bound by
+  // different resources (memory latency vs integer issue).
+  // Measured on kagome-36: no gain (89 ms vs 86.7 ms) -- both kernels fill the machine on their own, the hardware
+  // runs them back to back -- so it is off unless LS_B200_MV_PIPELINE=1.
+  bool pipelined = false;
+  if (char const *env = getenv("LS_B200_MV_PIPELINE")) pipelined = split && T > 0 && atoi(env) != 0;
+  if (pipelined && (row_end - row_begin) * (int64_t)T <= capacity / 2) pipelined = false;  // a single chunk
+  if (pipelined) capacity /= 2;
   int64_t chunk_rows = row_end - row_begin;
   OrbitKernel orbit = nullptr;
+  int const number_slots = pipelined ? 2 : 1;
   if (queued) {
     chunk_rows = std::max<int64_t>(1, std::min<int64_t>(chunk_rows, capacity / T));
     capacity = chunk_rows * T;
-    a.counts = sc.counts.reserve((size_t)chunk_rows + 1);
-    a.offsets = sc.offsets.reserve((size_t)chunk_rows + 1);
-    if (split) a.vals = sc.vals.reserve(((size_t)capacity + 32) * (complex_vectors ? 2 : 1));
-    if (fused) {
-      a.vals = sc.vals.reserve(((size_t)capacity + 32) * (complex_vectors ? 2 : 1));
-    } else {
-      a.q_rep = sc.q_rep.reserve((size_t)capacity + 32);
-      a.q_cidx = sc.q_cidx.reserve((size_t)capacity + 32);
-      if (want_tsign) a.q_tsign = sc.q_tsign.reserve((size_t)capacity + 32);
+    for (int k = 0; k < number_slots; ++k) {
+      ChunkSlot &slot = sc.slot[k];
+      slot.counts.reserve((size_t)chunk_rows + 1);
+      slot.offsets.reserve((size_t)chunk_rows + 1);
+      if (split || fused) slot.vals.reserve(((size_t)capacity + 32) * (complex_vectors ? 2 : 1));
+      if (!fused) {
+        slot.q_rep.reserve((size_t)capacity + 32);
+        slot.q_cidx.reserve((size_t)capacity + 32);
+        if (want_tsign) slot.q_tsign.reserve((size_t)capacity + 32);
+      }
+      if (pipelined && slot.orbit_done == nullptr) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&slot.orbit_done, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&slot.released, cudaEventDisableTiming));
+      }
     }
     size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, a.counts, a.offsets, (int)(chunk_rows + 1), rt.stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, sc.slot[0].counts.ptr, sc.slot[0].offsets.ptr, (int)(chunk_rows + 1), rt.stream);
     if (tmp > sc.scan_tmp_bytes) {
       sc.scan_tmp.reserve(tmp);
       sc.scan_tmp_bytes = sc.scan_tmp.capacity;
@@ -1327,54 +1365,105 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
                   : a.ix.lows32 != nullptr ? rank_gather_kernel<uint32_t>
                                            : rank_gather_kernel<uint64_t>;
 
-  for (int64_t begin = row_begin; begin < row_end; begin += chunk_rows) {
+  // persistent grids: as many CTAs as fit the machine at once (fused keeps one CTA per four blocks)
+  unsigned orbit_resident = ~0u, rank_resident = ~0u;
+  if (queued && !fused && a.mode == kModeGroup) {
+    int per_sm = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, orbit, kOrbitThreads, orbit_smem));
+    orbit_resident = (unsigned)std::max(1, per_sm) * (unsigned)rt.sm_count;
+  }
+  if (split && queued) {
+    int per_sm = 0;
+    size_t const rank_smem = want_tsign ? ((size_t)T + (size_t)a.number_chars) * 16 : 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_gather, kRankThreads, rank_smem));
+    rank_resident = (unsigned)std::max(1, per_sm) * (unsigned)rt.sm_count;
+  }
+  cudaStream_t const stream_a = rt.stream;
+  cudaStream_t stream_b = rt.stream;
+  if (pipelined) {
+    if (sc.stream_b == nullptr) {
+      int least = 0, greatest = 0;
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      int prio = greatest;  // rank + gather first: its CTAs are short and few of them fit next to the orbit kernel's
+      if (char const *env = getenv("LS_B200_MV_PRIORITY")) prio = atoi(env) != 0 ? greatest : least;
+      CUDA_CHECK(cudaStreamCreateWithPriority(&sc.stream_b, cudaStreamNonBlocking, prio));
+      CUDA_CHECK(cudaEventCreateWithFlags(&sc.inputs_ready, cudaEventDisableTiming));
+    }
+    stream_b = sc.stream_b;
+    // stream B reads x, xs (and everything earlier work on the library stream produced)
+    CUDA_CHECK(cudaEventRecord(sc.inputs_ready, stream_a));
+    CUDA_CHECK(cudaStreamWaitEvent(stream_b, sc.inputs_ready, 0));
+  }
+
+  int64_t chunk_index = 0;
+  for (int64_t begin = row_begin; begin < row_end; begin += chunk_rows, ++chunk_index) {
     int64_t const nrows = std::min(chunk_rows, row_end - begin);
+    ChunkSlot &slot = sc.slot[pipelined ? (chunk_index & 1) : 0];
     a.chunk_begin = begin;
     a.chunk_rows = (int)nrows;
+    a.counts = slot.counts.ptr;
+    a.offsets = slot.offsets.ptr;
+    a.q_rep = slot.q_rep.ptr;
+    a.q_cidx = slot.q_cidx.ptr;
+    a.q_tsign = want_tsign ? slot.q_tsign.ptr : nullptr;
+    a.vals = slot.vals.ptr;
     if (queued) {
-      row_count_kernel<<<ceil_div((size_t)nrows + 1, 256), 256, count_smem, rt.stream>>>(a);
+      if (pipelined && chunk_index >= 2) CUDA_CHECK(cudaStreamWaitEvent(stream_a, slot.released, 0));
+      row_count_kernel<<<ceil_div((size_t)nrows + 1, 256), 256, count_smem, stream_a>>>(a);
       size_t tmp = sc.scan_tmp_bytes;
-      cub::DeviceScan::ExclusiveSum(sc.scan_tmp.ptr, tmp, a.counts, a.offsets, (int)(nrows + 1), rt.stream);
+      cub::DeviceScan::ExclusiveSum(sc.scan_tmp.ptr, tmp, a.counts, a.offsets, (int)(nrows + 1), stream_a);
       count_launch(2);
       if (profile) {
         sc.spans.emplace_back(sc.events_used, 0);
-        CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+        CUDA_CHECK(cudaEventRecord(next_event(sc), stream_a));
       }
       if (a.mode == kModeGroup) {
         // grid for the worst case (every term matches); words past the chunk's total exit at once
         size_t const max_words = (((size_t)nrows * (size_t)T + 1023) / 1024) * 32;
-        orbit<<<ceil_div(max_words, kOrbitThreads), kOrbitThreads, orbit_smem, rt.stream>>>(a);
+        unsigned const blocks = std::min<unsigned>(ceil_div(max_words, kOrbitThreads), orbit_resident);
+        orbit<<<blocks, kOrbitThreads, orbit_smem, stream_a>>>(a);
       } else {
-        orbit_scalar_kernel<<<ceil_div((size_t)nrows, 128), 128, count_smem, rt.stream>>>(a);
+        orbit_scalar_kernel<<<ceil_div((size_t)nrows, 128), 128, count_smem, stream_a>>>(a);
       }
       count_launch();
-      if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+      if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), stream_a));
+      if (pipelined) {
+        CUDA_CHECK(cudaEventRecord(slot.orbit_done, stream_a));
+        CUDA_CHECK(cudaStreamWaitEvent(stream_b, slot.orbit_done, 0));
+      }
     }
     if (profile) {
       sc.spans.emplace_back(sc.events_used, 1);
-      CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+      CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
     }
     if (fused && queued) {
-      row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, rt.stream>>>(a);
+      row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, stream_b>>>(a);
     } else if (split && queued) {
       size_t const max_tiles = ceil_div((size_t)nrows * (size_t)T, 32 * kRankBatch);
       size_t const rank_smem = a.q_tsign != nullptr ? ((size_t)T + (size_t)a.number_chars) * 16 : 0;
-      rank_gather<<<ceil_div(max_tiles, kRankThreads / 32), kRankThreads, rank_smem, rt.stream>>>(a);
+      unsigned const blocks = std::min<unsigned>(ceil_div(max_tiles, kRankThreads / 32), rank_resident);
+      rank_gather<<<blocks, kRankThreads, rank_smem, stream_b>>>(a);
       count_launch();
       if (profile) {
-        CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+        CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
         sc.spans.emplace_back(sc.events_used, 2);
-        CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+        CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
       }
       if (a.q_tsign != nullptr)
-        row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, rt.stream>>>(a);
+        row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, stream_b>>>(a);
       else
-        row_combine<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
+        row_combine<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, stream_b>>>(a);
     } else
-      gather<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
+      gather<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, stream_b>>>(a);
     count_launch();
-    if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+    if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
+    if (pipelined) CUDA_CHECK(cudaEventRecord(slot.released, stream_b));
     CUDA_CHECK(cudaGetLastError());
+  }
+  if (pipelined) {
+    // the library stream continues only after stream B has written the last rows of y
+    for (int k = 0; k < 2; ++k)
+      if (chunk_index > k) CUDA_CHECK(cudaStreamWaitEvent(stream_a, sc.slot[k].released, 0));
   }
   CUDA_CHECK(cudaEventRecord(rt.ev1, rt.stream));
 }
