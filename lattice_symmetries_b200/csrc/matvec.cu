@@ -1365,9 +1365,13 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
                   : a.ix.lows32 != nullptr ? rank_gather_kernel<uint32_t>
                                            : rank_gather_kernel<uint64_t>;
 
-  // persistent grids: as many CTAs as fit the machine at once (fused keeps one CTA per four blocks)
+  // Persistent grids: as many CTAs as fit the machine at once.  rank_gather gains 8 % from it (tables staged
+  // once, no empty CTAs); the orbit kernel LOSES 15 % (46 -> 53 ms on kagome-36: its warps then walk through
+  // their load / integer phases in lockstep instead of staggered), so it keeps one CTA per four blocks unless
+  // LS_B200_ORBIT_PERSISTENT=1.
   unsigned orbit_resident = ~0u, rank_resident = ~0u;
-  if (queued && !fused && a.mode == kModeGroup) {
+  static bool const orbit_persistent = getenv("LS_B200_ORBIT_PERSISTENT") != nullptr;
+  if (orbit_persistent && queued && !fused && a.mode == kModeGroup) {
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, orbit, kOrbitThreads, orbit_smem));
     orbit_resident = (unsigned)std::max(1, per_sm) * (unsigned)rt.sm_count;
