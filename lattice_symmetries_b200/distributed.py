@@ -27,7 +27,8 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "row_bounds", "exchange_shards", "ShardedOperator", "build_sharded", "init_process"]
+__all__ = ["shard_bounds", "block_plan", "row_bounds", "exchange_shards", "exchange_blocks", "ShardedOperator",
+           "build_sharded", "init_process"]
 
 ALIGN = 32  # candidate shards start on a multiple of 32 (one bit-sliced word)
 
@@ -39,6 +40,20 @@ def shard_bounds(total: int, world: int, rank: int, align: int = ALIGN) -> Tuple
     lo = (words * rank) // world * align
     hi = (words * (rank + 1)) // world * align
     return min(lo, total), min(hi, total)
+
+
+def block_plan(total: int, world: int, blocks_per_rank: int = 16, min_block: int = 1 << 22,
+               align: int = ALIGN) -> List[Tuple[int, int]]:
+    """Block-cyclic split of the candidate-index range [0, total): block b = [lo, hi) belongs to rank
+    b % world.  Representatives -- and the work of finding them -- are NOT uniform in the candidate
+    index: a representative is the smallest member of its orbit, so they crowd into the low indices
+    (kagome-36 on two ranks: the lower half holds all 3.15e7 of them and 3/4 of the work).  Dealing
+    out ~16 blocks per rank evens that out while every block still yields a sorted range."""
+    if total <= 0:
+        return []
+    size = max(min_block, -(-total // (world * blocks_per_rank)))
+    size = -(-size // align) * align
+    return [(lo, min(lo + size, total)) for lo in range(0, total, size)]
 
 
 def row_bounds(dim: int, world: int, rank: int) -> Tuple[int, int, int]:
@@ -73,6 +88,39 @@ def exchange_shards(local, group=None):
             src = dist.get_global_rank(group, r) if group is not None else r
             dist.broadcast(full[offsets[r]:offsets[r + 1]], src=src, group=group)
     return full, offsets
+
+
+def exchange_blocks(pieces, number_blocks: int, group=None, dtype=None, device=None):
+    """Block-cyclic counterpart of ``exchange_shards``: ``pieces`` are this rank's blocks (block
+    b = rank + k * world for k = 0, 1, ...) as 1-D tensors, each sorted; every rank receives the
+    concatenation of ALL blocks in block order plus the block offsets."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if pieces:
+        local = torch.cat(pieces) if len(pieces) > 1 else pieces[0]
+    else:
+        local = torch.empty(0, dtype=dtype, device=device)
+    per_rank = (number_blocks + world - 1) // world
+    mine = torch.zeros(max(per_rank, 1), dtype=torch.int64, device=local.device)
+    for k, piece in enumerate(pieces):
+        mine[k] = piece.numel()
+    counts = torch.zeros(world * max(per_rank, 1), dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    counts = counts.cpu().view(world, max(per_rank, 1))
+    full, rank_offsets = exchange_shards(local, group)
+    out = torch.empty_like(full)
+    block_offsets = [0]
+    within = [0] * world
+    for b in range(number_blocks):
+        r, k = b % world, b // world
+        n = int(counts[r, k])
+        src = rank_offsets[r] + within[r]
+        out[block_offsets[-1]:block_offsets[-1] + n].copy_(full[src:src + n])
+        within[r] += n
+        block_offsets.append(block_offsets[-1] + n)
+    return out, block_offsets
 
 
 # ---- CUDA side ---------------------------------------------------------------------------
@@ -116,35 +164,41 @@ def init_process(local_rank: Optional[int] = None):
 
 
 def build_sharded(basis, group=None) -> List[int]:
-    """Build ``basis`` across the ranks of ``group``: every rank scans its
-    candidate range on its own GPU, the shards are exchanged over NCCL and the
-    full sorted representative list (+ norms) is installed on every rank.
-    Returns the shard offsets (rank r built rows [offsets[r], offsets[r+1]))."""
+    """Build ``basis`` across the ranks of ``group``: every rank scans its blocks of the candidate
+    range (``block_plan``: block-cyclic, because the work is concentrated at low indices) on its own
+    GPU, the pieces are exchanged over NCCL and the full sorted representative list (+ norms) is
+    installed on every rank.  Returns the block offsets into the representative list."""
     import torch
     import torch.distributed as dist
     from . import _lib
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     total = basis.number_candidates
-    lo, hi = shard_bounds(total, world, rank)
-    d_reps, d_norms, count = basis.build_shard(lo, hi)
-    local_reps = tensor_from_pointer(d_reps, count, "u8")
-    full_reps, offsets = exchange_shards(local_reps, group)
+    plan = block_plan(total, world)
+    raw, reps, norms = [], [], []
+    with_norms = basis.has_permutation_symmetries
+    for lo, hi in plan[rank::world]:
+        d_reps, d_norms, count = basis.build_shard(lo, hi)
+        raw.append((d_reps, d_norms))
+        reps.append(tensor_from_pointer(d_reps, count, "u8"))
+        if with_norms:
+            norms.append(tensor_from_pointer(d_norms, count, "f8"))
+    full_reps, offsets = exchange_blocks(reps, len(plan), group, dtype=torch.int64, device="cuda")
     dim = offsets[-1]
     # the library takes ownership of buffers it allocated itself
     own_reps = _lib.lib.ls_b200_device_malloc(max(8 * dim, 8))
     tensor_from_pointer(own_reps, dim, "u8").copy_(full_reps)
     own_norms = None
-    if basis.has_permutation_symmetries:
-        local_norms = tensor_from_pointer(d_norms, count, "f8")
-        full_norms, _ = exchange_shards(local_norms, group)
+    if with_norms:
+        full_norms, _ = exchange_blocks(norms, len(plan), group, dtype=torch.float64, device="cuda")
         own_norms = _lib.lib.ls_b200_device_malloc(max(8 * dim, 8))
         tensor_from_pointer(own_norms, dim, "f8").copy_(full_norms)
     torch.cuda.current_stream().synchronize()
-    if d_reps:
-        _lib.lib.ls_b200_device_free(d_reps)
-    if d_norms:
-        _lib.lib.ls_b200_device_free(d_norms)
+    for d_reps, d_norms in raw:
+        if d_reps:
+            _lib.lib.ls_b200_device_free(d_reps)
+        if d_norms:
+            _lib.lib.ls_b200_device_free(d_norms)
     basis.set_representatives_device(own_reps, own_norms, dim)
     return offsets
 

@@ -17,7 +17,7 @@ for p in (str(ROOT), str(ROOT / "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-from lattice_symmetries_b200.distributed import row_bounds, shard_bounds  # noqa: E402
+from lattice_symmetries_b200.distributed import block_plan, row_bounds, shard_bounds  # noqa: E402
 
 
 def _free_port() -> int:
@@ -38,6 +38,20 @@ def test_shard_bounds_partition(total, world):
     assert prev == total
     sizes = [shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world)]
     assert max(sizes) - min(sizes) <= 64
+
+
+@pytest.mark.parametrize("total", [0, 1, 31, 4096, 2704156, 4537567650])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_block_plan_partition(total, world):
+    plan = block_plan(total, world)
+    assert sum(hi - lo for lo, hi in plan) == total
+    prev = 0
+    for lo, hi in plan:
+        assert lo == prev and lo % 32 == 0 and hi > lo
+        prev = hi
+    assert prev == total
+    if total > (1 << 22) * world * 16:
+        assert world * 16 <= len(plan) <= world * 16 + 1
 
 
 @pytest.mark.parametrize("dim", [0, 1, 5, 13, 28968])
@@ -90,6 +104,46 @@ def _worker_build(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _worker_build_blocks(rank, world, port, out):
+    """Block-cyclic build (distributed.build_sharded's plan) with the oracle standing in for the GPU."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import helpers as H
+        from lattice_symmetries_b200 import lattices as L
+        from lattice_symmetries_b200.distributed import exchange_blocks
+        from oracle import ls_oracle as oracle
+        m = L.heisenberg_chain(16)
+        p = H.Problem(m.name, m.number_sites, m.expression, hamming_weight=m.hamming_weight,
+                      spin_inversion=m.spin_inversion, symmetries=m.symmetries)
+        ob = p.oracle_basis(oracle)
+        lib = oracle.lib()
+        r_lo = int(lib.oracle_fixed_hamming_state_to_index(ob.min_state()))
+        r_hi = int(lib.oracle_fixed_hamming_state_to_index(ob.max_state()))
+        total = r_hi - r_lo + 1
+        plan = block_plan(total, world, blocks_per_rank=3, min_block=64)
+        assert len(plan) >= 2 * world
+        pieces, norms = [], []
+        for lo, hi in plan[rank::world]:
+            first = int(lib.oracle_fixed_hamming_index_to_state(r_lo + lo, m.hamming_weight))
+            last = int(lib.oracle_fixed_hamming_index_to_state(r_lo + hi - 1, m.hamming_weight))
+            local = ob.enumerate_range(first, last)
+            pieces.append(torch.from_numpy(local.view(np.int64)))
+            norms.append(torch.from_numpy(ob.group.state_info(local)[2]))
+        full, offsets = exchange_blocks(pieces, len(plan), dtype=torch.int64, device="cpu")
+        want = ob.enumerate()
+        ok = np.array_equal(full.numpy().view(np.uint64), want) and offsets[-1] == want.shape[0]
+        ok = ok and len(offsets) == len(plan) + 1
+        full_norms, _ = exchange_blocks(norms, len(plan), dtype=torch.float64, device="cpu")
+        ok = ok and np.array_equal(full_norms.numpy(), ob.group.state_info(want)[2])
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker_matvec(rank, world, port, out):
     import torch
     import torch.distributed as dist
@@ -127,7 +181,7 @@ def _worker_matvec(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_worker_build, _worker_matvec])
+@pytest.mark.parametrize("worker", [_worker_build, _worker_build_blocks, _worker_matvec])
 @pytest.mark.parametrize("world", [2, 3])
 def test_gloo(worker, world):
     import torch.multiprocessing as mp
