@@ -312,6 +312,14 @@ int64_t ls_b200_count_matrix_elements(ls_hs_operator const *op,
 int ls_b200_build_shard(ls_hs_basis const *basis, uint64_t index_begin,
                         uint64_t index_end, uint64_t **representatives_dev,
                         double **norms_dev, uint64_t *count);
+/* The same for a rank's whole block-cyclic share in one call: blocks
+ * [first_begin + k stride, first_begin + k stride + block_size), k = 0 ..
+ * number_blocks - 1 (clipped to the enumeration range); the output is their
+ * concatenation, block_counts[k] (caller-provided) the states found in block k. */
+int ls_b200_build_blocks(ls_hs_basis const *basis, uint64_t first_begin,
+                         uint64_t block_size, uint64_t stride,
+                         uint64_t number_blocks, uint64_t **representatives_dev,
+                         double **norms_dev, uint64_t *block_counts);
 uint64_t ls_b200_number_candidates(ls_hs_basis const *basis);
 /* Install an (all-gathered) device-resident representative list + norms as
  * the basis' representatives; the library takes ownership of both buffers.

@@ -177,6 +177,9 @@ PROTOTYPES = {
     "ls_b200_build_shard": (
         C.c_int, [C.POINTER(ls_hs_basis), C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                   C.POINTER(C.c_uint64)]),
+    "ls_b200_build_blocks": (
+        C.c_int, [C.POINTER(ls_hs_basis), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p),
+                  C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ls_b200_number_candidates": (C.c_uint64, [C.POINTER(ls_hs_basis)]),
     "ls_b200_set_representatives_device": (
         C.c_int, [C.POINTER(ls_hs_basis), C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),

@@ -302,6 +302,19 @@ class Basis:
             raise RuntimeError("ls_b200_build_shard failed")
         return (reps.value or 0, norms.value or 0, int(count.value))
 
+    def build_blocks(self, first_begin: int, block_size: int, stride: int, number_blocks: int):
+        """Scan the candidate blocks [first_begin + k stride, + block_size), k < number_blocks, in one call;
+        returns (reps_dev, norms_dev, counts per block); the caller owns the device buffers."""
+        reps, norms = C.c_void_p(), C.c_void_p()
+        counts = (C.c_uint64 * max(int(number_blocks), 1))()
+        status = lib.ls_b200_build_blocks(
+            C.byref(self._payload), int(first_begin), int(block_size), int(stride), int(number_blocks),
+            C.byref(reps), C.byref(norms), counts)
+        _lib.check_error()
+        if status != 0:
+            raise RuntimeError("ls_b200_build_blocks failed")
+        return (reps.value or 0, norms.value or 0, [int(c) for c in counts[:int(number_blocks)]])
+
     def set_representatives_device(self, reps_dev: int, norms_dev: int, count: int, cache_bits: int = 22) -> None:
         status = lib.ls_b200_set_representatives_device(
             C.byref(self._payload), reps_dev, norms_dev or None, int(count), cache_bits)

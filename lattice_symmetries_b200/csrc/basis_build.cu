@@ -517,29 +517,42 @@ struct BuildResult {
   uint64_t count = 0;
 };
 
-// Build the representatives whose candidate index lies in [k_begin, k_end).
-static BuildResult build_range(ls_hs_basis const *basis, uint64_t k_begin, uint64_t k_end) {
+// Build the representatives whose candidate index lies in one of the (ascending, disjoint)
+// ranges; the output is their concatenation, counts[i] the number found in range i.  One call
+// serves a rank's whole block-cyclic share: scratch and output are allocated once.
+using Ranges = std::vector<std::pair<uint64_t, uint64_t>>;
+static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<uint64_t> *counts = nullptr) {
   Runtime &rt = runtime();
   BasisInfo const info = basis_info(basis);
   LSB_CHECK(info.number_bits <= 64, "bases with more than 64 bits are not supported");
   EnumPlan const plan = make_plan(basis, info);
   EnumView const &e = plan.view;
-  k_end = std::min(k_end, e.total);
+  uint64_t candidates = 0, longest = 0;
+  for (auto &r : ranges) {
+    r.second = std::min(r.second, e.total);
+    r.first = std::min(r.first, r.second);
+    candidates += r.second - r.first;
+    longest = std::max(longest, r.second - r.first);
+  }
+  if (counts != nullptr) counts->assign(ranges.size(), 0);
   BuildResult res;
-  if (k_begin >= k_end) return res;
+  if (candidates == 0) return res;
   CUDA_CHECK(cudaEventRecord(rt.ev0, rt.stream));
 
   if (!plan.projected) {
-    uint64_t const count = k_end - k_begin;
-    CUDA_CHECK(cudaMalloc(&res.d_reps, sizeof(uint64_t) * count));
-    unsigned const blocks = (unsigned)std::min<uint64_t>((count / 32 + 256) / 256, (uint64_t)rt.sm_count * 16);
-    generate_states_kernel<<<blocks, 256, 0, rt.stream>>>(e, k_begin, count, res.d_reps);
-    count_launch();
-    CUDA_CHECK(cudaGetLastError());
-    res.count = count;
+    CUDA_CHECK(cudaMalloc(&res.d_reps, sizeof(uint64_t) * candidates));
+    for (size_t i = 0; i < ranges.size(); ++i) {
+      uint64_t const count = ranges[i].second - ranges[i].first;
+      if (count == 0) continue;
+      unsigned const blocks = (unsigned)std::min<uint64_t>((count / 32 + 256) / 256, (uint64_t)rt.sm_count * 16);
+      generate_states_kernel<<<blocks, 256, 0, rt.stream>>>(e, ranges[i].first, count, res.d_reps + res.count);
+      count_launch();
+      CUDA_CHECK(cudaGetLastError());
+      res.count += count;
+      if (counts != nullptr) (*counts)[i] = count;
+    }
   } else {
     GroupData const &g = *info.group;
-    LSB_CHECK(k_begin % 32 == 0, "shard boundaries must be multiples of 32 candidates");
     int const np = std::max(4, (g.number_bits + 3) / 4 * 4);
     bool const inv = g.spin_inversion != 0;
     char const *mode = getenv("LS_B200_BUILD");
@@ -557,10 +570,8 @@ static BuildResult build_range(ls_hs_basis const *basis, uint64_t k_begin, uint6
       CUDA_CHECK(cudaFuncSetAttribute(build_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)masks_bytes));
     }
 
-    uint64_t const words_total = (k_end - k_begin + 31) / 32;
-    uint64_t const word0 = k_begin / 32;
     uint64_t const super = uint64_t(1) << 26;  // words per super-chunk (2^31 candidates)
-    uint64_t const super_words = std::min(words_total, super);
+    uint64_t const super_words = std::min((longest + 31) / 32, super);
     uint64_t const super_blocks = (super_words + kBuildThreads - 1) / kBuildThreads;
     DeviceBuffer<uint32_t> alive, events, block_counts, block_offsets;
     DeviceBuffer<unsigned char> scan_tmp;
@@ -574,57 +585,69 @@ static BuildResult build_range(ls_hs_basis const *basis, uint64_t k_begin, uint6
 
     // Output capacity: orbit-counting estimate, grown on demand.
     uint64_t const images = (uint64_t)g.number_masks * (inv ? 2 : 1);
-    uint64_t capacity = std::min<uint64_t>(k_end - k_begin, (k_end - k_begin) / images * 5 / 4 + (1u << 16));
+    uint64_t capacity = std::min<uint64_t>(candidates, candidates / images * 5 / 4 + (1u << 16));
     CUDA_CHECK(cudaMalloc(&res.d_reps, sizeof(uint64_t) * capacity));
     CUDA_CHECK(cudaMalloc(&res.d_norms, sizeof(double) * capacity));
-    uint64_t emitted = 0;
+    uint64_t emitted = 0, scanned = 0;
     GroupView const gv = g.view();
 
-    for (uint64_t done = 0; done < words_total; done += super) {
-      uint64_t const nwords = std::min(super, words_total - done);
-      unsigned const blocks = (unsigned)((nwords + kBuildThreads - 1) / kBuildThreads);
-      // Clip the enumeration so that the tail word of this shard is masked.
-      EnumView ev = e;
-      ev.total = k_end;
-      if (use_scalar) {
-        build_flags_scalar_kernel<<<blocks, kBuildThreads, masks_bytes, rt.stream>>>(
-            gv, ev, word0 + done, nwords, alive.ptr, events.ptr, block_counts.ptr);
-      } else {
-        flags_kernel<<<blocks, kBuildThreads, smem_bitsliced, rt.stream>>>(
-            gv, ev, word0 + done, nwords, identity_first ? 1 : 0, alive.ptr, events.ptr, block_counts.ptr);
-      }
-      count_launch();
-      CUDA_CHECK(cudaGetLastError());
-      CUDA_CHECK(cudaMemsetAsync(block_counts.ptr + blocks, 0, sizeof(uint32_t), rt.stream));
-      cub::DeviceScan::ExclusiveSum(scan_tmp.ptr, tmp_bytes, block_counts.ptr, block_offsets.ptr, (int)(blocks + 1), rt.stream);
-      count_launch();
-      uint32_t chunk_total = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&chunk_total, block_offsets.ptr + blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, rt.stream));
-      CUDA_CHECK(cudaStreamSynchronize(rt.stream));
-      if (emitted + chunk_total > capacity) {
-        uint64_t const remaining_words = words_total - done;
-        uint64_t const projected = emitted + (uint64_t)((double)chunk_total * (double)remaining_words / (double)nwords * 1.1) + (1u << 16);
-        uint64_t const new_capacity = std::max<uint64_t>(emitted + chunk_total, std::min<uint64_t>(projected, k_end - k_begin));
-        uint64_t *new_reps = nullptr;
-        double *new_norms = nullptr;
-        CUDA_CHECK(cudaMalloc(&new_reps, sizeof(uint64_t) * new_capacity));
-        CUDA_CHECK(cudaMalloc(&new_norms, sizeof(double) * new_capacity));
-        CUDA_CHECK(cudaMemcpyAsync(new_reps, res.d_reps, sizeof(uint64_t) * emitted, cudaMemcpyDeviceToDevice, rt.stream));
-        CUDA_CHECK(cudaMemcpyAsync(new_norms, res.d_norms, sizeof(double) * emitted, cudaMemcpyDeviceToDevice, rt.stream));
-        CUDA_CHECK(cudaStreamSynchronize(rt.stream));
-        cudaFree(res.d_reps);
-        cudaFree(res.d_norms);
-        res.d_reps = new_reps;
-        res.d_norms = new_norms;
-        capacity = new_capacity;
-      }
-      if (chunk_total > 0) {
-        build_scatter_kernel<<<blocks, kBuildThreads, masks_bytes, rt.stream>>>(
-            gv, ev, word0 + done, nwords, alive.ptr, events.ptr, block_offsets.ptr, emitted, res.d_reps, res.d_norms);
+    for (size_t i = 0; i < ranges.size(); ++i) {
+      uint64_t const k_begin = ranges[i].first, k_end = ranges[i].second;
+      if (k_begin >= k_end) continue;
+      LSB_CHECK(k_begin % 32 == 0, "shard boundaries must be multiples of 32 candidates");
+      uint64_t const words_total = (k_end - k_begin + 31) / 32;
+      uint64_t const word0 = k_begin / 32;
+      uint64_t const emitted_before = emitted;
+      for (uint64_t done = 0; done < words_total; done += super) {
+        uint64_t const nwords = std::min(super, words_total - done);
+        unsigned const blocks = (unsigned)((nwords + kBuildThreads - 1) / kBuildThreads);
+        // Clip the enumeration so that the tail word of this range is masked.
+        EnumView ev = e;
+        ev.total = k_end;
+        if (use_scalar) {
+          build_flags_scalar_kernel<<<blocks, kBuildThreads, masks_bytes, rt.stream>>>(
+              gv, ev, word0 + done, nwords, alive.ptr, events.ptr, block_counts.ptr);
+        } else {
+          flags_kernel<<<blocks, kBuildThreads, smem_bitsliced, rt.stream>>>(
+              gv, ev, word0 + done, nwords, identity_first ? 1 : 0, alive.ptr, events.ptr, block_counts.ptr);
+        }
         count_launch();
         CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemsetAsync(block_counts.ptr + blocks, 0, sizeof(uint32_t), rt.stream));
+        cub::DeviceScan::ExclusiveSum(scan_tmp.ptr, tmp_bytes, block_counts.ptr, block_offsets.ptr, (int)(blocks + 1), rt.stream);
+        count_launch();
+        uint32_t chunk_total = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&chunk_total, block_offsets.ptr + blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, rt.stream));
+        CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+        scanned += std::min<uint64_t>(nwords * 32, k_end - k_begin - done * 32);
+        if (emitted + chunk_total > capacity) {
+          // density so far, with head room; never more than what is left to scan
+          uint64_t const remaining = candidates - scanned;
+          uint64_t const projected =
+              emitted + chunk_total + std::min<uint64_t>(remaining, (uint64_t)((double)(emitted + chunk_total) / (double)scanned * (double)remaining * 1.1) + (1u << 16));
+          uint64_t const new_capacity = std::max<uint64_t>(emitted + chunk_total, projected);
+          uint64_t *new_reps = nullptr;
+          double *new_norms = nullptr;
+          CUDA_CHECK(cudaMalloc(&new_reps, sizeof(uint64_t) * new_capacity));
+          CUDA_CHECK(cudaMalloc(&new_norms, sizeof(double) * new_capacity));
+          CUDA_CHECK(cudaMemcpyAsync(new_reps, res.d_reps, sizeof(uint64_t) * emitted, cudaMemcpyDeviceToDevice, rt.stream));
+          CUDA_CHECK(cudaMemcpyAsync(new_norms, res.d_norms, sizeof(double) * emitted, cudaMemcpyDeviceToDevice, rt.stream));
+          CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+          cudaFree(res.d_reps);
+          cudaFree(res.d_norms);
+          res.d_reps = new_reps;
+          res.d_norms = new_norms;
+          capacity = new_capacity;
+        }
+        if (chunk_total > 0) {
+          build_scatter_kernel<<<blocks, kBuildThreads, masks_bytes, rt.stream>>>(
+              gv, ev, word0 + done, nwords, alive.ptr, events.ptr, block_offsets.ptr, emitted, res.d_reps, res.d_norms);
+          count_launch();
+          CUDA_CHECK(cudaGetLastError());
+        }
+        emitted += chunk_total;
       }
-      emitted += chunk_total;
+      if (counts != nullptr) (*counts)[i] = emitted - emitted_before;
     }
     res.count = emitted;
   }
@@ -634,6 +657,10 @@ static BuildResult build_range(ls_hs_basis const *basis, uint64_t k_begin, uint6
   CUDA_CHECK(cudaEventElapsedTime(&ms, rt.ev0, rt.ev1));
   rt.last_build_ms = ms;
   return res;
+}
+
+static BuildResult build_range(ls_hs_basis const *basis, uint64_t k_begin, uint64_t k_end) {
+  return build_ranges(basis, Ranges{{k_begin, k_end}});
 }
 
 static void free_pinned(void *p) {
@@ -721,6 +748,30 @@ void ensure_norms(IndexData &ix, GroupData const &g) {
 using namespace lsb;
 
 extern "C" {
+
+int ls_b200_build_blocks(ls_hs_basis const *basis, uint64_t first_begin, uint64_t block_size, uint64_t stride,
+                         uint64_t number_blocks, uint64_t **representatives_dev, double **norms_dev,
+                         uint64_t *block_counts) {
+  int status = -1;
+  guarded(__func__, [&] {
+    auto const t0 = std::chrono::steady_clock::now();
+    Ranges ranges;
+    for (uint64_t b = 0; b < number_blocks; ++b)
+      ranges.emplace_back(first_begin + b * stride, first_begin + b * stride + block_size);
+    std::vector<uint64_t> counts;
+    BuildResult r = build_ranges(basis, ranges, &counts);
+    for (uint64_t b = 0; b < number_blocks; ++b) block_counts[b] = counts[(size_t)b];
+    if (getenv("LS_B200_PROFILE") != nullptr)
+      fprintf(stderr, "[ls_b200] build_blocks %llu x [%llu + k %llu, +%llu): %llu states, device %.2f ms, wall %.2f ms\n",
+              (unsigned long long)number_blocks, (unsigned long long)first_begin, (unsigned long long)stride,
+              (unsigned long long)block_size, (unsigned long long)r.count, runtime().last_build_ms,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    *representatives_dev = r.d_reps;
+    if (norms_dev != nullptr) *norms_dev = r.d_norms; else cudaFree(r.d_norms);
+    status = 0;
+  });
+  return status;
+}
 
 uint64_t ls_b200_number_candidates(ls_hs_basis const *basis) {
   uint64_t total = 0;

@@ -175,14 +175,22 @@ def build_sharded(basis, group=None) -> List[int]:
     rank = dist.get_rank(group)
     total = basis.number_candidates
     plan = block_plan(total, world)
-    raw, reps, norms = [], [], []
+    reps, norms = [], []
     with_norms = basis.has_permutation_symmetries
-    for lo, hi in plan[rank::world]:
-        d_reps, d_norms, count = basis.build_shard(lo, hi)
-        raw.append((d_reps, d_norms))
-        reps.append(tensor_from_pointer(d_reps, count, "u8"))
-        if with_norms:
-            norms.append(tensor_from_pointer(d_norms, count, "f8"))
+    mine = plan[rank::world]
+    d_reps = d_norms = 0
+    if mine:
+        size = plan[0][1] - plan[0][0]
+        d_reps, d_norms, counts = basis.build_blocks(mine[0][0], size, size * world, len(mine))
+        all_reps = tensor_from_pointer(d_reps, sum(counts), "u8")
+        all_norms = tensor_from_pointer(d_norms, sum(counts), "f8") if with_norms else None
+        start = 0
+        for c in counts:
+            reps.append(all_reps[start:start + c])
+            if with_norms:
+                norms.append(all_norms[start:start + c])
+            start += c
+    raw = [(d_reps, d_norms)]
     full_reps, offsets = exchange_blocks(reps, len(plan), group, dtype=torch.int64, device="cuda")
     dim = offsets[-1]
     # the library takes ownership of buffers it allocated itself

@@ -141,6 +141,41 @@ def test_sharded_build_concatenates(oracle, built, name, shards):
     assert np.array_equal(np.concatenate(parts), reps)
 
 
+@pytest.mark.parametrize("name", ["chain24_symm", "kagome18_c2", "hubbard_2x4", "hphi01"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_block_cyclic_build_interleaves(oracle, built, name, world):
+    """A rank's block-cyclic share in one call (ls_b200_build_blocks); the ranks' pieces interleave
+    block by block to the full sorted list, with norms."""
+    from lattice_symmetries_b200 import _lib
+    from lattice_symmetries_b200.distributed import block_plan
+    p, (ob, reps, *_), basis, op = built(name, oracle)
+    fresh = p.product_basis()
+    total = fresh.number_candidates
+    plan = block_plan(total, world, blocks_per_rank=3, min_block=64)
+    size = plan[0][1] - plan[0][0]
+    pieces = {}
+    for rank in range(world):
+        mine = plan[rank::world]
+        if not mine:
+            continue
+        d_reps, d_norms, counts = fresh.build_blocks(mine[0][0], size, size * world, len(mine))
+        states = _lib.device_to_numpy(d_reps, sum(counts), np.uint64)
+        norms = _lib.device_to_numpy(d_norms, sum(counts), np.float64) if d_norms else None
+        start = 0
+        for k, c in enumerate(counts):
+            pieces[rank + k * world] = (states[start:start + c], None if norms is None else norms[start:start + c])
+            start += c
+        _lib.lib.ls_b200_device_free(d_reps)
+        if d_norms:
+            _lib.lib.ls_b200_device_free(d_norms)
+    assert sorted(pieces) == list(range(len(plan)))
+    assert np.array_equal(np.concatenate([pieces[b][0] for b in range(len(plan))]), reps)
+    if ob.group is not None and pieces[0][1] is not None:
+        want = ob.group.state_info(reps)[2]
+        got = np.concatenate([pieces[b][1] for b in range(len(plan))])
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
 def test_basis_lists_reference_known_answers():
     """python/test/test_api.py:38-42, python/run_tests.py:102-113."""
     ls = _ls()
