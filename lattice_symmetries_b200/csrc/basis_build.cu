@@ -272,16 +272,20 @@ __device__ __noinline__ double lane_norm_sum(GroupView const &g, uint64_t const 
 // One thread = 32 consecutive candidates (one "word").
 //   alive_out[w]  bit k: candidate 32w+k is a representative with norm > 0
 //   event_out[w]  bit k: ... and has a non-trivial stabiliser (norm != 1/sqrt|G|)
-template <int NP, bool INV>
+// FILTER: first pass of the two-phase build -- only the first `rows` table rows, only the
+// "some image is smaller" verdict (no stabiliser events, no norms).  `list` != nullptr: the 32
+// states of word w are list[32 w ..] (the survivors of the filter) instead of candidates by index.
+template <int NP, bool INV, bool FILTER>
 __global__ void __launch_bounds__(kBuildThreads, (NP <= 40 ? 5 : NP <= 52 ? 4 : 3))  // NP <= 40: five CTAs per SM (<= 102 registers)
 build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint64_t number_words,
-                             int identity_first, uint32_t *__restrict__ alive_out,
-                             uint32_t *__restrict__ event_out, uint32_t *__restrict__ block_counts) {
+                             int identity_first, int rows, uint64_t const *__restrict__ list, uint64_t list_count,
+                             uint32_t *__restrict__ alive_out, uint32_t *__restrict__ event_out,
+                             uint32_t *__restrict__ block_counts) {
   extern __shared__ unsigned char smem_raw[];
   uint64_t *smasks = reinterpret_cast<uint64_t *>(smem_raw);
   uint32_t *planes = reinterpret_cast<uint32_t *>(smasks + (size_t)g.depth * g.number_masks);
   __shared__ uint32_t warp_counts[kBuildThreads / 32];
-  stage_masks<uint64_t>(g, smasks);
+  if (!FILTER) stage_masks<uint64_t>(g, smasks);
 
   int const tid = threadIdx.x;
   uint64_t const w = (uint64_t)blockIdx.x * kBuildThreads + tid;
@@ -292,18 +296,28 @@ build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint6
 
   if (w < number_words) {
     uint64_t const k0 = (word_begin + w) * 32;
-    uint64_t const remaining = e.total - k0;
+    uint64_t const remaining = (list != nullptr ? list_count : e.total) - k0;
     int const valid = remaining >= 32 ? 32 : (int)remaining;
     alive = valid == 32 ? 0xffffffffu : ((1u << valid) - 1u);
     uint32_t lo[32], hi[32];
-    CandidateIter it;
-    it.init(e, k0);
+    if (list != nullptr) {
+      uint64_t v = 0;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      uint64_t const v = it.value(e);
-      lo[k] = (uint32_t)v;
-      hi[k] = (uint32_t)(v >> 32);
-      if (k + 1 < valid) it.next(e);
+      for (int k = 0; k < 32; ++k) {
+        if (k < valid) v = __ldg(list + k0 + k);
+        lo[k] = (uint32_t)v;
+        hi[k] = (uint32_t)(v >> 32);
+      }
+    } else {
+      CandidateIter it;
+      it.init(e, k0);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        uint64_t const v = it.value(e);
+        lo[k] = (uint32_t)v;
+        hi[k] = (uint32_t)(v >> 32);
+        if (k + 1 < valid) it.next(e);
+      }
     }
     transpose32(lo);
     if (NP > 32) transpose32(hi);
@@ -315,7 +329,7 @@ build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint6
   __syncwarp();  // a thread only ever reads its own column
 
   unsigned char const *column = reinterpret_cast<unsigned char const *>(planes + tid);
-  int const G = g.number_masks;
+  int const G = min(rows, g.number_masks);
   int const nbits = g.number_bits;
 #pragma unroll 1
   for (int j = 0; j < G; ++j) {
@@ -339,15 +353,20 @@ build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint6
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       uint32_t const z = *reinterpret_cast<uint32_t const *>(column + off[i]);
-      cmp_step(z, xr[i], lt, eq);
+      if (FILTER) {
+        uint32_t const d = z ^ xr[i];
+        lt = (d & xr[i]) | (~d & lt);
+      } else {
+        cmp_step(z, xr[i], lt, eq);
+      }
     }
     alive &= ~lt;
-    events |= (identity_first && j == 0) ? 0u : eq;
+    if (!FILTER) events |= (identity_first && j == 0) ? 0u : eq;
     if (__all_sync(0xffffffffu, alive == 0)) break;
   }
   events &= alive;
   // Lanes with a non-trivial stabiliser: decide norm > 0 with the exact sum.
-  uint32_t pending = events;
+  uint32_t pending = FILTER ? 0u : events;
   while (pending != 0) {
     int const lane = __ffs((int)pending) - 1;
     pending &= pending - 1;
@@ -359,7 +378,7 @@ build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint6
   }
   if (w < number_words) {
     alive_out[w] = alive;
-    event_out[w] = events;
+    if (!FILTER) event_out[w] = events;
   }
   // block survivor count
   unsigned c = (unsigned)__popc(alive);
@@ -434,17 +453,18 @@ build_flags_scalar_kernel(GroupView g, EnumView e, uint64_t word_begin, uint64_t
 // ---- pass C: ordered scatter ------------------------------------------------------------------
 __global__ void __launch_bounds__(kBuildThreads)
 build_scatter_kernel(GroupView g, EnumView e, uint64_t word_begin, uint64_t number_words,
-                     uint32_t const *__restrict__ alive_in, uint32_t const *__restrict__ event_in,
-                     uint32_t const *__restrict__ block_offsets, uint64_t out_base,
-                     uint64_t *__restrict__ reps_out, double *__restrict__ norms_out) {
+                     uint64_t const *__restrict__ list, uint32_t const *__restrict__ alive_in,
+                     uint32_t const *__restrict__ event_in, uint32_t const *__restrict__ block_offsets,
+                     uint64_t out_base, uint64_t *__restrict__ reps_out, double *__restrict__ norms_out) {
   extern __shared__ unsigned char smem_raw[];
   uint64_t *smasks = reinterpret_cast<uint64_t *>(smem_raw);
   __shared__ uint32_t warp_sums[kBuildThreads / 32];
-  stage_masks<uint64_t>(g, smasks);
+  // norms_out == nullptr: first phase of the two-phase build, only the surviving states are wanted
+  if (norms_out != nullptr) stage_masks<uint64_t>(g, smasks);
   int const tid = threadIdx.x;
   uint64_t const w = (uint64_t)blockIdx.x * kBuildThreads + tid;
   uint32_t const alive = (w < number_words) ? alive_in[w] : 0u;
-  uint32_t const events = (w < number_words) ? event_in[w] : 0u;
+  uint32_t const events = (w < number_words && event_in != nullptr) ? event_in[w] : 0u;
   // exclusive scan of popcounts within the block
   unsigned const mine = (unsigned)__popc(alive);
   unsigned incl = mine;
@@ -463,10 +483,10 @@ build_scatter_kernel(GroupView g, EnumView e, uint64_t word_begin, uint64_t numb
   uint64_t const k0 = (word_begin + w) * 32;
   int const last = 31 - __clz((int)alive);
   CandidateIter it;
-  it.init(e, k0);
+  if (list == nullptr) it.init(e, k0);
   for (int k = 0; k <= last; ++k) {
     if ((alive >> k) & 1u) {
-      uint64_t const x = it.value(e);
+      uint64_t const x = list != nullptr ? __ldg(list + k0 + k) : it.value(e);
       double norm = trivial_norm;
       if ((events >> k) & 1u) {
         uint64_t rep;
@@ -475,38 +495,40 @@ build_scatter_kernel(GroupView g, EnumView e, uint64_t word_begin, uint64_t numb
         norm = norm_from_sum(g, n);
       }
       reps_out[pos] = x;
-      norms_out[pos] = norm;
+      if (norms_out != nullptr) norms_out[pos] = norm;
       ++pos;
     }
-    if (k < last) it.next(e);
+    if (k < last && list == nullptr) it.next(e);
   }
 }
 
 // ---- host driver ---------------------------------------------------------------------------------
-using FlagsKernel = void (*)(GroupView, EnumView, uint64_t, uint64_t, int, uint32_t *, uint32_t *, uint32_t *);
+using FlagsKernel = void (*)(GroupView, EnumView, uint64_t, uint64_t, int, int, uint64_t const *, uint64_t, uint32_t *,
+                             uint32_t *, uint32_t *);
 
 template <int NP>
-static FlagsKernel pick_inv(bool inv) {
-  return inv ? build_flags_bitsliced_kernel<NP, true> : build_flags_bitsliced_kernel<NP, false>;
+static FlagsKernel pick_inv(bool inv, bool filter) {
+  if (filter) return inv ? build_flags_bitsliced_kernel<NP, true, true> : build_flags_bitsliced_kernel<NP, false, true>;
+  return inv ? build_flags_bitsliced_kernel<NP, true, false> : build_flags_bitsliced_kernel<NP, false, false>;
 }
-static FlagsKernel pick_flags_kernel(int np, bool inv) {
+static FlagsKernel pick_flags_kernel(int np, bool inv, bool filter) {
   switch (np) {
-    case 4: return pick_inv<4>(inv);
-    case 8: return pick_inv<8>(inv);
-    case 12: return pick_inv<12>(inv);
-    case 16: return pick_inv<16>(inv);
-    case 20: return pick_inv<20>(inv);
-    case 24: return pick_inv<24>(inv);
-    case 28: return pick_inv<28>(inv);
-    case 32: return pick_inv<32>(inv);
-    case 36: return pick_inv<36>(inv);
-    case 40: return pick_inv<40>(inv);
-    case 44: return pick_inv<44>(inv);
-    case 48: return pick_inv<48>(inv);
-    case 52: return pick_inv<52>(inv);
-    case 56: return pick_inv<56>(inv);
-    case 60: return pick_inv<60>(inv);
-    case 64: return pick_inv<64>(inv);
+    case 4: return pick_inv<4>(inv, filter);
+    case 8: return pick_inv<8>(inv, filter);
+    case 12: return pick_inv<12>(inv, filter);
+    case 16: return pick_inv<16>(inv, filter);
+    case 20: return pick_inv<20>(inv, filter);
+    case 24: return pick_inv<24>(inv, filter);
+    case 28: return pick_inv<28>(inv, filter);
+    case 32: return pick_inv<32>(inv, filter);
+    case 36: return pick_inv<36>(inv, filter);
+    case 40: return pick_inv<40>(inv, filter);
+    case 44: return pick_inv<44>(inv, filter);
+    case 48: return pick_inv<48>(inv, filter);
+    case 52: return pick_inv<52>(inv, filter);
+    case 56: return pick_inv<56>(inv, filter);
+    case 60: return pick_inv<60>(inv, filter);
+    case 64: return pick_inv<64>(inv, filter);
   }
   return nullptr;
 }
@@ -562,9 +584,19 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
     if (!use_scalar && (smem_bitsliced > rt.smem_optin || !upload_plane_offsets(g, np, kBuildThreads))) use_scalar = true;
     LSB_CHECK(masks_bytes <= rt.smem_optin, "symmetry group too large for shared memory staging");
     bool const identity_first = identity_is_first(g);
-    FlagsKernel flags_kernel = use_scalar ? nullptr : pick_flags_kernel(np, inv);
+    FlagsKernel flags_kernel = use_scalar ? nullptr : pick_flags_kernel(np, inv, false);
     if (flags_kernel != nullptr && smem_bitsliced > 48 * 1024)
       CUDA_CHECK(cudaFuncSetAttribute(flags_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bitsliced));
+    // Two-phase build: a candidate survives the first few group elements with probability ~1/(2 K + 1), so
+    // the full orbit walk (and its stabiliser bookkeeping) runs only on the compacted survivors of a cheap
+    // K-row filter.  LS_B200_BUILD=onepass keeps the single full pass; LS_B200_BUILD_FILTER_ROWS sets K.
+    int filter_rows = 8;
+    if (char const *env = getenv("LS_B200_BUILD_FILTER_ROWS")) filter_rows = std::max(1, atoi(env));
+    bool const two_phase = !use_scalar && g.number_masks >= 4 * filter_rows && !(mode != nullptr && strcmp(mode, "onepass") == 0);
+    FlagsKernel filter_kernel = two_phase ? pick_flags_kernel(np, inv, true) : nullptr;
+    if (filter_kernel != nullptr && smem_bitsliced > 48 * 1024)
+      CUDA_CHECK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bitsliced));
+    DeviceBuffer<uint64_t> survivors;
     if (masks_bytes > 48 * 1024) {
       CUDA_CHECK(cudaFuncSetAttribute(build_flags_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)masks_bytes));
       CUDA_CHECK(cudaFuncSetAttribute(build_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)masks_bytes));
@@ -604,21 +636,61 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
         // Clip the enumeration so that the tail word of this range is masked.
         EnumView ev = e;
         ev.total = k_end;
+        // `source` / `source_words` / `source_blocks`: what the final scatter reads -- candidates by index, or
+        // (two-phase) the compacted survivors of the filter
+        uint64_t const *source = nullptr;
+        uint64_t source_words = nwords;
+        unsigned source_blocks = blocks;
+        uint64_t source_word0 = word0 + done;
+        auto scan_counts = [&](unsigned nblocks) -> uint32_t {
+          CUDA_CHECK(cudaMemsetAsync(block_counts.ptr + nblocks, 0, sizeof(uint32_t), rt.stream));
+          cub::DeviceScan::ExclusiveSum(scan_tmp.ptr, tmp_bytes, block_counts.ptr, block_offsets.ptr, (int)(nblocks + 1), rt.stream);
+          count_launch();
+          uint32_t total = 0;
+          CUDA_CHECK(cudaMemcpyAsync(&total, block_offsets.ptr + nblocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, rt.stream));
+          CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+          return total;
+        };
+        uint32_t chunk_total = 0;
         if (use_scalar) {
           build_flags_scalar_kernel<<<blocks, kBuildThreads, masks_bytes, rt.stream>>>(
               gv, ev, word0 + done, nwords, alive.ptr, events.ptr, block_counts.ptr);
-        } else {
+          count_launch();
+          CUDA_CHECK(cudaGetLastError());
+          chunk_total = scan_counts(blocks);
+        } else if (!two_phase) {
           flags_kernel<<<blocks, kBuildThreads, smem_bitsliced, rt.stream>>>(
-              gv, ev, word0 + done, nwords, identity_first ? 1 : 0, alive.ptr, events.ptr, block_counts.ptr);
+              gv, ev, word0 + done, nwords, identity_first ? 1 : 0, g.number_masks, nullptr, 0, alive.ptr, events.ptr,
+              block_counts.ptr);
+          count_launch();
+          CUDA_CHECK(cudaGetLastError());
+          chunk_total = scan_counts(blocks);
+        } else {
+          // phase 1: K-row filter over the candidates, survivors compacted (in order) into a list
+          filter_kernel<<<blocks, kBuildThreads, smem_bitsliced, rt.stream>>>(
+              gv, ev, word0 + done, nwords, identity_first ? 1 : 0, filter_rows, nullptr, 0, alive.ptr, events.ptr,
+              block_counts.ptr);
+          count_launch();
+          CUDA_CHECK(cudaGetLastError());
+          uint32_t const alive_total = scan_counts(blocks);
+          if (alive_total > 0) {
+            survivors.reserve((size_t)alive_total + 32);
+            build_scatter_kernel<<<blocks, kBuildThreads, masks_bytes, rt.stream>>>(
+                gv, ev, word0 + done, nwords, nullptr, alive.ptr, nullptr, block_offsets.ptr, 0, survivors.ptr, nullptr);
+            count_launch();
+            // phase 2: the full walk on the survivors
+            source = survivors.ptr;
+            source_words = ((uint64_t)alive_total + 31) / 32;
+            source_blocks = (unsigned)((source_words + kBuildThreads - 1) / kBuildThreads);
+            source_word0 = 0;
+            flags_kernel<<<source_blocks, kBuildThreads, smem_bitsliced, rt.stream>>>(
+                gv, ev, 0, source_words, identity_first ? 1 : 0, g.number_masks, survivors.ptr, alive_total, alive.ptr,
+                events.ptr, block_counts.ptr);
+            count_launch();
+            CUDA_CHECK(cudaGetLastError());
+            chunk_total = scan_counts(source_blocks);
+          }
         }
-        count_launch();
-        CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaMemsetAsync(block_counts.ptr + blocks, 0, sizeof(uint32_t), rt.stream));
-        cub::DeviceScan::ExclusiveSum(scan_tmp.ptr, tmp_bytes, block_counts.ptr, block_offsets.ptr, (int)(blocks + 1), rt.stream);
-        count_launch();
-        uint32_t chunk_total = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&chunk_total, block_offsets.ptr + blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, rt.stream));
-        CUDA_CHECK(cudaStreamSynchronize(rt.stream));
         scanned += std::min<uint64_t>(nwords * 32, k_end - k_begin - done * 32);
         if (emitted + chunk_total > capacity) {
           // density so far, with head room; never more than what is left to scan
@@ -640,8 +712,9 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
           capacity = new_capacity;
         }
         if (chunk_total > 0) {
-          build_scatter_kernel<<<blocks, kBuildThreads, masks_bytes, rt.stream>>>(
-              gv, ev, word0 + done, nwords, alive.ptr, events.ptr, block_offsets.ptr, emitted, res.d_reps, res.d_norms);
+          build_scatter_kernel<<<source_blocks, kBuildThreads, masks_bytes, rt.stream>>>(
+              gv, ev, source_word0, source_words, source, alive.ptr, events.ptr, block_offsets.ptr, emitted, res.d_reps,
+              res.d_norms);
           count_launch();
           CUDA_CHECK(cudaGetLastError());
         }

@@ -98,7 +98,7 @@ def test_build_matches_oracle(oracle, built, name):
 
 
 @pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome12_complex", "kagome24_c2v_inv"])
-@pytest.mark.parametrize("mode", ["scalar", "bitsliced"])
+@pytest.mark.parametrize("mode", ["scalar", "bitsliced", "onepass"])
 def test_build_kernel_variants_agree(oracle, name, mode, monkeypatch):
     """Both pass-A kernels (bit-sliced plane renaming / scalar Benes walk) emit the oracle's list."""
     monkeypatch.setenv("LS_B200_BUILD", mode)
