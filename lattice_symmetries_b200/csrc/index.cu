@@ -23,6 +23,7 @@ IndexView IndexData::view() const {
   v.steps = steps;
   v.sub_info = d_sub_info;
   v.subtab = d_subtab;
+  v.entry8 = d_entry8;
   return v;
 }
 
@@ -34,6 +35,7 @@ IndexData::~IndexData() {
   cudaFree(d_lows32);
   cudaFree(d_sub_info);
   cudaFree(d_subtab);
+  cudaFree(d_entry8);
   cudaFree(d_norms);
   magic = 0;
 }
@@ -90,7 +92,8 @@ constexpr int kSubTargetLog2 = 3; // ... of about 2^3 entries per slot
 constexpr int kMaxSubBits = 24;
 
 __device__ __forceinline__ int sub_bits(uint32_t n, int shift) {
-  if (n <= (uint32_t)kDenseBucket || shift <= 0) return 0;
+  // (positions inside a sub-table are packed into 26 bits; larger buckets -- never seen -- are searched directly)
+  if (n <= (uint32_t)kDenseBucket || shift <= 0 || n >= (1u << 26)) return 0;
   int const len = 32 - __clz(n - 1);  // ceil(log2 n)
   return max(1, min(min(shift, kMaxSubBits), len - kSubTargetLog2));
 }
@@ -111,7 +114,7 @@ sub_sizes_kernel(uint32_t const *__restrict__ offsets, int64_t number_buckets, i
 // place by sub_info (first[p] is read before).
 __global__ void __launch_bounds__(256)
 sub_fill_kernel(IndexView ix, uint32_t const *__restrict__ first, uint32_t *__restrict__ units_then_info,
-                uint32_t *__restrict__ subtab, unsigned long long *__restrict__ max_window) {
+                uint32_t *__restrict__ subtab, uint2 *__restrict__ entry8, unsigned long long *__restrict__ max_window) {
   int const lane = threadIdx.x & 31;
   int64_t const warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t const warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -123,7 +126,10 @@ sub_fill_kernel(IndexView ix, uint32_t const *__restrict__ first, uint32_t *__re
     int const p2 = sub_bits(n, ix.shift);
     if (p2 == 0) {
       widest = max(widest, n);
-      if (lane == 0) units_then_info[p] = 0;
+      if (lane == 0) {
+        units_then_info[p] = 0;
+        entry8[p] = make_uint2(lo, n);  // a plain length: n <= kDenseBucket, or an oversized bucket below 2^27
+      }
       continue;
     }
     uint32_t const t = first[p];
@@ -146,7 +152,23 @@ sub_fill_kernel(IndexView ix, uint32_t const *__restrict__ first, uint32_t *__re
     __syncwarp();
     for (uint32_t e = lane; e < slots; e += 32) widest = max(widest, tab[e + 1] - tab[e]);
     __syncwarp();
-    if (lane == 0) units_then_info[p] = ((uint32_t)p2 << 27) | t;
+    // pack: position << 6 | min(length, 63), 32 entries at a time in ascending order (an entry's length needs its
+    // right neighbour still unpacked)
+    for (uint32_t base = 0; base <= slots; base += 32) {
+      uint32_t const e = base + lane;
+      uint32_t v0 = 0, v1 = 0;
+      if (e <= slots) {
+        v0 = tab[e];
+        v1 = e < slots ? tab[e + 1] : v0;
+      }
+      __syncwarp();
+      if (e <= slots) tab[e] = (v0 << 6) | min(v1 - v0, 63u);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      units_then_info[p] = ((uint32_t)p2 << 27) | t;
+      entry8[p] = make_uint2(lo, ((uint32_t)p2 << 27) | t);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) widest = max(widest, __shfl_xor_sync(0xffffffffu, widest, o));
@@ -232,9 +254,11 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
     // (no 32-bit wrap: a crowded bucket of n states adds at most n / 64 + 1 units and n sums to < 2^32)
     if (total_units > 0 && total_units < (1u << 27)) {
       CUDA_CHECK(cudaMalloc(&ix.d_subtab, sizeof(uint32_t) * (size_t)total_units * 8));
+      CUDA_CHECK(cudaMalloc(&ix.d_entry8, sizeof(uint2) * (size_t)nb));
       IndexView v = ix.view();
       v.sub_info = nullptr;
-      sub_fill_kernel<<<blocks, 256, 0, rt.stream>>>(v, d_first, d_units, ix.d_subtab, d_max);
+      v.entry8 = nullptr;
+      sub_fill_kernel<<<blocks, 256, 0, rt.stream>>>(v, d_first, d_units, ix.d_subtab, ix.d_entry8, d_max);
       count_launch();
       ix.d_sub_info = d_units;
       d_units = nullptr;

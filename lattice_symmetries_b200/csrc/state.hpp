@@ -59,6 +59,7 @@ struct IndexData {
   uint32_t *d_lows32 = nullptr;  // (16 < shift <= 32)
   uint32_t *d_sub_info = nullptr;  // second-level tables of the crowded buckets (IndexView)
   uint32_t *d_subtab = nullptr;
+  uint2 *d_entry8 = nullptr;       // level 1 packed for the hot kernels (IndexView::entry8)
   double *d_norms = nullptr;  // state_info norms of the representatives (lazy)
 
   IndexView view() const;

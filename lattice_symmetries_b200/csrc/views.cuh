@@ -53,7 +53,12 @@ struct IndexView {
   // table at subtab + 8 t, whose entries k2, k2 + 1 bracket the window relative to the
   // bucket's start.
   uint32_t const *sub_info;   // [2^prefix] or nullptr
+  // subtab entries: (position relative to the bucket's start) << 6 | min(window length, 63); a length
+  // field of 63 means "look at the next entry".  One 4-byte load brackets the window.
   uint32_t const *subtab;
+  // level 1 as the hot kernels read it: {offsets32[p], sub_info[p] != 0 ? sub_info[p] : bucket length (< 2^27)}
+  // -- one 8-byte load instead of three 4-byte ones (nullptr when there is no second level)
+  uint2 const *entry8;
 };
 
 // Operator terms, structure-of-arrays on the device
@@ -101,9 +106,11 @@ __device__ __forceinline__ void index_window(IndexView const &ix, uint64_t needl
       int const p2 = (int)(s >> 27);
       uint64_t const k2 = (needle >> (ix.shift - p2)) & ((uint64_t(1) << p2) - 1);
       uint32_t const *t = ix.subtab + (size_t)(s & 0x7ffffffu) * 8 + k2;
-      uint32_t const r0 = __ldg(t);
-      lo += (int64_t)r0;
-      n = (int64_t)(__ldg(t + 1) - r0);
+      uint32_t const v = __ldg(t);
+      uint32_t cnt = v & 63u;
+      if (cnt == 63u) cnt = (__ldg(t + 1) >> 6) - (v >> 6);
+      lo += (int64_t)(v >> 6);
+      n = (int64_t)cnt;
     }
   }
 }
@@ -174,16 +181,25 @@ __device__ __forceinline__ void index_find32(IndexView const &ix, uint64_t const
     uint64_t const p = needle[u] >> ix.shift;
     uint32_t l = 0, n = 0;
     if (live[u] && p < ix.number_buckets) {
-      l = __ldg(ix.offsets32 + p);
-      n = __ldg(ix.offsets32 + p + 1) - l;
-      uint32_t const s = ix.sub_info != nullptr ? __ldg(ix.sub_info + p) : 0u;
+      uint32_t s = 0;
+      if (ix.entry8 != nullptr) {
+        uint2 const e = __ldg(ix.entry8 + p);
+        l = e.x;
+        n = e.y;
+        s = (e.y >> 27) != 0 ? e.y : 0u;  // p2 >= 1 sits in the top five bits; plain lengths are < 2^27
+      } else {
+        l = __ldg(ix.offsets32 + p);
+        n = __ldg(ix.offsets32 + p + 1) - l;
+        s = ix.sub_info != nullptr ? __ldg(ix.sub_info + p) : 0u;
+      }
       if (s != 0) {
         int const p2 = (int)(s >> 27);
         uint32_t const k2 = (uint32_t)(needle[u] >> (ix.shift - p2)) & ((1u << p2) - 1u);
         uint32_t const *t = ix.subtab + (size_t)(s & 0x7ffffffu) * 8 + k2;
-        uint32_t const r0 = __ldg(t);
-        l += r0;
-        n = __ldg(t + 1) - r0;
+        uint32_t const v = __ldg(t);
+        n = v & 63u;
+        if (n == 63u) n = (__ldg(t + 1) >> 6) - (v >> 6);
+        l += v >> 6;
       }
     }
     lo[u] = pos[u] = l;
