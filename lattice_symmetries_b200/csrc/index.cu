@@ -87,8 +87,14 @@ max_bucket_kernel(T const *__restrict__ offsets, int64_t number_buckets, unsigne
 }
 
 // ---- second level for crowded buckets ---------------------------------------------
-constexpr int kDenseBucket = 15;  // buckets with more entries get a sub-table ...
-constexpr int kSubTargetLog2 = 3; // ... of about 2^3 entries per slot
+#ifndef LS_INDEX_DENSE
+#define LS_INDEX_DENSE 15
+#endif
+#ifndef LS_INDEX_SUBLOG2
+#define LS_INDEX_SUBLOG2 3
+#endif
+constexpr int kDenseBucket = LS_INDEX_DENSE;  // buckets with more entries get a sub-table ...
+constexpr int kSubTargetLog2 = LS_INDEX_SUBLOG2; // ... of about 2^3 entries per slot
 constexpr int kMaxSubBits = 24;
 
 __device__ __forceinline__ int sub_bits(uint32_t n, int shift) {

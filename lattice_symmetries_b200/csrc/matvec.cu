@@ -268,12 +268,10 @@ orbit_kernel(MatvecArgs const a) {
   uint64_t *stage = reinterpret_cast<uint64_t *>(slab);   // [k][lane]: element 32 * lane + k of the warp
   uint32_t *planes = reinterpret_cast<uint32_t *>(slab);  // [plane][lane], after the betas have been read
   uint32_t const total = a.offsets[a.chunk_rows];
-  // persistent: the grid is sized to the machine, a warp strides over the chunk's 1024-element blocks
-  // (whole warps leave together: everything below runs converged)
-  uint64_t const warp_stride = (uint64_t)gridDim.x * (kOrbitThreads / 32) * 1024;
-  for (uint64_t warp_q0 = ((uint64_t)blockIdx.x * (kOrbitThreads / 32) + (tid >> 5)) * 1024; warp_q0 < total;
-       warp_q0 += warp_stride) {
-  __syncwarp();  // the previous block's planes are dead: the slab may be overwritten
+  // One CTA per four 1024-element blocks.  (A persistent grid sized to the machine was measured 15 % slower on
+  // kagome-36: the warps of an SM then walk through their load / integer phases in lockstep.)
+  uint64_t const warp_q0 = ((uint64_t)blockIdx.x * (kOrbitThreads / 32) + (tid >> 5)) * 1024;
+  if (warp_q0 >= total) return;  // whole warps leave: everything below runs converged
   uint64_t const warp_q1 = min((uint64_t)total, warp_q0 + 1024);
   uint64_t const q0 = warp_q0 + 32 * (uint64_t)lane;
   int const lanes = q0 < total ? (int)min((uint64_t)32, total - q0) : 0;
@@ -447,7 +445,6 @@ orbit_kernel(MatvecArgs const a) {
         if (k < lanes) out[k] = (uint8_t)info[k];
     }
   }
-  }  // blocks of this warp
 }
 
 // ---- fused path: canonicalise, rank and gather in one kernel ------------------------
@@ -1365,17 +1362,9 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
                   : a.ix.lows32 != nullptr ? rank_gather_kernel<uint32_t>
                                            : rank_gather_kernel<uint64_t>;
 
-  // Persistent grids: as many CTAs as fit the machine at once.  rank_gather gains 8 % from it (tables staged
-  // once, no empty CTAs); the orbit kernel LOSES 15 % (46 -> 53 ms on kagome-36: its warps then walk through
-  // their load / integer phases in lockstep instead of staggered), so it keeps one CTA per four blocks unless
-  // LS_B200_ORBIT_PERSISTENT=1.
-  unsigned orbit_resident = ~0u, rank_resident = ~0u;
-  static bool const orbit_persistent = getenv("LS_B200_ORBIT_PERSISTENT") != nullptr;
-  if (orbit_persistent && queued && !fused && a.mode == kModeGroup) {
-    int per_sm = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, orbit, kOrbitThreads, orbit_smem));
-    orbit_resident = (unsigned)std::max(1, per_sm) * (unsigned)rt.sm_count;
-  }
+  // rank_gather runs as a persistent grid sized to the machine (tables staged once, no empty CTAs: 8 % faster);
+  // the orbit kernel keeps one CTA per four blocks (see there).
+  unsigned rank_resident = ~0u;
   if (split && queued) {
     int per_sm = 0;
     size_t const rank_smem = want_tsign ? ((size_t)T + (size_t)a.number_chars) * 16 : 0;
@@ -1424,8 +1413,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
       if (a.mode == kModeGroup) {
         // grid for the worst case (every term matches); words past the chunk's total exit at once
         size_t const max_words = (((size_t)nrows * (size_t)T + 1023) / 1024) * 32;
-        unsigned const blocks = std::min<unsigned>(ceil_div(max_words, kOrbitThreads), orbit_resident);
-        orbit<<<blocks, kOrbitThreads, orbit_smem, stream_a>>>(a);
+        orbit<<<ceil_div(max_words, kOrbitThreads), kOrbitThreads, orbit_smem, stream_a>>>(a);
       } else {
         orbit_scalar_kernel<<<ceil_div((size_t)nrows, 128), 128, count_smem, stream_a>>>(a);
       }
