@@ -756,7 +756,10 @@ row_sum_kernel(MatvecArgs const a) {
 #define LS_RANK_MINBLOCKS 5  // <= 48 registers
 #endif
 constexpr int kRankThreads = 256;
-constexpr int kRankBatch = 4;
+#ifndef LS_RANK_BATCH
+#define LS_RANK_BATCH 4
+#endif
+constexpr int kRankBatch = LS_RANK_BATCH;
 constexpr unsigned long long kMissBits = 0x7ff8dead00000001ull;  // a quiet NaN no computation produces
 
 template <class Low>
