@@ -466,11 +466,16 @@ def main():
         ops = (nnz_local + rows_local) * w_m
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
-    prof = ROOT / "profiles" / "r01k" / f"{kernel_name}_{args.workload}.summary.txt"
-    if prof.exists():  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel (MB)
+    alu_pct = None
+    profs = sorted((ROOT / "profiles").glob(f"r*/{kernel_name}_{args.workload}.summary.txt"))
+    prof = profs[-1] if profs else None  # the latest committed ncu capture of this kernel on this workload
+    if prof is not None:  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel (MB)
         vals = dict(l.split()[:2] for l in prof.read_text().splitlines() if l.startswith("dram__bytes_"))
         if "dram__bytes_read.sum" in vals and "dram__bytes_write.sum" in vals:
             traffic = (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6
+        for l in prof.read_text().splitlines():
+            if l.startswith("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"):
+                alu_pct = float(l.split()[1])
     lop3_peak = float(lib.ls_b200_measure_lop3_peak())  # measured LOP3 thread-instructions/s (alu pipe)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -481,6 +486,7 @@ def main():
                             "row_sum_kernel": pk.get("combine"), "whole_step": step_ms},
         "int": {"reference_u64_ops_per_element": w_m, "achieved_Tops": ops / (k_ms * 1e-3) / 1e12,
                 "lop3_peak_Tops": lop3_peak / 1e12,
+                "alu_pipe_pct_of_peak_ncu": alu_pct,  # executed alu-pipe instructions vs peak, from the committed ncu capture
                 "note": "achieved = un-pruned reference op count / orbit_kernel time; the bit-sliced kernel executes "
                         "~3 LOP3 per plane per group element for 32 states, so this exceeds the LOP3 peak"},
     }
