@@ -1028,7 +1028,13 @@ gather_kernel(MatvecArgs const a) {
     }
     // rank: kGatherBatch independent branchless searches in lockstep
     int64_t j[kGatherBatch];
-    index_find<kGatherBatch>(ix, needle, live, j);
+    if (ix.offsets32 != nullptr && !ix.identity) {  // lean 32-bit search on the basis' key type (warp-uniform choice)
+      if (ix.lows16 != nullptr) index_find32<uint16_t, kGatherBatch>(ix, needle, live, j);
+      else if (ix.lows32 != nullptr) index_find32<uint32_t, kGatherBatch>(ix, needle, live, j);
+      else index_find32<uint64_t, kGatherBatch>(ix, needle, live, j);
+    } else {
+      index_find<kGatherBatch>(ix, needle, live, j);
+    }
 #pragma unroll
     for (int u = 0; u < kGatherBatch; ++u) {
       if (!live[u]) continue;
