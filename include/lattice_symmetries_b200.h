@@ -291,6 +291,16 @@ int ls_b200_matvec_device(ls_hs_operator const *op, int64_t row_begin,
                           int64_t row_end, double const *x_dev, double *y_dev);
 /* Complex128 variant (interleaved re, im).  Extension: the reference's matvec
  * is real-only (DistributedMatrixVector.chpl:1090-1091). */
+/* Block matvec (extension; the reference halts on numVectors != 1,
+ * chapel/src/DistributedMatrixVector.chpl:1096-1097): vector v is
+ * x_dev + v x_stride -> y_dev + v y_stride (strides in doubles).  All vectors
+ * share ONE canonicalisation + ranking pass over the matrix elements, so k
+ * vectors cost far less than k products.  ls_chpl_matrix_vector_product accepts
+ * num_vectors > 1 the same way (contiguous vectors of length dim). */
+int ls_b200_matvec_block_device(ls_hs_operator const *op, int64_t row_begin,
+                                int64_t row_end, int number_vectors,
+                                double const *x_dev, int64_t x_stride,
+                                double *y_dev, int64_t y_stride);
 int ls_b200_matvec_device_c128(ls_hs_operator const *op, int64_t row_begin,
                                int64_t row_end, ls_hs_scalar const *x_dev,
                                ls_hs_scalar *y_dev);

@@ -165,6 +165,10 @@ struct MatvecArgs {
   uint8_t *q_cidx;       // [capacity] index of the minimising character
   uint16_t *q_tsign;     // [capacity] split path: term | sign << 15 of every matrix element (nullptr: not recorded)
   double *vals;          // [capacity] (x2 when complex) fused path: conj(chi) w sign n_j x_j of every matrix element
+  // block matvec (split path): vector v reads x + v x_stride / xs + v x_stride, writes y + v y_stride and
+  // vals + v vals_stride (strides in scalars of the vector type)
+  int number_vectors;
+  int64_t x_stride, xs_stride, y_stride, vals_stride;
 };
 
 // Stabiliser character sum of x read straight from the global tables; used on
@@ -712,17 +716,18 @@ row_sum_kernel(MatvecArgs const a) {
   __syncthreads();
   int const r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.chunk_rows) return;
+  int64_t const vec = blockIdx.y;  // block matvec: one grid row per vector
   int64_t const row = a.chunk_begin + r;
   uint64_t const alpha = __ldg(a.ix.reps + row);
   uint32_t const qa = __ldg(a.offsets + r), qb = __ldg(a.offsets + r + 1);
   double acc_r = 0.0, acc_i = 0.0;
   for (uint32_t q = qa; q < qb; ++q) {
     if (CPLX) {
-      double2 const v = __ldcs(reinterpret_cast<double2 const *>(a.vals) + q);
+      double2 const v = __ldcs(reinterpret_cast<double2 const *>(a.vals) + vec * a.vals_stride + q);
       acc_r += v.x;
       acc_i += v.y;
     } else {
-      acc_r += __ldcs(a.vals + q);
+      acc_r += __ldcs(a.vals + vec * a.vals_stride + q);
     }
   }
   double dr = 0.0, di = 0.0;
@@ -735,13 +740,13 @@ row_sum_kernel(MatvecArgs const a) {
   double const ni = a.norms != nullptr ? __ldg(a.norms + row) : 1.0;
   int64_t const out = row - a.row_begin;
   if (CPLX) {
-    double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.x) + row);
+    double2 const xv = __ldg(reinterpret_cast<double2 const *>(a.x) + vec * a.x_stride + row);
     double2 res;
     res.x = acc_r / ni + (dr * xv.x - di * xv.y);
     res.y = acc_i / ni + (dr * xv.y + di * xv.x);
-    reinterpret_cast<double2 *>(a.y)[out] = res;
+    reinterpret_cast<double2 *>(a.y)[vec * a.y_stride + out] = res;
   } else {
-    a.y[out] = acc_r / ni + dr * __ldg(a.x + row);  // kernels/reference.c:84-91 uses creal(v) only
+    a.y[vec * a.y_stride + out] = acc_r / ni + dr * __ldg(a.x + vec * a.x_stride + row);  // kernels/reference.c:84-91 uses creal(v) only
   }
 }
 
@@ -819,13 +824,14 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
     if (!live[u]) continue;
     uint64_t const q = warp_q0 + (uint64_t)u * 32 + lane;
     bool const missing = j[u] < 0;
+    double fr = 1.0, fi = 0.0;
     if (product) {
       unsigned const ts = __ldcs(a.q_tsign + q);
       double2 w = tw[ts & 0x7fffu];
       if (ts & 0x8000u) { w.x = -w.x; w.y = -w.y; }
       double2 const ch = chars[a.number_idx_planes > 0 ? __ldcs(a.q_cidx + q) : 0];
-      double const fr = ch.x * w.x + ch.y * w.y;  // conj(chi) * w
-      double const fi = ch.x * w.y - ch.y * w.x;
+      fr = ch.x * w.x + ch.y * w.y;  // conj(chi) * w
+      fi = ch.x * w.y - ch.y * w.x;
       // not in the basis: fine when its norm vanishes, an error otherwise (DistributedMatrixVector.chpl:127-135)
       if (missing && (fr != 0.0 || fi != 0.0) && stabiliser_sum_global(a.g, needle[u]) > kNormThreshold)
         atomicOr(a.error_flag, 1);
@@ -835,6 +841,20 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
     }
     if (cplx) reinterpret_cast<double2 *>(a.vals)[q] = xv[u];
     else a.vals[q] = xv[u].x;
+    // block matvec: the other vectors reuse the rank and the coefficient (product mode only)
+    for (int v = 1; v < a.number_vectors; ++v) {
+      double2 o = make_double2(0.0, 0.0);
+      if (!missing) {
+        if (cplx) {
+          double2 const xo = __ldg(reinterpret_cast<double2 const *>(a.xs) + v * a.xs_stride + j[u]);
+          o = make_double2(fr * xo.x - fi * xo.y, fr * xo.y + fi * xo.x);
+        } else {
+          o.x = fr * __ldg(a.xs + v * a.xs_stride + j[u]);
+        }
+      }
+      if (cplx) reinterpret_cast<double2 *>(a.vals)[v * a.vals_stride + q] = o;
+      else a.vals[v * a.vals_stride + q] = o.x;
+    }
   }
   }  // tiles of this warp
 }
@@ -1205,8 +1225,12 @@ static cudaEvent_t next_event(MatvecScratch &sc) {
 }
 
 // y[row_begin:row_end] = (H x)[row_begin:row_end]; x, y in device memory.
+// number_vectors > 1 (block matvec, an extension: the reference halts, DistributedMatrixVector.chpl:1096-1097):
+// vector v is x + v x_stride -> y + v y_stride (strides in scalars of the vector type).  On the split path all
+// vectors share ONE canonicalisation + ranking pass -- the integer work is per matrix element, not per vector.
 static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end, double const *d_x,
-                          double *d_y, bool complex_vectors) {
+                          double *d_y, bool complex_vectors, int number_vectors = 1, int64_t x_stride = 0,
+                          int64_t y_stride = 0) {
   Runtime &rt = runtime();
   ls_hs_basis const *basis = op->basis;
   IndexData *ix = index_of(basis);
@@ -1265,10 +1289,15 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     if (!bitsliced) a.number_idx_planes = std::max(a.number_idx_planes, 1);  // the scalar kernel always writes q_cidx
     // pre-scaled copy of x
     size_t const words = (size_t)dim * (complex_vectors ? 2 : 1);
-    double *xs = sc.xs.reserve(words);
+    double *xs = sc.xs.reserve(words * (size_t)number_vectors);
     unsigned const blocks = (unsigned)std::min<int64_t>((dim + 255) / 256, (int64_t)rt.sm_count * 16);
-    prescale_kernel<<<blocks, 256, 0, rt.stream>>>(dim, a.complex_vectors, ix->d_norms, d_x, xs);
-    count_launch();
+    for (int v = 0; v < number_vectors; ++v) {
+      // (xs is packed: vector v at xs + v dim, whatever the caller's stride)
+      prescale_kernel<<<blocks, 256, 0, rt.stream>>>(dim, a.complex_vectors, ix->d_norms,
+                                                     d_x + (size_t)v * (size_t)x_stride * (complex_vectors ? 2 : 1),
+                                                     xs + (size_t)v * words);
+      count_launch();
+    }
     CUDA_CHECK(cudaGetLastError());
     a.xs = xs;
   } else if (info.has_spin_inversion) {
@@ -1306,10 +1335,25 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     orbit_smem = ((AdjointTerms::bytes(T, true) + 15) & ~size_t(15)) + (size_t)(kOrbitThreads / 32) * kWarpSlabBytes;
   LSB_CHECK(gather_smem <= rt.smem_optin && orbit_smem <= rt.smem_optin,
             "operator / symmetry tables do not fit in shared memory");
+  a.number_vectors = 1;
+  if (number_vectors > 1) {
+    if (!(split && want_tsign && T > 0)) {
+      // no shared pass to amortise on this path: one vector at a time
+      size_t const scalar = complex_vectors ? 2 : 1;
+      for (int v = 0; v < number_vectors; ++v)
+        matvec_device(op, row_begin, row_end, d_x + (size_t)v * (size_t)x_stride * scalar,
+                      d_y + (size_t)v * (size_t)y_stride * scalar, complex_vectors);
+      return;
+    }
+    a.number_vectors = number_vectors;
+    a.x_stride = x_stride;
+    a.xs_stride = dim;
+    a.y_stride = y_stride;
+  }
 
   // Chunk of rows: its intermediates (up to 19 bytes per matrix element) must fit the
   // scratch capacity even if every term matched every row.
-  int64_t capacity = int64_t(1) << 27;
+  int64_t capacity = (int64_t(1) << 27) / a.number_vectors;
   if (char const *env = getenv("LS_B200_MV_CHUNK")) capacity = std::max<int64_t>(4096, atoll(env));
   // Pipelined split path (experimental): two half-size slots, rank + gather + row sum of
   // chunk c on a second stream while the orbit kernel of chunk c + 1 runs on the first -- the two are bound by
@@ -1330,7 +1374,8 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
       ChunkSlot &slot = sc.slot[k];
       slot.counts.reserve((size_t)chunk_rows + 1);
       slot.offsets.reserve((size_t)chunk_rows + 1);
-      if (split || fused) slot.vals.reserve(((size_t)capacity + 32) * (complex_vectors ? 2 : 1));
+      if (split || fused)
+        slot.vals.reserve(((size_t)capacity + 32) * (complex_vectors ? 2 : 1) * (size_t)a.number_vectors);
       if (!fused) {
         slot.q_rep.reserve((size_t)capacity + 32);
         slot.q_cidx.reserve((size_t)capacity + 32);
@@ -1409,6 +1454,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     a.q_cidx = slot.q_cidx.ptr;
     a.q_tsign = want_tsign ? slot.q_tsign.ptr : nullptr;
     a.vals = slot.vals.ptr;
+    a.vals_stride = capacity + 32;
     if (queued) {
       if (pipelined && chunk_index >= 2) CUDA_CHECK(cudaStreamWaitEvent(stream_a, slot.released, 0));
       row_count_kernel<<<ceil_div((size_t)nrows + 1, 256), 256, count_smem, stream_a>>>(a);
@@ -1451,7 +1497,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
         CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
       }
       if (a.q_tsign != nullptr)
-        row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, stream_b>>>(a);
+        row_sum<<<dim3(ceil_div((size_t)nrows, 256), (unsigned)a.number_vectors), 256, sum_smem, stream_b>>>(a);
       else
         row_combine<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, stream_b>>>(a);
     } else
@@ -1511,8 +1557,10 @@ void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors, double c
     ls_hs_error("bases with more than 64 bits are not yet implemented");
     return;
   }
-  if (num_vectors != 1) {
-    ls_hs_error("applying the Operator to more than 1 vector is not yet implemented");
+  // num_vectors > 1 is an extension (the reference halts, DistributedMatrixVector.chpl:1096-1097):
+  // x and y hold num_vectors contiguous vectors of length dim; all share one canonicalisation pass.
+  if (num_vectors < 1) {
+    ls_hs_error("matrix_vector_product: the number of vectors must be positive");
     return;
   }
   bool ok = true;
@@ -1523,11 +1571,12 @@ void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors, double c
     if (dim == 0) return;
     MatvecScratch &sc = mv_scratch();
     cudaStream_t s = runtime().stream;
-    double *d_x = sc.x.reserve((size_t)dim);
-    double *d_y = sc.y.reserve((size_t)dim);
-    CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)dim, cudaMemcpyHostToDevice, s));
-    matvec_device(op, 0, dim, d_x, d_y, false);
-    CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * (size_t)dim, cudaMemcpyDeviceToHost, s));
+    size_t const n = (size_t)dim * (size_t)num_vectors;
+    double *d_x = sc.x.reserve(n);
+    double *d_y = sc.y.reserve(n);
+    CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    matvec_device(op, 0, dim, d_x, d_y, false, num_vectors, dim, dim);
+    CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     ok = matvec_finish();
   });
   if (!ok) ls_hs_error(kInvalidIndexMessage);
@@ -1538,6 +1587,17 @@ int ls_b200_matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   int status = -1;
   guarded(__func__, [&] {
     matvec_device(op, row_begin, row_end, x_dev, y_dev, false);
+    status = 0;
+  });
+  return status;
+}
+
+int ls_b200_matvec_block_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end, int number_vectors,
+                                double const *x_dev, int64_t x_stride, double *y_dev, int64_t y_stride) {
+  int status = -1;
+  guarded(__func__, [&] {
+    LSB_CHECK(number_vectors >= 1, "the number of vectors must be positive");
+    matvec_device(op, row_begin, row_end, x_dev, y_dev, false, number_vectors, x_stride, y_stride);
     status = 0;
   });
   return status;

@@ -195,14 +195,35 @@ class Operator(_Base):
             raise TypeError(
                 "expected a NDArray[float64], but got {}[{}]".format(type(vector).__name__, type(vector.dtype)))
         vector = np.ascontiguousarray(vector)
-        if vector.shape != (self._basis.number_states,):
-            raise ValueError(f"expected a vector of shape ({self._basis.number_states},), got {vector.shape}")
+        dim = self._basis.number_states
+        # extension: a (k, dim) block of vectors shares one pass over the matrix elements (the reference halts
+        # on numVectors != 1, chapel/src/DistributedMatrixVector.chpl:1096-1097)
+        if vector.shape != (dim,) and not (vector.ndim == 2 and vector.shape[1] == dim and vector.shape[0] >= 1):
+            raise ValueError(f"expected a vector of shape ({dim},), got {vector.shape}")
+        number_vectors = 1 if vector.ndim == 1 else vector.shape[0]
         out = np.empty_like(vector)
         kernels = lib.ls_hs_internal_get_chpl_kernels()
         kernels.contents.matrix_vector_product(
-            C.byref(self._payload), 1, vector.ctypes.data_as(_lib.f64_p), out.ctypes.data_as(_lib.f64_p))
+            C.byref(self._payload), number_vectors, vector.ctypes.data_as(_lib.f64_p), out.ctypes.data_as(_lib.f64_p))
         _lib.check_error()
         return out
+
+    def matvec_block_device(self, number_vectors: int, x_ptr: int, x_stride: int, y_ptr: int, y_stride: int,
+                            row_begin: int = 0, row_end: int = -1, sync: bool = False) -> None:
+        """Block matvec on device-resident float64 vectors: vector v is x_ptr + 8 v x_stride -> y_ptr + 8 v y_stride;
+        all vectors share one canonicalisation + ranking pass."""
+        self._check_basis_is_built("matvec_block_device")
+        if row_end < 0:
+            row_end = self._basis.number_states
+        status = lib.ls_b200_matvec_block_device(
+            C.byref(self._payload), int(row_begin), int(row_end), int(number_vectors), x_ptr, int(x_stride), y_ptr,
+            int(y_stride))
+        _lib.check_error()
+        if status != 0:
+            raise RuntimeError("ls_b200_matvec_block_device failed")
+        if sync:
+            lib.ls_b200_matvec_sync()
+            _lib.check_error()
 
     def matvec_device(self, x_ptr: int, y_ptr: int, row_begin: int = 0, row_end: int = -1,
                       complex_vectors: bool = False, sync: bool = False) -> None:

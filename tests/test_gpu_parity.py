@@ -378,6 +378,29 @@ def test_matvec_complex_pipeline_variants_agree(oracle, built, name, monkeypatch
         assert _rel_err(d_y.numpy(), y0) < MATVEC_RTOL, variant
 
 
+@pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome24_c2v_inv", "hubbard_2x4", "chain12_inv_only"])
+def test_block_matvec_equals_single_vectors(oracle, built, name, monkeypatch):
+    """Extension (the reference halts on numVectors != 1): k vectors through one pass == k products, bit for bit;
+    also on a row range with strided device vectors and with tiny chunks."""
+    from lattice_symmetries_b200 import _lib
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    dim = reps.shape[0]
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((3, dim))
+    want = np.stack([op.apply_to_state_vector(x) for x in X])
+    assert np.array_equal(op.apply_to_state_vector(X), want)
+    monkeypatch.setenv("LS_B200_MV_CHUNK", "4096")
+    assert np.array_equal(op.apply_to_state_vector(X), want)
+    monkeypatch.delenv("LS_B200_MV_CHUNK")
+    lo, hi = dim // 4, dim - dim // 5
+    pad = 7
+    d_x = _lib.DeviceArray.from_numpy(np.concatenate([np.concatenate([x, np.zeros(pad)]) for x in X]))
+    d_y = _lib.DeviceArray(3 * (hi - lo + pad), np.float64)
+    op.matvec_block_device(3, d_x.ptr, dim + pad, d_y.ptr, hi - lo + pad, lo, hi, sync=True)
+    got = d_y.numpy().reshape(3, hi - lo + pad)[:, :hi - lo]
+    assert np.array_equal(got, want[:, lo:hi])
+
+
 @pytest.mark.parametrize("name", ["chain16_symm", "kagome18_c2", "hubbard_2x4"])
 def test_matvec_device_row_ranges(oracle, built, name):
     """Device-resident entry point on contiguous row shards == host-pointer entry point."""
