@@ -1195,6 +1195,11 @@ struct MatvecScratch {
   ChunkSlot slot[2];
   cudaStream_t stream_b = nullptr;
   cudaEvent_t inputs_ready = nullptr;
+  // host-pointer entry point: finished row chunks of y drain to the caller's buffer on a copy stream while the
+  // next chunks are computed
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_done;
+  cudaEvent_t copies_done = nullptr;
   DeviceBuffer<unsigned char> scan_tmp;
   size_t scan_tmp_bytes = 0;
   int *d_error = nullptr;
@@ -1230,7 +1235,7 @@ static cudaEvent_t next_event(MatvecScratch &sc) {
 // vectors share ONE canonicalisation + ranking pass -- the integer work is per matrix element, not per vector.
 static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end, double const *d_x,
                           double *d_y, bool complex_vectors, int number_vectors = 1, int64_t x_stride = 0,
-                          int64_t y_stride = 0) {
+                          int64_t y_stride = 0, double *host_y = nullptr) {
   Runtime &rt = runtime();
   ls_hs_basis const *basis = op->basis;
   IndexData *ix = index_of(basis);
@@ -1342,7 +1347,8 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
       size_t const scalar = complex_vectors ? 2 : 1;
       for (int v = 0; v < number_vectors; ++v)
         matvec_device(op, row_begin, row_end, d_x + (size_t)v * (size_t)x_stride * scalar,
-                      d_y + (size_t)v * (size_t)y_stride * scalar, complex_vectors);
+                      d_y + (size_t)v * (size_t)y_stride * scalar, complex_vectors, 1, 0, 0,
+                      host_y != nullptr ? host_y + (size_t)v * (size_t)y_stride * scalar : nullptr);
       return;
     }
     a.number_vectors = number_vectors;
@@ -1506,6 +1512,30 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
     if (pipelined) CUDA_CHECK(cudaEventRecord(slot.released, stream_b));
     CUDA_CHECK(cudaGetLastError());
+    if (host_y != nullptr) {
+      // rows [begin, begin + nrows) of y are final: copy them out behind the next chunk's kernels
+      if (sc.copy_stream == nullptr) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&sc.copies_done, cudaEventDisableTiming));
+      }
+      while (sc.chunk_done.size() <= (size_t)chunk_index) {
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        sc.chunk_done.push_back(e);
+      }
+      CUDA_CHECK(cudaEventRecord(sc.chunk_done[(size_t)chunk_index], stream_b));
+      CUDA_CHECK(cudaStreamWaitEvent(sc.copy_stream, sc.chunk_done[(size_t)chunk_index], 0));
+      size_t const scalar = sizeof(double) * (complex_vectors ? 2 : 1);
+      for (int v = 0; v < a.number_vectors; ++v) {
+        size_t const at = ((size_t)v * (size_t)(a.number_vectors > 1 ? a.y_stride : 0) + (size_t)(begin - row_begin)) * scalar;
+        CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(host_y) + at, reinterpret_cast<char const *>(d_y) + at,
+                                   (size_t)nrows * scalar, cudaMemcpyDeviceToHost, sc.copy_stream));
+      }
+    }
+  }
+  if (host_y != nullptr && sc.copy_stream != nullptr) {
+    CUDA_CHECK(cudaEventRecord(sc.copies_done, sc.copy_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(rt.stream, sc.copies_done, 0));
   }
   if (pipelined) {
     // the library stream continues only after stream B has written the last rows of y
@@ -1575,8 +1605,13 @@ void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors, double c
     double *d_x = sc.x.reserve(n);
     double *d_y = sc.y.reserve(n);
     CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
-    matvec_device(op, 0, dim, d_x, d_y, false, num_vectors, dim, dim);
-    CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    // pinned y: finished row chunks drain on a copy stream behind the next chunks' kernels; pageable y (where an
+    // "async" copy blocks the host and would stall the launch loop): one copy at the end
+    cudaPointerAttributes attr{};
+    bool const pinned = cudaPointerGetAttributes(&attr, y) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    matvec_device(op, 0, dim, d_x, d_y, false, num_vectors, dim, dim, pinned ? y : nullptr);
+    if (!pinned) CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     ok = matvec_finish();
   });
   if (!ok) ls_hs_error(kInvalidIndexMessage);
