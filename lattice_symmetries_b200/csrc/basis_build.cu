@@ -543,7 +543,9 @@ struct BuildResult {
 // ranges; the output is their concatenation, counts[i] the number found in range i.  One call
 // serves a rank's whole block-cyclic share: scratch and output are allocated once.
 using Ranges = std::vector<std::pair<uint64_t, uint64_t>>;
-static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<uint64_t> *counts = nullptr) {
+static bool want_managed_view();
+static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<uint64_t> *counts = nullptr,
+                                bool host_visible = false) {
   Runtime &rt = runtime();
   BasisInfo const info = basis_info(basis);
   LSB_CHECK(info.number_bits <= 64, "bases with more than 64 bits are not supported");
@@ -559,10 +561,27 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
   if (counts != nullptr) counts->assign(ranges.size(), 0);
   BuildResult res;
   if (candidates == 0) return res;
+  static bool const profile = getenv("LS_B200_PROFILE") != nullptr;
+  auto const wall0 = std::chrono::steady_clock::now();
+  double alloc_ms = 0, sync_ms = 0;
+  auto since = [](std::chrono::steady_clock::time_point t) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+  };
   CUDA_CHECK(cudaEventRecord(rt.ev0, rt.stream));
 
+  // host_visible: the representatives go straight into the managed allocation that will serve as the caller's
+  // host view (make_host_view then has nothing to copy)
+  auto alloc_reps = [&](uint64_t **p, uint64_t n) {
+    if (host_visible && want_managed_view() && cudaMallocManaged(p, sizeof(uint64_t) * n) == cudaSuccess) {
+      CUDA_CHECK(cudaMemAdvise(*p, sizeof(uint64_t) * n, cudaMemAdviseSetPreferredLocation, rt.device));
+      CUDA_CHECK(cudaMemPrefetchAsync(*p, sizeof(uint64_t) * n, rt.device, rt.stream));
+      return;
+    }
+    (void)cudaGetLastError();
+    CUDA_CHECK(cudaMalloc(p, sizeof(uint64_t) * n));
+  };
   if (!plan.projected) {
-    CUDA_CHECK(cudaMalloc(&res.d_reps, sizeof(uint64_t) * candidates));
+    alloc_reps(&res.d_reps, candidates);
     for (size_t i = 0; i < ranges.size(); ++i) {
       uint64_t const count = ranges[i].second - ranges[i].first;
       if (count == 0) continue;
@@ -602,11 +621,14 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
       CUDA_CHECK(cudaFuncSetAttribute(build_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)masks_bytes));
     }
 
-    uint64_t const super = uint64_t(1) << 26;  // words per super-chunk (2^31 candidates)
+    // words per super-chunk (2^28 candidates): scratch stays at ~64 MB + survivors -- cudaMalloc / cudaFree of
+    // GB-sized buffers showed 2..170 ms run-to-run variance on the test boxes, more than the kernels
+    uint64_t const super = uint64_t(1) << 23;
     uint64_t const super_words = std::min((longest + 31) / 32, super);
     uint64_t const super_blocks = (super_words + kBuildThreads - 1) / kBuildThreads;
     DeviceBuffer<uint32_t> alive, events, block_counts, block_offsets;
     DeviceBuffer<unsigned char> scan_tmp;
+    auto const t_alloc = std::chrono::steady_clock::now();
     alive.reserve(super_words);
     events.reserve(super_words);
     block_counts.reserve(super_blocks + 1);
@@ -616,10 +638,13 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
     scan_tmp.reserve(tmp_bytes);
 
     // Output capacity: orbit-counting estimate, grown on demand.
-    uint64_t const images = (uint64_t)g.number_masks * (inv ? 2 : 1);
+    // (with spin inversion the candidate range is already halved -- top bit clear, Basis.hs:736-740 -- so the
+    // orbits cover it |G| times, not 2 |G| times)
+    uint64_t const images = (uint64_t)std::max(1, g.number_masks);
     uint64_t capacity = std::min<uint64_t>(candidates, candidates / images * 5 / 4 + (1u << 16));
-    CUDA_CHECK(cudaMalloc(&res.d_reps, sizeof(uint64_t) * capacity));
+    alloc_reps(&res.d_reps, capacity);
     CUDA_CHECK(cudaMalloc(&res.d_norms, sizeof(double) * capacity));
+    alloc_ms += since(t_alloc);
     uint64_t emitted = 0, scanned = 0;
     GroupView const gv = g.view();
 
@@ -647,8 +672,10 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
           cub::DeviceScan::ExclusiveSum(scan_tmp.ptr, tmp_bytes, block_counts.ptr, block_offsets.ptr, (int)(nblocks + 1), rt.stream);
           count_launch();
           uint32_t total = 0;
+          auto const t_sync = std::chrono::steady_clock::now();
           CUDA_CHECK(cudaMemcpyAsync(&total, block_offsets.ptr + nblocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, rt.stream));
           CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+          sync_ms += since(t_sync);
           return total;
         };
         uint32_t chunk_total = 0;
@@ -674,7 +701,9 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
           CUDA_CHECK(cudaGetLastError());
           uint32_t const alive_total = scan_counts(blocks);
           if (alive_total > 0) {
+            auto const t_grow = std::chrono::steady_clock::now();
             survivors.reserve((size_t)alive_total + 32);
+            alloc_ms += since(t_grow);
             build_scatter_kernel<<<blocks, kBuildThreads, masks_bytes, rt.stream>>>(
                 gv, ev, word0 + done, nwords, nullptr, alive.ptr, nullptr, block_offsets.ptr, 0, survivors.ptr, nullptr);
             count_launch();
@@ -700,7 +729,8 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
           uint64_t const new_capacity = std::max<uint64_t>(emitted + chunk_total, projected);
           uint64_t *new_reps = nullptr;
           double *new_norms = nullptr;
-          CUDA_CHECK(cudaMalloc(&new_reps, sizeof(uint64_t) * new_capacity));
+          auto const t_grow = std::chrono::steady_clock::now();
+          alloc_reps(&new_reps, new_capacity);
           CUDA_CHECK(cudaMalloc(&new_norms, sizeof(double) * new_capacity));
           CUDA_CHECK(cudaMemcpyAsync(new_reps, res.d_reps, sizeof(uint64_t) * emitted, cudaMemcpyDeviceToDevice, rt.stream));
           CUDA_CHECK(cudaMemcpyAsync(new_norms, res.d_norms, sizeof(double) * emitted, cudaMemcpyDeviceToDevice, rt.stream));
@@ -710,6 +740,7 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
           res.d_reps = new_reps;
           res.d_norms = new_norms;
           capacity = new_capacity;
+          alloc_ms += since(t_grow);
         }
         if (chunk_total > 0) {
           build_scatter_kernel<<<source_blocks, kBuildThreads, masks_bytes, rt.stream>>>(
@@ -729,11 +760,15 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, rt.ev0, rt.ev1));
   rt.last_build_ms = ms;
+  if (profile)
+    fprintf(stderr, "[ls_b200] build_ranges: %llu candidates -> %llu states; device span %.2f ms, wall %.2f ms of which "
+                    "allocations %.2f ms, waiting for kernels + counts %.2f ms\n",
+            (unsigned long long)candidates, (unsigned long long)res.count, ms, since(wall0), alloc_ms, sync_ms);
   return res;
 }
 
-static BuildResult build_range(ls_hs_basis const *basis, uint64_t k_begin, uint64_t k_end) {
-  return build_ranges(basis, Ranges{{k_begin, k_end}});
+static BuildResult build_range(ls_hs_basis const *basis, uint64_t k_begin, uint64_t k_end, bool host_visible = false) {
+  return build_ranges(basis, Ranges{{k_begin, k_end}}, nullptr, host_visible);
 }
 
 static void free_pinned(void *p) {
@@ -762,16 +797,25 @@ static void free_pinned(void *p) {
 // keeps a second, pinned host copy instead (cudaMallocHost of the whole array:
 // ~0.4 ms per MB, more than the build itself for large bases).
 // Takes ownership of d_reps; returns the host-visible pointer and updates d_reps.
+static bool want_managed_view() {
+  char const *mode = getenv("LS_B200_HOST_MIRROR");
+  if (mode != nullptr && strcmp(mode, "pinned") == 0) return false;
+  int concurrent = 0;
+  cudaDeviceGetAttribute(&concurrent, cudaDevAttrConcurrentManagedAccess, runtime().device);
+  return concurrent != 0;
+}
 static uint64_t *make_host_view(uint64_t *&d_reps, uint64_t count) {
   Runtime &rt = runtime();
   size_t const bytes = sizeof(uint64_t) * count;
-  char const *mode = getenv("LS_B200_HOST_MIRROR");
-  bool managed = mode == nullptr || strcmp(mode, "pinned") != 0;
-  if (managed) {
-    int concurrent = 0;
-    cudaDeviceGetAttribute(&concurrent, cudaDevAttrConcurrentManagedAccess, rt.device);
-    managed = concurrent != 0;
+  bool const managed = want_managed_view();
+  cudaPointerAttributes attr{};
+  if (cudaPointerGetAttributes(&attr, d_reps) == cudaSuccess && attr.type == cudaMemoryTypeManaged) {
+    // built in place (build_ranges, host_visible): only the advice is missing
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    CUDA_CHECK(cudaMemAdvise(d_reps, bytes, cudaMemAdviseSetReadMostly, rt.device));
+    return d_reps;
   }
+  (void)cudaGetLastError();
   if (managed) {
     uint64_t *m = nullptr;
     if (cudaMallocManaged(&m, bytes) == cudaSuccess) {
@@ -883,7 +927,7 @@ void ls_chpl_enumerate_representatives(ls_hs_basis const *basis, uint64_t lower,
   guarded(__func__, [&] {
     static bool const profile = getenv("LS_B200_PROFILE") != nullptr;
     auto const t0 = std::chrono::steady_clock::now();
-    BuildResult r = build_range(basis, 0, ~uint64_t(0));
+    BuildResult r = build_range(basis, 0, ~uint64_t(0), true);
     auto const t1 = std::chrono::steady_clock::now();
     uint64_t *host = nullptr;
     if (r.count > 0) {
