@@ -615,7 +615,7 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
     FlagsKernel filter_kernel = two_phase ? pick_flags_kernel(np, inv, true) : nullptr;
     if (filter_kernel != nullptr && smem_bitsliced > 48 * 1024)
       CUDA_CHECK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bitsliced));
-    DeviceBuffer<uint64_t> survivors;
+
     if (masks_bytes > 48 * 1024) {
       CUDA_CHECK(cudaFuncSetAttribute(build_flags_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)masks_bytes));
       CUDA_CHECK(cudaFuncSetAttribute(build_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)masks_bytes));
@@ -626,8 +626,11 @@ static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::ve
     uint64_t const super = uint64_t(1) << 23;
     uint64_t const super_words = std::min((longest + 31) / 32, super);
     uint64_t const super_blocks = (super_words + kBuildThreads - 1) / kBuildThreads;
-    DeviceBuffer<uint32_t> alive, events, block_counts, block_offsets;
-    DeviceBuffer<unsigned char> scan_tmp;
+    // scratch lives for the process (grow-only): cudaFree of these buffers at the end of every build cost
+    // 10..200 ms on the test boxes (device-wide synchronisation + unmapping), far more than the kernels
+    static DeviceBuffer<uint32_t> alive, events, block_counts, block_offsets;
+    static DeviceBuffer<unsigned char> scan_tmp;
+    static DeviceBuffer<uint64_t> survivors;
     auto const t_alloc = std::chrono::steady_clock::now();
     alive.reserve(super_words);
     events.reserve(super_words);
