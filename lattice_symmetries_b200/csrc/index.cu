@@ -234,29 +234,31 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
     low_bits_kernel<uint32_t><<<lblocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, mask, ix.d_lows32);
     count_launch();
   }
-  unsigned long long *d_max = nullptr, h_max = 0;
-  CUDA_CHECK(cudaMalloc(&d_max, sizeof h_max));
+  // temporaries live for the process (grow-only): a cudaFree inside the build is a device-wide synchronisation
+  // that cost up to 200 ms on the test boxes
+  static DeviceBuffer<unsigned long long> max_buffer;
+  static DeviceBuffer<uint32_t> first_buffer;
+  static DeviceBuffer<unsigned char> scan_buffer;
+  unsigned long long *d_max = max_buffer.reserve(1), h_max = 0;
   CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof h_max, rt.stream));
   static bool const no_sub = getenv("LS_B200_INDEX_FLAT") != nullptr;  // A/B knob: first level only
   bool have_sub = false;
   if (ix.d_offsets32 != nullptr && ix.shift > 0 && !no_sub) {
     // second level: sizes -> exclusive scan -> fill; dropped when nothing is crowded
     int64_t const nb = number_offsets - 1;
-    uint32_t *d_units = nullptr, *d_first = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_units, sizeof(uint32_t) * (size_t)(nb + 1)));
-    CUDA_CHECK(cudaMalloc(&d_first, sizeof(uint32_t) * (size_t)(nb + 1)));
+    uint32_t *d_units = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_units, sizeof(uint32_t) * (size_t)(nb + 1)));  // becomes sub_info
+    uint32_t *d_first = first_buffer.reserve((size_t)(nb + 1));
     CUDA_CHECK(cudaMemsetAsync(d_units + nb, 0, sizeof(uint32_t), rt.stream));
     sub_sizes_kernel<<<blocks, 256, 0, rt.stream>>>(ix.d_offsets32, nb, ix.shift, d_units);
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_units, d_first, (int)(nb + 1), rt.stream);
-    void *d_tmp = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_tmp, tmp_bytes));
+    void *d_tmp = scan_buffer.reserve(tmp_bytes);
     cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_units, d_first, (int)(nb + 1), rt.stream);
     count_launch(2);
     uint32_t total_units = 0;
     CUDA_CHECK(cudaMemcpyAsync(&total_units, d_first + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, rt.stream));
     CUDA_CHECK(cudaStreamSynchronize(rt.stream));
-    cudaFree(d_tmp);
     // (no 32-bit wrap: a crowded bucket of n states adds at most n / 64 + 1 units and n sums to < 2^32)
     if (total_units > 0 && total_units < (1u << 27)) {
       CUDA_CHECK(cudaMalloc(&ix.d_subtab, sizeof(uint32_t) * (size_t)total_units * 8));
@@ -270,9 +272,8 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
       d_units = nullptr;
       have_sub = true;
     }
-    cudaFree(d_units);
+    if (d_units != nullptr) cudaFree(d_units);  // nothing was crowded
     CUDA_CHECK(cudaStreamSynchronize(rt.stream));
-    cudaFree(d_first);
   }
   if (have_sub) {
     // sub_fill_kernel has folded every final window into d_max
@@ -286,7 +287,6 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof h_max, cudaMemcpyDeviceToHost, rt.stream));
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
-  cudaFree(d_max);
   ix.steps = 0;
   while ((h_max >> ix.steps) != 0) ++ix.steps;
 }
