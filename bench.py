@@ -491,14 +491,42 @@ def main():
                         "~3 LOP3 per plane per group element for 32 states, so this exceeds the LOP3 peak"},
     }
 
+    # ---- full-size, size-independent checks (the parity tests proper run at sizes the oracle can follow) ---------
+    checks = {}
+    if world == 1:
+        states = np.asarray(basis.states[:min(dim, 1 << 22)])
+        checks["representatives_sorted_prefix"] = bool(np.all(states[1:] > states[:-1]))
+        if not complex_vectors:
+            # Hermiticity of the projected operator: <u, H v> == <v, H u>
+            gen = torch.Generator(device="cpu")
+            gen.manual_seed(7)
+            u = sh.empty_vector(vdtype)
+            u[:dim].copy_(torch.randn(dim, dtype=torch.float64, generator=gen))
+            hu, hv = sh.empty_vector(vdtype), sh.empty_vector(vdtype)
+            sh.matvec(u, hu)
+            sh.matvec(x, hv)
+            lib.ls_b200_matvec_sync()
+            _lib.check_error()
+            a = float(torch.dot(u[:dim], hv[:dim]).item())
+            b = float(torch.dot(x[:dim], hu[:dim]).item())
+            scale = float(torch.linalg.vector_norm(u[:dim]).item() * torch.linalg.vector_norm(hv[:dim]).item())
+            checks["hermiticity_rel_err"] = abs(a - b) / max(scale, 1e-300)
+            del u, hu, hv
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1 and not complex_vectors:
         try:
             v, sample, cores, _ = cpu_matvec_sample(model, np.asarray(basis.states), 12.0)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-            cb, _ = cpu_build_sample(model, 8.0)
+            cb, cpu_reps = cpu_build_sample(model, 8.0)
             if cb is not None:
                 cpu_baseline["build"] = cb
+                # full-size parity check for free: the CPU port enumerated a prefix of the candidate range
+                # (a complete basis when the range is small) -- it must be the head of the GPU's sorted list
+                head = np.asarray(basis.states[:cpu_reps.shape[0]])
+                checks["build_prefix_equals_cpu_port"] = bool(
+                    cpu_reps.shape[0] <= dim and np.array_equal(head, cpu_reps))
+                checks["build_prefix_states"] = int(cpu_reps.shape[0])
         except Exception as e:  # the baseline is informational; never lose the GPU line over it
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
 
@@ -513,6 +541,7 @@ def main():
                   "ms": build_ms, "kernel_ms_last_shard": build_kernel_ms, "wall_ms": build_wall * 1e3,
                   "gpu_launches": int(build_launches), "unit": "states/s"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "checks": checks,
     }
     print(json.dumps(line))
     if world > 1:

@@ -55,6 +55,14 @@ def _problems():
         "hphi02": H.hphi_02_ladder,
         "hphi03": H.hphi_03_hcor,
         "hphi05": H.hphi_05_hubbard_tri,
+        # wide states at low filling: the hi-word planes (NP > 32), NP > 48 (no room for (term, sign) in the staged
+        # states: row_combine path) and NP = 64, at sizes the oracle enumerates instantly
+        "chain40_hw3": lambda: H.Problem("chain40_hw3", 40, L.heisenberg_chain(40).expression, hamming_weight=3,
+                                         symmetries=L.heisenberg_chain(40).symmetries),
+        "chain56_hw3": lambda: H.Problem("chain56_hw3", 56, L.heisenberg_chain(56).expression, hamming_weight=3,
+                                         symmetries=L.heisenberg_chain(56).symmetries),
+        "chain64_hw2": lambda: H.Problem("chain64_hw2", 64, L.heisenberg_chain(64).expression, hamming_weight=2,
+                                         symmetries=L.heisenberg_chain(64).symmetries),
         "chain12_inv_only": lambda: H.Problem(
             "chain12_inv_only", 12, L.heisenberg_chain(12).expression, hamming_weight=6, spin_inversion=-1),
         "chain10_inv_nohw": lambda: H.Problem(
@@ -63,7 +71,7 @@ def _problems():
 
 
 SYMMETRIC = ["chain10", "chain16_symm", "chain20_k3", "chain24_symm", "kagome12_complex", "kagome18_c2",
-             "kagome24_c2v_inv", "ladder_2x8_dm"]
+             "kagome24_c2v_inv", "ladder_2x8_dm", "chain40_hw3", "chain56_hw3", "chain64_hw2"]
 ALL = list(_problems().keys())
 REAL_MATVEC = [k for k in ALL if k not in ("ladder_2x8_dm", "kagome12_complex", "chain20_k3")]
 
@@ -343,7 +351,8 @@ def test_matvec_scalar_variant_agrees(oracle, built, name, monkeypatch):
     assert _rel_err(y1, y0) < MATVEC_RTOL
 
 
-@pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome24_c2v_inv", "kagome18_c2"])
+@pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome24_c2v_inv", "kagome18_c2", "chain40_hw3",
+                                  "chain56_hw3", "chain64_hw2"])
 @pytest.mark.parametrize("chunk", [None, "4096"])
 def test_matvec_pipeline_variants_agree(oracle, built, name, chunk, monkeypatch):
     """Fused (canonicalise + rank + gather in one kernel, default) vs the three-kernel
