@@ -221,7 +221,12 @@ struct CandidateIter {
     if (e.mode == 0) {
       a += 1;
     } else if (e.mode == 1) {
-      a = next_same_popcount(a);
+      // Gosper step; when the lowest run of ones does not reach bit 31 the step stays inside the low word
+      uint32_t const l = (uint32_t)a, tl = l | (l - 1);
+      if (l != 0 && tl != 0xffffffffu)
+        a = (a & 0xffffffff00000000ull) | (uint64_t)((tl + 1) | (((~tl & (tl + 1)) - 1) >> __ffs((int)l)));
+      else
+        a = next_same_popcount(a);
     } else {
       if (++ka == e.count_a) {
         ka = 0;
@@ -319,8 +324,20 @@ build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint6
         if (k + 1 < valid) it.next(e);
       }
     }
-    transpose32(lo);
-    if (NP > 32) transpose32(hi);
+    // the 32 states ascend (padding repeats the last one): equal ends mean equal everywhere, and a constant
+    // bit is a constant plane -- the common case for everything above the low ~10 bits
+    // (ascending as 64-bit values: the low words ascend only where the high words agree)
+    bool const same_hi = NP <= 32 || hi[0] == hi[31];
+    if (same_hi && ((lo[0] ^ lo[31]) >> 16) == 0) transpose32_low16(lo); else transpose32(lo);
+    if (NP > 32) {
+      if (same_hi) {
+        uint32_t const h = hi[0];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) hi[i] = ((h >> i) & 1u) ? 0xffffffffu : 0u;
+      } else {
+        transpose32(hi);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NP; ++i) xr[i] = (i < 32) ? lo[i] : hi[i - 32];
   }

@@ -40,6 +40,33 @@ LSB_HD void transpose32(uint32_t (&a)[32]) {
   }
 }
 
+// 32 ascending states whose bits 16..31 all agree (consecutive fixed-weight candidates almost always do):
+// planes 16..31 are constants and planes 0..15 come from a 16x16 butterfly on packed halves (states k and
+// k + 16 share a word) -- four stages on 16 words instead of five on 32.  In place: a[i] becomes plane i.
+LSB_HD void transpose32_low16(uint32_t (&a)[32]) {
+  uint32_t const upper = a[0] >> 16;
+  uint32_t w[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w[k] = (a[k] & 0xffffu) | (a[k + 16] << 16);
+  uint32_t m = 0x00ff00ffu;
+#pragma unroll
+  for (int j = 8; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if ((k & j) == 0) {
+        uint32_t const t = ((w[k] >> j) ^ w[k + j]) & m;
+        w[k + j] ^= t;
+        w[k] ^= t << j;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    a[i] = w[i];
+    a[i + 16] = ((upper >> i) & 1u) ? 0xffffffffu : 0u;
+  }
+}
+
 // Bit-serial comparison state for 32 lanes, fed least-significant plane first.
 //   lt: y < x so far,  eq: y == x so far.
 // One LOP3 each: a higher differing plane overrides the verdict of lower ones.
