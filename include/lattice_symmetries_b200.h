@@ -291,6 +291,15 @@ int ls_b200_matvec_device(ls_hs_operator const *op, int64_t row_begin,
                           int64_t row_end, double const *x_dev, double *y_dev);
 /* Complex128 variant (interleaved re, im).  Extension: the reference's matvec
  * is real-only (DistributedMatrixVector.chpl:1090-1091). */
+/* The product in two phases (split path; other paths do everything in phase 2):
+ * phase 1 canonicalises every matrix element of the row range -- none of that
+ * depends on x, so x_dev / y_dev may be NULL -- into buffers that persist;
+ * phase 2 ranks, gathers and sums.  A multi-GPU caller overlaps phase 1 of the
+ * next product with the NCCL all-gather of this product's result.  Every
+ * product still performs both phases exactly once. */
+int ls_b200_matvec_device_phase(ls_hs_operator const *op, int64_t row_begin,
+                                int64_t row_end, void const *x_dev, void *y_dev,
+                                int complex_vectors, int phase);
 /* Block matvec (extension; the reference halts on numVectors != 1,
  * chapel/src/DistributedMatrixVector.chpl:1096-1097): vector v is
  * x_dev + v x_stride -> y_dev + v y_stride (strides in doubles).  All vectors

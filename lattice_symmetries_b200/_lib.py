@@ -171,6 +171,8 @@ PROTOTYPES = {
         C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ls_b200_index_info": (C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_int64)]),
     "ls_b200_matvec_device": (C.c_int, [C.POINTER(ls_hs_operator), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ls_b200_matvec_device_phase": (
+        C.c_int, [C.POINTER(ls_hs_operator), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "ls_b200_matvec_block_device": (
         C.c_int, [C.POINTER(ls_hs_operator), C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "ls_b200_matvec_device_c128": (C.c_int, [C.POINTER(ls_hs_operator), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -122,7 +122,10 @@ OperatorDev &operator_dev(ls_hs_operator const *op) {
     d.diag.upload(op->diag_terms);
     changed = true;
   }
-  if (changed) d.stats_rows = -1;
+  if (changed) {
+    d.stats_rows = -1;
+    ++d.version;
+  }
   return d;
 }
 
@@ -1197,6 +1200,13 @@ struct MatvecScratch {
   cudaEvent_t inputs_ready = nullptr;
   // host-pointer entry point: finished row chunks of y drain to the caller's buffer on a copy stream while the
   // next chunks are computed
+  // phased products: one slot per chunk, sized by the chunk's exact element count, kept between the phases
+  std::vector<std::unique_ptr<ChunkSlot>> phase_slots;
+  std::vector<int64_t> phase_elements;  // exact elements per chunk, cached with the tag below
+  void const *phase_op = nullptr, *phase_index = nullptr;
+  uint64_t phase_version = 0;  // OperatorDev::version the counts were taken with
+  int64_t phase_row_begin = -1, phase_row_end = -1, phase_chunk_rows = -1;
+  bool phase_ready = false;  // phase 1 has run for the tag and phase 2 has not consumed it yet
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_done;
   cudaEvent_t copies_done = nullptr;
@@ -1235,7 +1245,10 @@ static cudaEvent_t next_event(MatvecScratch &sc) {
 // vectors share ONE canonicalisation + ranking pass -- the integer work is per matrix element, not per vector.
 static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end, double const *d_x,
                           double *d_y, bool complex_vectors, int number_vectors = 1, int64_t x_stride = 0,
-                          int64_t y_stride = 0, double *host_y = nullptr) {
+                          int64_t y_stride = 0, double *host_y = nullptr, int phase = 0) {
+  // phase (split path, one vector): 1 = canonicalise only -- row counts, offsets, representatives of every chunk,
+  // none of which depends on x -- into per-chunk buffers that persist; 2 = rank + gather + row sums from them.
+  // A multi-GPU caller runs phase 1 of the NEXT product while NCCL all-gathers the result of this one.
   Runtime &rt = runtime();
   ls_hs_basis const *basis = op->basis;
   IndexData *ix = index_of(basis);
@@ -1296,7 +1309,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     size_t const words = (size_t)dim * (complex_vectors ? 2 : 1);
     double *xs = sc.xs.reserve(words * (size_t)number_vectors);
     unsigned const blocks = (unsigned)std::min<int64_t>((dim + 255) / 256, (int64_t)rt.sm_count * 16);
-    for (int v = 0; v < number_vectors; ++v) {
+    for (int v = 0; v < number_vectors && phase != 1; ++v) {
       // (xs is packed: vector v at xs + v dim, whatever the caller's stride)
       prescale_kernel<<<blocks, 256, 0, rt.stream>>>(dim, a.complex_vectors, ix->d_norms,
                                                      d_x + (size_t)v * (size_t)x_stride * (complex_vectors ? 2 : 1),
@@ -1372,7 +1385,9 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   if (pipelined) capacity /= 2;
   int64_t chunk_rows = row_end - row_begin;
   OrbitKernel orbit = nullptr;
-  int const number_slots = pipelined ? 2 : 1;
+  bool const phased = phase != 0 && split && T > 0 && a.mode == kModeGroup && a.number_vectors == 1 && host_y == nullptr;
+  if (phased) pipelined = false;
+  int const number_slots = phased ? 0 : (pipelined ? 2 : 1);
   if (queued) {
     chunk_rows = std::max<int64_t>(1, std::min<int64_t>(chunk_rows, capacity / T));
     capacity = chunk_rows * T;
@@ -1393,7 +1408,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
       }
     }
     size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, sc.slot[0].counts.ptr, sc.slot[0].offsets.ptr, (int)(chunk_rows + 1), rt.stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(chunk_rows + 1), rt.stream);
     if (tmp > sc.scan_tmp_bytes) {
       sc.scan_tmp.reserve(tmp);
       sc.scan_tmp_bytes = sc.scan_tmp.capacity;
@@ -1430,6 +1445,81 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     size_t const rank_smem = want_tsign ? ((size_t)T + (size_t)a.number_chars) * 16 : 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_gather, kRankThreads, rank_smem));
     rank_resident = (unsigned)std::max(1, per_sm) * (unsigned)rt.sm_count;
+  }
+  if (phase == 1 && !phased) return;  // nothing to precompute on this path: phase 2 does the whole product
+  if (phased) {
+    int64_t const number_chunks = (row_end - row_begin + chunk_rows - 1) / chunk_rows;
+    bool const same = sc.phase_op == op && sc.phase_index == ix && sc.phase_version == od.version &&
+                      sc.phase_row_begin == row_begin &&
+                      sc.phase_row_end == row_end && sc.phase_chunk_rows == chunk_rows &&
+                      (int64_t)sc.phase_elements.size() == number_chunks;
+    if (!same) {
+      // exact element counts per chunk (one counting pass, cached): the persistent buffers are sized by them
+      sc.phase_elements.assign((size_t)number_chunks, 0);
+      for (int64_t c = 0; c < number_chunks; ++c) {
+        int64_t const begin = row_begin + c * chunk_rows;
+        sc.phase_elements[(size_t)c] = count_elements(od, *ix, begin, std::min(row_end, begin + chunk_rows));
+      }
+      sc.phase_op = op;
+      sc.phase_index = ix;
+      sc.phase_version = od.version;
+      sc.phase_row_begin = row_begin;
+      sc.phase_row_end = row_end;
+      sc.phase_chunk_rows = chunk_rows;
+      sc.phase_ready = false;
+      while ((int64_t)sc.phase_slots.size() < number_chunks) sc.phase_slots.push_back(std::make_unique<ChunkSlot>());
+    }
+    int64_t most = 0;
+    for (int64_t n : sc.phase_elements) most = std::max(most, n);
+    auto bind = [&](int64_t c) {
+      ChunkSlot &slot = *sc.phase_slots[(size_t)c];
+      int64_t const begin = row_begin + c * chunk_rows;
+      int64_t const nrows = std::min(chunk_rows, row_end - begin);
+      size_t const n = (size_t)sc.phase_elements[(size_t)c] + 32;
+      a.chunk_begin = begin;
+      a.chunk_rows = (int)nrows;
+      a.counts = slot.counts.reserve((size_t)nrows + 1);
+      a.offsets = slot.offsets.reserve((size_t)nrows + 1);
+      a.q_rep = slot.q_rep.reserve(n);
+      a.q_cidx = slot.q_cidx.reserve(n);
+      a.q_tsign = want_tsign ? slot.q_tsign.reserve(n) : nullptr;
+      a.vals = sc.slot[0].vals.reserve(((size_t)most + 32) * (complex_vectors ? 2 : 1));
+      a.vals_stride = most + 32;
+      return nrows;
+    };
+    if (phase == 1 || !sc.phase_ready) {
+      for (int64_t c = 0; c < number_chunks; ++c) {
+        int64_t const nrows = bind(c);
+        row_count_kernel<<<ceil_div((size_t)nrows + 1, 256), 256, count_smem, rt.stream>>>(a);
+        size_t tmp = sc.scan_tmp_bytes;
+        cub::DeviceScan::ExclusiveSum(sc.scan_tmp.ptr, tmp, a.counts, a.offsets, (int)(nrows + 1), rt.stream);
+        size_t const words = (((size_t)sc.phase_elements[(size_t)c] + 1023) / 1024) * 32;
+        if (words > 0) orbit<<<ceil_div(words, kOrbitThreads), kOrbitThreads, orbit_smem, rt.stream>>>(a);
+        count_launch(3);
+      }
+      CUDA_CHECK(cudaGetLastError());
+      sc.phase_ready = true;
+    }
+    if (phase == 2) {
+      for (int64_t c = 0; c < number_chunks; ++c) {
+        int64_t const nrows = bind(c);
+        size_t const tiles = ceil_div((size_t)sc.phase_elements[(size_t)c], 32 * kRankBatch);
+        size_t const rank_smem = a.q_tsign != nullptr ? ((size_t)T + (size_t)a.number_chars) * 16 : 0;
+        if (tiles > 0) {
+          unsigned const blocks = std::min<unsigned>(ceil_div(tiles, kRankThreads / 32), rank_resident);
+          rank_gather<<<blocks, kRankThreads, rank_smem, rt.stream>>>(a);
+        }
+        if (a.q_tsign != nullptr)
+          row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, rt.stream>>>(a);
+        else
+          row_combine<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
+        count_launch(2);
+      }
+      CUDA_CHECK(cudaGetLastError());
+      sc.phase_ready = false;
+    }
+    CUDA_CHECK(cudaEventRecord(rt.ev1, rt.stream));
+    return;
   }
   cudaStream_t const stream_a = rt.stream;
   cudaStream_t stream_b = rt.stream;
@@ -1622,6 +1712,18 @@ int ls_b200_matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   int status = -1;
   guarded(__func__, [&] {
     matvec_device(op, row_begin, row_end, x_dev, y_dev, false);
+    status = 0;
+  });
+  return status;
+}
+
+int ls_b200_matvec_device_phase(ls_hs_operator const *op, int64_t row_begin, int64_t row_end, void const *x_dev,
+                                void *y_dev, int complex_vectors, int phase) {
+  int status = -1;
+  guarded(__func__, [&] {
+    LSB_CHECK(phase == 1 || phase == 2, "phase must be 1 (canonicalise) or 2 (apply)");
+    matvec_device(op, row_begin, row_end, static_cast<double const *>(x_dev), static_cast<double *>(y_dev),
+                  complex_vectors != 0, 1, 0, 0, nullptr, phase);
     status = 0;
   });
   return status;

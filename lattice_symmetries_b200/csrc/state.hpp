@@ -95,6 +95,7 @@ struct TermsDev {
 struct OperatorDev {
   TermsDev off, diag;
   int distinct_x = 0;  // Operator.hs:190-193 maxNumberOffDiag
+  uint64_t version = 1;  // bumped whenever the term tables are re-uploaded
   // matrix-element statistics of the basis the operator was last used with
   void const *stats_index = nullptr;
   int64_t stats_rows = -1;

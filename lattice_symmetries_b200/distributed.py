@@ -260,14 +260,29 @@ class ShardedOperator:
         if gather and L.world > 1:
             mine = y_full[L.rank * L.chunk:(L.rank + 1) * L.chunk]
             if cplx:
-                dist.all_gather_into_tensor(torch.view_as_real(y_full), torch.view_as_real(mine), group=self.group)
+                work = dist.all_gather_into_tensor(torch.view_as_real(y_full), torch.view_as_real(mine), group=self.group,
+                                                   async_op=True)
             else:
-                dist.all_gather_into_tensor(y_full, mine, group=self.group)
+                work = dist.all_gather_into_tensor(y_full, mine, group=self.group, async_op=True)
+            # While NCCL replicates y: canonicalise the matrix elements for the NEXT product (they do not depend
+            # on the vector).  Every product still runs both phases exactly once.
+            if L.row_end > L.row_begin:
+                self._prepare_rows(L.row_begin, L.row_end, cplx)
+            work.wait()
 
     def _local_rows(self, x_full, y_full, row_begin: int, row_end: int, cplx: bool) -> None:
         """y_full[row_begin:row_end] = (H x)[row_begin:row_end] on this rank's GPU."""
         y_ptr = y_full.data_ptr() + row_begin * y_full.element_size()
-        self.op.matvec_device(x_full.data_ptr(), y_ptr, row_begin, row_end, complex_vectors=cplx)
+        if self.layout.world > 1:
+            # phase 2 (phase 1 ran during the previous all-gather, or runs now on the first call)
+            self.op.matvec_device_phase(2, x_full.data_ptr(), y_ptr, row_begin, row_end, complex_vectors=cplx)
+        else:
+            self.op.matvec_device(x_full.data_ptr(), y_ptr, row_begin, row_end, complex_vectors=cplx)
+
+    def _prepare_rows(self, row_begin: int, row_end: int, cplx: bool) -> None:
+        """Work of the next product that does not depend on the vector (overridable; no-op without an operator)."""
+        if self.op is not None:
+            self.op.matvec_device_phase(1, 0, 0, row_begin, row_end, complex_vectors=cplx)
 
     def dot(self, a_full, b_full):
         """Global <a, b> from the local rows (one all-reduce of a scalar)."""

@@ -208,6 +208,19 @@ class Operator(_Base):
         _lib.check_error()
         return out
 
+    def matvec_device_phase(self, phase: int, x_ptr: int = 0, y_ptr: int = 0, row_begin: int = 0, row_end: int = -1,
+                            complex_vectors: bool = False) -> None:
+        """Phase 1: canonicalise the matrix elements of the row range (independent of x); phase 2: rank, gather, sum."""
+        self._check_basis_is_built("matvec_device_phase")
+        if row_end < 0:
+            row_end = self._basis.number_states
+        status = lib.ls_b200_matvec_device_phase(
+            C.byref(self._payload), int(row_begin), int(row_end), x_ptr or None, y_ptr or None,
+            1 if complex_vectors else 0, int(phase))
+        _lib.check_error()
+        if status != 0:
+            raise RuntimeError("ls_b200_matvec_device_phase failed")
+
     def matvec_block_device(self, number_vectors: int, x_ptr: int, x_stride: int, y_ptr: int, y_stride: int,
                             row_begin: int = 0, row_end: int = -1, sync: bool = False) -> None:
         """Block matvec on device-resident float64 vectors: vector v is x_ptr + 8 v x_stride -> y_ptr + 8 v y_stride;

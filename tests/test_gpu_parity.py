@@ -410,6 +410,35 @@ def test_block_matvec_equals_single_vectors(oracle, built, name, monkeypatch):
     assert np.array_equal(got, want[:, lo:hi])
 
 
+@pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome24_c2v_inv", "chain56_hw3", "hubbard_2x4",
+                                  "ladder_2x8_dm"])
+def test_phased_matvec_equals_plain(oracle, built, name, monkeypatch):
+    """canonicalise (phase 1) + apply (phase 2) == the plain product, also when phase 1 ran for an earlier vector,
+    when it is skipped (phase 2 catches up) and with several chunks."""
+    from lattice_symmetries_b200 import _lib
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    dim = reps.shape[0]
+    cplx = name == "ladder_2x8_dm"
+    dtype = np.complex128 if cplx else np.float64
+    rng = np.random.default_rng(21)
+    lo, hi = dim // 5, dim - dim // 7
+    for chunk in (None, "4096"):
+        if chunk is not None:
+            monkeypatch.setenv("LS_B200_MV_CHUNK", chunk)
+        for trial in range(3):
+            x = rng.standard_normal(dim) + (1j * rng.standard_normal(dim) if cplx else 0)
+            d_x = _lib.DeviceArray.from_numpy(x.astype(dtype))
+            d_y = _lib.DeviceArray(hi - lo, dtype)
+            d_z = _lib.DeviceArray(hi - lo, dtype)
+            op.matvec_device(d_x.ptr, d_y.ptr, lo, hi, complex_vectors=cplx, sync=True)
+            if trial != 1:
+                op.matvec_device_phase(1, 0, 0, lo, hi, complex_vectors=cplx)
+            op.matvec_device_phase(2, d_x.ptr, d_z.ptr, lo, hi, complex_vectors=cplx)
+            _lib.lib.ls_b200_matvec_sync()
+            _lib.check_error()
+            assert np.array_equal(d_z.numpy(), d_y.numpy()), (chunk, trial)
+
+
 @pytest.mark.parametrize("name", ["chain16_symm", "kagome18_c2", "hubbard_2x4"])
 def test_matvec_device_row_ranges(oracle, built, name):
     """Device-resident entry point on contiguous row shards == host-pointer entry point."""
