@@ -1494,7 +1494,12 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
         size_t tmp = sc.scan_tmp_bytes;
         cub::DeviceScan::ExclusiveSum(sc.scan_tmp.ptr, tmp, a.counts, a.offsets, (int)(nrows + 1), rt.stream);
         size_t const words = (((size_t)sc.phase_elements[(size_t)c] + 1023) / 1024) * 32;
+        if (profile) {
+          sc.spans.emplace_back(sc.events_used, 0);
+          CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+        }
         if (words > 0) orbit<<<ceil_div(words, kOrbitThreads), kOrbitThreads, orbit_smem, rt.stream>>>(a);
+        if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
         count_launch(3);
       }
       CUDA_CHECK(cudaGetLastError());
@@ -1505,14 +1510,24 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
         int64_t const nrows = bind(c);
         size_t const tiles = ceil_div((size_t)sc.phase_elements[(size_t)c], 32 * kRankBatch);
         size_t const rank_smem = a.q_tsign != nullptr ? ((size_t)T + (size_t)a.number_chars) * 16 : 0;
+        if (profile) {
+          sc.spans.emplace_back(sc.events_used, 1);
+          CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+        }
         if (tiles > 0) {
           unsigned const blocks = std::min<unsigned>(ceil_div(tiles, kRankThreads / 32), rank_resident);
           rank_gather<<<blocks, kRankThreads, rank_smem, rt.stream>>>(a);
+        }
+        if (profile) {
+          CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
+          sc.spans.emplace_back(sc.events_used, 2);
+          CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
         }
         if (a.q_tsign != nullptr)
           row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, rt.stream>>>(a);
         else
           row_combine<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
+        if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
         count_launch(2);
       }
       CUDA_CHECK(cudaGetLastError());
