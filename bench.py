@@ -408,11 +408,10 @@ def main():
             hx[:rows].copy_(host_x[L.row_begin:L.row_end])
 
             def e2e_step():
-                mine = x[L.rank * L.chunk:(L.rank + 1) * L.chunk]
-                mine.copy_(hx, non_blocking=True)
-                dist.all_gather_into_tensor(x, mine)
+                x[L.row_begin:L.row_end].copy_(hx[:rows], non_blocking=True)
+                sh.gather_rows(x)
                 sh.matvec(x, y, gather=False)
-                hy.copy_(y[L.rank * L.chunk:(L.rank + 1) * L.chunk], non_blocking=True)
+                hy[:rows].copy_(y[L.row_begin:L.row_end], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
             e2e_step()
             sync()
@@ -536,7 +535,8 @@ def main():
         "dtype": "c128" if complex_vectors else "f64", "data": "synthetic",
         "config": {"workload": desc, "name": args.workload, "dim": dim, "candidates": total_candidates,
                    "off_diag_elements": nnz_total, "l2": "flushed between steps" if small else "inputs larger than L2",
-                   "parallelism": f"rows sharded over {world} rank(s), x all-gathered" if world > 1 else "single GPU"},
+                   "parallelism": (f"rows sharded over {world} rank(s) by matrix-element count, result all-gathered"
+                                   if world > 1 else "single GPU")},
         "build": {"candidates_per_s": total_candidates / (build_ms * 1e-3), "representatives_per_s": dim / (build_ms * 1e-3),
                   "ms": build_ms, "kernel_ms_last_shard": build_kernel_ms, "wall_ms": build_wall * 1e3,
                   "gpu_launches": int(build_launches), "unit": "states/s"},

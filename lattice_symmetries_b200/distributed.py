@@ -27,7 +27,8 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "block_plan", "row_bounds", "exchange_shards", "exchange_blocks", "ShardedOperator",
+__all__ = ["shard_bounds", "block_plan", "row_bounds", "balanced_row_bounds", "exchange_shards", "exchange_blocks",
+           "ShardedOperator",
            "build_sharded", "init_process"]
 
 ALIGN = 32  # candidate shards start on a multiple of 32 (one bit-sliced word)
@@ -218,7 +219,31 @@ class _Layout:
     rank: int
     row_begin: int
     row_end: int
-    chunk: int
+    chunk: int                      # rows of the largest shard: the all-gather slot size
+    bounds: Optional[list] = None   # (row_begin, row_end) of every rank; None: the even split of row_bounds
+
+
+def balanced_row_bounds(block_costs, block_rows: int, dim: int, world: int):
+    """Contiguous row ranges of (nearly) equal cost from per-block costs (block b = rows
+    [b block_rows, (b + 1) block_rows)): rank r ends at the first block boundary where the running
+    cost reaches (r + 1) / world of the total.  Rows of the sorted basis do not cost the same -- on
+    kagome-36 the first eighth of the rows holds 0.87x, the last 1.12x the mean number of matrix
+    elements -- and a step is as slow as its slowest rank."""
+    total = float(sum(block_costs))
+    bounds, lo, acc, b = [], 0, 0.0, 0
+    for r in range(world):
+        target = total * (r + 1) / world
+        while b < len(block_costs) and (acc + block_costs[b] <= target or r == world - 1):
+            acc += block_costs[b]
+            b += 1
+        # take the block that straddles the target if that lands closer to it
+        if r < world - 1 and b < len(block_costs) and target - acc > acc + block_costs[b] - target:
+            acc += block_costs[b]
+            b += 1
+        hi = dim if r == world - 1 else min(dim, b * block_rows)
+        bounds.append((lo, max(lo, hi)))
+        lo = max(lo, hi)
+    return bounds
 
 
 class ShardedOperator:
@@ -230,7 +255,10 @@ class ShardedOperator:
 
     device = "cuda"
 
-    def __init__(self, operator, group=None, dim: Optional[int] = None):
+    def __init__(self, operator, group=None, dim: Optional[int] = None, bounds=None, balance: bool = True):
+        """``bounds``: explicit (row_begin, row_end) per rank; otherwise, with an operator and ``balance``, the
+        rows are split by matrix-element count (every rank computes the same split from the replicated basis),
+        else evenly."""
         import torch.distributed as dist
         self.op = operator
         self.group = group
@@ -238,8 +266,29 @@ class ShardedOperator:
             dim = operator.basis.number_states
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
-        lo, hi, chunk = row_bounds(dim, world, rank)
-        self.layout = _Layout(dim, world, rank, lo, hi, chunk)
+        if bounds is None and balance and operator is not None and world > 1 and dim >= 4096 * world:
+            blocks = 64 * world
+            block_rows = -(-dim // blocks)
+            costs = []
+            for b in range(blocks):
+                lo_b, hi_b = min(b * block_rows, dim), min((b + 1) * block_rows, dim)
+                # 4 row-proportional units (alpha, norm, x, y traffic and the term scan) per row on top of its elements
+                costs.append(operator.count_matrix_elements(lo_b, hi_b) + 4 * (hi_b - lo_b) if hi_b > lo_b else 0)
+            bounds = balanced_row_bounds(costs, block_rows, dim, world)
+        if bounds is not None:
+            bounds = [(int(a), int(b)) for a, b in bounds]
+            assert len(bounds) == world and bounds[0][0] == 0 and bounds[-1][1] == dim
+            assert all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
+            chunk = max(hi - lo for lo, hi in bounds)
+            even = [row_bounds(dim, world, r)[:2] for r in range(world)]
+            if [tuple(b) for b in bounds] == [tuple(e) for e in even]:
+                bounds = None
+        if bounds is None:
+            lo, hi, chunk = row_bounds(dim, world, rank)
+        else:
+            lo, hi = bounds[rank]
+        self.layout = _Layout(dim, world, rank, lo, hi, chunk, bounds)
+        self._gather_buffers = {}
 
     def empty_vector(self, dtype=None):
         import torch
@@ -258,17 +307,43 @@ class ShardedOperator:
         if L.row_end > L.row_begin:
             self._local_rows(x_full, y_full, L.row_begin, L.row_end, cplx)
         if gather and L.world > 1:
-            mine = y_full[L.rank * L.chunk:(L.rank + 1) * L.chunk]
-            if cplx:
-                work = dist.all_gather_into_tensor(torch.view_as_real(y_full), torch.view_as_real(mine), group=self.group,
-                                                   async_op=True)
-            else:
-                work = dist.all_gather_into_tensor(y_full, mine, group=self.group, async_op=True)
             # While NCCL replicates y: canonicalise the matrix elements for the NEXT product (they do not depend
             # on the vector).  Every product still runs both phases exactly once.
-            if L.row_end > L.row_begin:
-                self._prepare_rows(L.row_begin, L.row_end, cplx)
+            self.gather_rows(y_full, overlap=(lambda: self._prepare_rows(L.row_begin, L.row_end, cplx))
+                             if L.row_end > L.row_begin else None)
+
+    def gather_rows(self, v_full, overlap=None) -> None:
+        """Replicate every rank's rows of ``v_full`` on all ranks (one all-gather); ``overlap`` is called while
+        the collective is in flight."""
+        import torch
+        import torch.distributed as dist
+        L = self.layout
+        if L.world == 1:
+            return
+        real = (lambda t: torch.view_as_real(t)) if v_full.dtype == torch.complex128 else (lambda t: t)
+        if L.bounds is None:
+            # even split: rank r's rows already sit in slot r of the padded vector -- gather in place
+            mine = v_full[L.rank * L.chunk:(L.rank + 1) * L.chunk]
+            work = dist.all_gather_into_tensor(real(v_full), real(mine), group=self.group, async_op=True)
+            if overlap is not None:
+                overlap()
             work.wait()
+            return
+        # balanced (uneven) split: gather fixed-size slots into a side buffer, then copy the other ranks' rows home
+        key = (v_full.dtype, v_full.device)
+        buf = self._gather_buffers.get(key)
+        if buf is None:
+            buf = torch.zeros(L.world * L.chunk, dtype=v_full.dtype, device=v_full.device)
+            self._gather_buffers[key] = buf
+        mine = buf[L.rank * L.chunk:(L.rank + 1) * L.chunk]
+        mine[:L.row_end - L.row_begin].copy_(v_full[L.row_begin:L.row_end])
+        work = dist.all_gather_into_tensor(real(buf), real(mine), group=self.group, async_op=True)
+        if overlap is not None:
+            overlap()
+        work.wait()
+        for r, (lo, hi) in enumerate(L.bounds):
+            if r != L.rank and hi > lo:
+                v_full[lo:hi].copy_(buf[r * L.chunk:r * L.chunk + (hi - lo)])
 
     def _local_rows(self, x_full, y_full, row_begin: int, row_end: int, cplx: bool) -> None:
         """y_full[row_begin:row_end] = (H x)[row_begin:row_end] on this rank's GPU."""

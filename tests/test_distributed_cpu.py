@@ -17,7 +17,7 @@ for p in (str(ROOT), str(ROOT / "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-from lattice_symmetries_b200.distributed import block_plan, row_bounds, shard_bounds  # noqa: E402
+from lattice_symmetries_b200.distributed import balanced_row_bounds, block_plan, row_bounds, shard_bounds  # noqa: E402
 
 
 def _free_port() -> int:
@@ -52,6 +52,22 @@ def test_block_plan_partition(total, world):
     assert prev == total
     if total > (1 << 22) * world * 16:
         assert world * 16 <= len(plan) <= world * 16 + 1
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_balanced_row_bounds(world):
+    rng = np.random.default_rng(3)
+    blocks, block_rows = 64 * world, 100
+    dim = blocks * block_rows - 37
+    costs = list(np.linspace(0.8, 1.2, blocks) * 1000 + rng.integers(0, 50, blocks))
+    bounds = balanced_row_bounds(costs, block_rows, dim, world)
+    assert len(bounds) == world and bounds[0][0] == 0 and bounds[-1][1] == dim
+    assert all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
+    per_rank = [sum(costs[lo // block_rows:-(-hi // block_rows)]) for lo, hi in bounds]
+    assert max(per_rank) <= 1.03 * sum(costs) / world + max(costs)
+    # rows no longer split evenly: later (costlier) ranks own fewer rows
+    if world > 1:
+        assert bounds[0][1] - bounds[0][0] > bounds[-1][1] - bounds[-1][0]
 
 
 @pytest.mark.parametrize("dim", [0, 1, 5, 13, 28968])
@@ -164,6 +180,16 @@ def _worker_matvec(rank, world, port, out):
             def _local_rows(self, x_full, y_full, row_begin, row_end, cplx):
                 y_full[row_begin:row_end] = torch.from_numpy(A[row_begin:row_end] @ x_full[:dim].numpy())
 
+        # uneven (balanced-style) shards: same answers through the side-buffer gather
+        cuts = [0] + sorted({(dim * (2 * r + 1)) // (2 * world + 1) for r in range(1, world)}) + [dim]
+        while len(cuts) < world + 1:
+            cuts.insert(-1, cuts[-2])
+        uneven = Dense(None, dim=dim, bounds=list(zip(cuts[:-1], cuts[1:])))
+        xu = uneven.empty_vector()
+        xu[:dim] = torch.from_numpy(np.arange(dim, dtype=np.float64))
+        yu = uneven.empty_vector()
+        uneven.matvec(xu, yu)
+        assert np.allclose(yu[:dim].numpy(), A @ np.arange(dim, dtype=np.float64))
         sh = Dense(None, dim=dim)
         x = sh.empty_vector()
         x[:dim] = torch.from_numpy(rng.standard_normal(dim))
