@@ -700,17 +700,13 @@ orbit_gather_kernel(__grid_constant__ MatvecArgs const a) {
   }
 }
 
-// Thread per row: sum the row's values in term order, add the diagonal, write y once.  The values of a
-// block's 256 rows are one contiguous span: it streams through shared memory in tiles (coalesced loads) and
-// every thread adds the part of its row that lies in the tile -- same summation order as a plain loop.
-constexpr int kSumTile = 2048;  // doubles per tile (16 KB)
+// Thread per row: sum the row's values in term order, add the diagonal, write y once.
 template <bool CPLX>
 __global__ void __launch_bounds__(256)
 row_sum_kernel(MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
   int const TD = a.diag.number_terms;
-  double *tile = reinterpret_cast<double *>(smem);
-  double2 *d_v = reinterpret_cast<double2 *>(tile + kSumTile);
+  double2 *d_v = reinterpret_cast<double2 *>(smem);
   uint64_t *d_m = reinterpret_cast<uint64_t *>(d_v + TD);
   uint64_t *d_r = d_m + TD;
   uint64_t *d_s = d_r + TD;
@@ -720,41 +716,23 @@ row_sum_kernel(MatvecArgs const a) {
     d_s[t] = a.diag.s[t];
     d_v[t] = a.diag.v[t];
   }
-  int const r0 = blockIdx.x * blockDim.x;
-  int const r = r0 + threadIdx.x;
-  bool const mine = r < a.chunk_rows;
+  __syncthreads();
+  int const r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.chunk_rows) return;
   int64_t const vec = blockIdx.y;  // block matvec: one grid row per vector
-  int64_t const row = a.chunk_begin + (mine ? r : 0);
+  int64_t const row = a.chunk_begin + r;
   uint64_t const alpha = __ldg(a.ix.reps + row);
-  uint32_t const qa = mine ? __ldg(a.offsets + r) : 0u, qb = mine ? __ldg(a.offsets + r + 1) : 0u;
-  uint32_t const span_begin = __ldg(a.offsets + r0);
-  uint32_t const span_end = __ldg(a.offsets + min(r0 + (int)blockDim.x, a.chunk_rows));
-  constexpr uint32_t kPerTile = CPLX ? kSumTile / 2 : kSumTile;  // elements per tile
+  uint32_t const qa = __ldg(a.offsets + r), qb = __ldg(a.offsets + r + 1);
   double acc_r = 0.0, acc_i = 0.0;
-  for (uint32_t t0 = span_begin; t0 < span_end; t0 += kPerTile) {
-    uint32_t const t1 = min(span_end, t0 + kPerTile);
-    __syncthreads();  // the previous tile has been consumed (and the diagonal tables are staged)
+  for (uint32_t q = qa; q < qb; ++q) {
     if (CPLX) {
-      double2 const *src = reinterpret_cast<double2 const *>(a.vals) + vec * a.vals_stride;
-      for (uint32_t q = t0 + threadIdx.x; q < t1; q += blockDim.x) reinterpret_cast<double2 *>(tile)[q - t0] = __ldcs(src + q);
+      double2 const v = __ldcs(reinterpret_cast<double2 const *>(a.vals) + vec * a.vals_stride + q);
+      acc_r += v.x;
+      acc_i += v.y;
     } else {
-      double const *src = a.vals + vec * a.vals_stride;
-      for (uint32_t q = t0 + threadIdx.x; q < t1; q += blockDim.x) tile[q - t0] = __ldcs(src + q);
-    }
-    __syncthreads();
-    uint32_t const lo = max(qa, t0), hi = min(qb, t1);
-    for (uint32_t q = lo; q < hi; ++q) {
-      if (CPLX) {
-        double2 const v = reinterpret_cast<double2 const *>(tile)[q - t0];
-        acc_r += v.x;
-        acc_i += v.y;
-      } else {
-        acc_r += tile[q - t0];
-      }
+      acc_r += __ldcs(a.vals + vec * a.vals_stride + q);
     }
   }
-  __syncthreads();  // (rows without values never entered the loop: make sure the diagonal tables are staged)
-  if (!mine) return;
   double dr = 0.0, di = 0.0;
   for (int k = 0; k < TD; ++k)
     if ((alpha & d_m[k]) == d_r[k]) {
@@ -1356,7 +1334,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   size_t orbit_smem = ((count_smem + 15) & ~size_t(15)) + (size_t)(kOrbitThreads / 32) * kWarpSlabBytes;
   size_t const fused_smem = ((AdjointTerms::bytes(T, true) + 15) & ~size_t(15)) + (size_t)a.number_chars * 16 +
                             (size_t)(kOrbitThreads / 32) * kFusedWarpBytes;
-  size_t const sum_smem = (size_t)a.diag.number_terms * 40 + (size_t)kSumTile * sizeof(double);
+  size_t const sum_smem = (size_t)a.diag.number_terms * 40;
   // Pipeline variants (LS_B200_MATVEC, for A/B measurements; results agree to rounding):
   //   split   (default) orbit kernel -> full-occupancy rank + gather kernel -> per-row sum
   //   fused   canonicalise + rank + gather in one kernel, then a per-row sum
