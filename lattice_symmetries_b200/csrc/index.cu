@@ -28,6 +28,7 @@ IndexView IndexData::view() const {
 }
 
 IndexData::~IndexData() {
+  matvec_forget_index(this);
   if (owns_d_reps) cudaFree(d_reps);
   cudaFree(d_offsets32);
   cudaFree(d_offsets64);

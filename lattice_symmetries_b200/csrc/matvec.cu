@@ -1224,6 +1224,16 @@ static MatvecScratch &mv_scratch() {
   return s;
 }
 
+void matvec_forget_index(IndexData const *ix) {
+  MatvecScratch &sc = mv_scratch();
+  if (sc.phase_index == ix) {
+    sc.phase_index = nullptr;
+    sc.phase_op = nullptr;
+    sc.phase_ready = false;
+    sc.phase_elements.clear();
+  }
+}
+
 template <class K>
 static void allow_dynamic_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024)

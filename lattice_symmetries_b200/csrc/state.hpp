@@ -117,6 +117,8 @@ struct BasisInfo {
 };
 BasisInfo basis_info(ls_hs_basis const *basis);
 IndexData *index_of(ls_hs_basis const *basis);
+// An index object is going away: cached per-index state of the matvec (phased canonicalisation) must not outlive it.
+void matvec_forget_index(IndexData const *ix);
 
 // Combinadics (haskell/src/LatticeSymmetries/Basis.hs:487-550)
 uint64_t binomial(int n, int k);
