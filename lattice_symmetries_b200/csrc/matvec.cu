@@ -1209,7 +1209,7 @@ struct MatvecScratch {
   bool phase_ready = false;  // phase 1 has run for the tag and phase 2 has not consumed it yet
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_done;
-  cudaEvent_t copies_done = nullptr;
+  cudaEvent_t copies_done = nullptr, x_uploaded = nullptr;
   DeviceBuffer<unsigned char> scan_tmp;
   size_t scan_tmp_bytes = 0;
   int *d_error = nullptr;
@@ -1395,7 +1395,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   if (pipelined) capacity /= 2;
   int64_t chunk_rows = row_end - row_begin;
   OrbitKernel orbit = nullptr;
-  bool const phased = phase != 0 && split && T > 0 && a.mode == kModeGroup && a.number_vectors == 1 && host_y == nullptr;
+  bool const phased = phase != 0 && split && T > 0 && a.mode == kModeGroup && a.number_vectors == 1;
   if (phased) pipelined = false;
   int const number_slots = phased ? 0 : (pipelined ? 2 : 1);
   if (queued) {
@@ -1456,6 +1456,33 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_gather, kRankThreads, rank_smem));
     rank_resident = (unsigned)std::max(1, per_sm) * (unsigned)rt.sm_count;
   }
+  // host-pointer callers: rows [begin, begin + nrows) of y are final once `producer` reaches this point -- copy them
+  // out on the copy stream behind the next chunk's kernels
+  auto drain = [&](int64_t chunk_no, int64_t begin, int64_t nrows, cudaStream_t producer) {
+    if (host_y == nullptr) return;
+    if (sc.copy_stream == nullptr) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&sc.copies_done, cudaEventDisableTiming));
+    }
+    while (sc.chunk_done.size() <= (size_t)chunk_no) {
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      sc.chunk_done.push_back(e);
+    }
+    CUDA_CHECK(cudaEventRecord(sc.chunk_done[(size_t)chunk_no], producer));
+    CUDA_CHECK(cudaStreamWaitEvent(sc.copy_stream, sc.chunk_done[(size_t)chunk_no], 0));
+    size_t const scalar = sizeof(double) * (complex_vectors ? 2 : 1);
+    for (int v = 0; v < a.number_vectors; ++v) {
+      size_t const at = ((size_t)v * (size_t)(a.number_vectors > 1 ? a.y_stride : 0) + (size_t)(begin - row_begin)) * scalar;
+      CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(host_y) + at, reinterpret_cast<char const *>(d_y) + at,
+                                 (size_t)nrows * scalar, cudaMemcpyDeviceToHost, sc.copy_stream));
+    }
+  };
+  auto drain_finish = [&]() {
+    if (host_y == nullptr || sc.copy_stream == nullptr) return;
+    CUDA_CHECK(cudaEventRecord(sc.copies_done, sc.copy_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(rt.stream, sc.copies_done, 0));
+  };
   if (phase == 1 && !phased) return;  // nothing to precompute on this path: phase 2 does the whole product
   if (phased) {
     int64_t const number_chunks = (row_end - row_begin + chunk_rows - 1) / chunk_rows;
@@ -1539,8 +1566,10 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
           row_combine<<<ceil_div((size_t)nrows, kGatherThreads), kGatherThreads, gather_smem, rt.stream>>>(a);
         if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), rt.stream));
         count_launch(2);
+        drain(c, a.chunk_begin, nrows, rt.stream);
       }
       CUDA_CHECK(cudaGetLastError());
+      drain_finish();
       sc.phase_ready = false;
     }
     CUDA_CHECK(cudaEventRecord(rt.ev1, rt.stream));
@@ -1627,36 +1656,9 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     if (profile) CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
     if (pipelined) CUDA_CHECK(cudaEventRecord(slot.released, stream_b));
     CUDA_CHECK(cudaGetLastError());
-    if (host_y != nullptr) {
-      // rows [begin, begin + nrows) of y are final: copy them out behind the next chunk's kernels
-      if (sc.copy_stream == nullptr) {
-        CUDA_CHECK(cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
-        CUDA_CHECK(cudaEventCreateWithFlags(&sc.copies_done, cudaEventDisableTiming));
-      }
-      while (sc.chunk_done.size() <= (size_t)chunk_index) {
-        cudaEvent_t e;
-        CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        sc.chunk_done.push_back(e);
-      }
-      CUDA_CHECK(cudaEventRecord(sc.chunk_done[(size_t)chunk_index], stream_b));
-      CUDA_CHECK(cudaStreamWaitEvent(sc.copy_stream, sc.chunk_done[(size_t)chunk_index], 0));
-      size_t const scalar = sizeof(double) * (complex_vectors ? 2 : 1);
-      for (int v = 0; v < a.number_vectors; ++v) {
-        size_t const at = ((size_t)v * (size_t)(a.number_vectors > 1 ? a.y_stride : 0) + (size_t)(begin - row_begin)) * scalar;
-        CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(host_y) + at, reinterpret_cast<char const *>(d_y) + at,
-                                   (size_t)nrows * scalar, cudaMemcpyDeviceToHost, sc.copy_stream));
-      }
-    }
+    drain(chunk_index, begin, nrows, stream_b);
   }
-  if (host_y != nullptr && sc.copy_stream != nullptr) {
-    CUDA_CHECK(cudaEventRecord(sc.copies_done, sc.copy_stream));
-    CUDA_CHECK(cudaStreamWaitEvent(rt.stream, sc.copies_done, 0));
-  }
-  if (pipelined) {
-    // the library stream continues only after stream B has written the last rows of y
-    for (int k = 0; k < 2; ++k)
-      if (chunk_index > k) CUDA_CHECK(cudaStreamWaitEvent(stream_a, sc.slot[k].released, 0));
-  }
+  drain_finish();
   CUDA_CHECK(cudaEventRecord(rt.ev1, rt.stream));
 }
 
@@ -1719,13 +1721,37 @@ void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors, double c
     size_t const n = (size_t)dim * (size_t)num_vectors;
     double *d_x = sc.x.reserve(n);
     double *d_y = sc.y.reserve(n);
-    CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
     // pinned y: finished row chunks drain on a copy stream behind the next chunks' kernels; pageable y (where an
     // "async" copy blocks the host and would stall the launch loop): one copy at the end
     cudaPointerAttributes attr{};
     bool const pinned = cudaPointerGetAttributes(&attr, y) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     (void)cudaGetLastError();
-    matvec_device(op, 0, dim, d_x, d_y, false, num_vectors, dim, dim, pinned ? y : nullptr);
+    // One vector from pinned memory: the upload of x runs on the copy stream under the canonicalise phase (which
+    // does not read x); needs the canonicalised elements of ALL chunks at once (11 B each), so only below 24 GB.
+    OperatorDev &od = operator_dev(op);
+    if (od.stats_index != ix || od.stats_rows != dim) {
+      od.stats_elements = count_elements(od, *ix, 0, dim);
+      od.stats_index = ix;
+      od.stats_rows = dim;
+    }
+    bool const two_phases = pinned && num_vectors == 1 && od.stats_elements > 0 &&
+                            od.stats_elements * 11 <= (int64_t(24) << 30) && getenv("LS_B200_NO_PHASED_E2E") == nullptr;
+    if (two_phases) {
+      MatvecScratch &scr = mv_scratch();
+      if (scr.copy_stream == nullptr) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&scr.copy_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&scr.copies_done, cudaEventDisableTiming));
+      }
+      if (scr.x_uploaded == nullptr) CUDA_CHECK(cudaEventCreateWithFlags(&scr.x_uploaded, cudaEventDisableTiming));
+      CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, scr.copy_stream));
+      CUDA_CHECK(cudaEventRecord(scr.x_uploaded, scr.copy_stream));
+      matvec_device(op, 0, dim, nullptr, nullptr, false, 1, 0, 0, nullptr, 1);
+      CUDA_CHECK(cudaStreamWaitEvent(s, scr.x_uploaded, 0));
+      matvec_device(op, 0, dim, d_x, d_y, false, 1, 0, 0, y, 2);
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+      matvec_device(op, 0, dim, d_x, d_y, false, num_vectors, dim, dim, pinned ? y : nullptr);
+    }
     if (!pinned) CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     ok = matvec_finish();
   });
