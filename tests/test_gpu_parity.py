@@ -439,6 +439,35 @@ def test_phased_matvec_equals_plain(oracle, built, name, monkeypatch):
             assert np.array_equal(d_z.numpy(), d_y.numpy()), (chunk, trial)
 
 
+@pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome24_c2v_inv", "hubbard_2x4", "chain56_hw3"])
+@pytest.mark.parametrize("chunk", [None, "4096"])
+def test_matvec_pinned_host_buffers(oracle, built, name, chunk, monkeypatch):
+    """The reference-facing call with PINNED host buffers takes the overlapped route (x uploads under the
+    canonicalise phase, y drains chunk by chunk): same bits as with pageable buffers."""
+    import ctypes as C
+    from lattice_symmetries_b200 import _lib
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    dim = reps.shape[0]
+    lib = _lib.lib
+    x = np.random.default_rng(31).standard_normal(dim)
+    want = op.apply_to_state_vector(x)
+    if chunk is not None:
+        monkeypatch.setenv("LS_B200_MV_CHUNK", chunk)
+    hx, hy = lib.ls_b200_host_malloc(8 * dim), lib.ls_b200_host_malloc(8 * dim)
+    try:
+        np.frombuffer((C.c_double * dim).from_address(hx), dtype=np.float64)[:] = x
+        mv = lib.ls_hs_internal_get_chpl_kernels().contents.matrix_vector_product
+        for _ in range(2):  # the second call reuses the cached element counts / buffers
+            np.frombuffer((C.c_double * dim).from_address(hy), dtype=np.float64)[:] = np.nan
+            mv(C.byref(op._payload), 1, C.cast(hx, _lib.f64_p), C.cast(hy, _lib.f64_p))
+            _lib.check_error()
+            got = np.frombuffer((C.c_double * dim).from_address(hy), dtype=np.float64).copy()
+            assert np.array_equal(got, want)
+    finally:
+        lib.ls_b200_host_free(hx)
+        lib.ls_b200_host_free(hy)
+
+
 @pytest.mark.parametrize("name", ["chain16_symm", "kagome18_c2", "hubbard_2x4"])
 def test_matvec_device_row_ranges(oracle, built, name):
     """Device-resident entry point on contiguous row shards == host-pointer entry point."""
