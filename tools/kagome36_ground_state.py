@@ -9,16 +9,16 @@ from lattice_symmetries_b200.lanczos import lanczos_ground_state  # noqa: E402
 
 import os  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "kagome36"
-model, desc = bench.make_model(name)
-basis = model.basis()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
 if world > 1:  # torchrun: rows sharded over the ranks, vectors replicated by all-gather
     import torch
     import torch.distributed as dist
     from lattice_symmetries_b200.distributed import build_sharded, init_process
-    init_process(int(os.environ.get("LOCAL_RANK", "0")))
+    init_process(int(os.environ.get("LOCAL_RANK", "0")))  # select this rank's GPU BEFORE the library touches a device
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+model, desc = bench.make_model(name)
+basis = model.basis()
 t0 = time.perf_counter()
 if world > 1:
     build_sharded(basis)
