@@ -23,6 +23,11 @@ void Runtime::ensure() {
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   if (char const *s = getenv("LS_B200_DEVICE")) dev = atoi(s) % count;
+  else if (char const *r = getenv("LOCAL_RANK")) {
+    // torchrun: nothing selected a device yet (still the default 0) -> this rank's own GPU, so that the library
+    // lands on the same device a later torch.cuda.set_device(LOCAL_RANK) picks
+    if (dev == 0 && count > 1) dev = atoi(r) % count;
+  }
   CUDA_CHECK(cudaSetDevice(dev));
   device = dev;
   cudaDeviceProp prop;
