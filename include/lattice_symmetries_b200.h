@@ -360,6 +360,60 @@ int ls_b200_copy_to_host(void *dst_host, void const *src_dev, size_t bytes);
 void *ls_b200_host_malloc(size_t bytes);
 void ls_b200_host_free(void *p);
 
+/* Drops the device-side tables cached for an operator (term tables, phased-product buffers); call before the
+ * ls_hs_operator struct is freed.  Harmless for operators the library has never seen. */
+void ls_b200_operator_release(ls_hs_operator const *op);
+
+/* ---- extensions: several GPUs of one node ------------------------------------------
+ * Replaces the multi-locale half of the Chapel library (chapel/src/StatesEnumeration.chpl:198-212, :537-602;
+ * chapel/src/DistributedMatrixVector.chpl:179-339, :545-579, :775-807, :1060-1088).  One process per GPU; the
+ * library owns its NCCL communicator: rank 0 calls ls_b200_comm_unique_id, the host distributes the 128 bytes by
+ * any means (MPI, torch.distributed, a file), every rank calls ls_b200_comm_init.  From then on
+ *   ls_hs_build_representatives      builds the basis across all ranks; basis->representatives is THIS rank's
+ *                                    block: a contiguous range of the globally sorted list (not a hash class);
+ *   ls_chpl_matrix_vector_product    takes this rank's blocks of x and y (host pointers), like the per-locale
+ *                                    blocks of DistributedMatrixVector.chpl:1066-1073.
+ * Every rank must make the same calls in the same order (they contain collectives). */
+int ls_b200_comm_unique_id(void *out, size_t bytes); /* bytes >= 128 */
+int ls_b200_comm_init(int world, int rank, void const *unique_id);
+void ls_b200_comm_finalize(void);
+int ls_b200_comm_size(void);
+int ls_b200_comm_rank(void);
+/* In-place sum over the ranks of `count` doubles in device memory, ordered on ls_b200_stream() (Lanczos dots). */
+int ls_b200_comm_allreduce_f64(double *values_dev, int count);
+/* The sharded build, explicitly.  balance_for (optional): move the row boundaries so that every rank holds the same
+ * number of matrix elements of that operator.  flags: 1 = no replicated index (all-to-all products only),
+ * 2 = replicate compact keys only ("wide" index) even for small bases, 4 = keep the even row split. */
+int ls_b200_dist_build(ls_hs_basis *basis, ls_hs_operator const *balance_for, int flags);
+/* y_local = (H x)_local with this rank's blocks of x and y in DEVICE memory; asynchronous on ls_b200_stream()
+ * (finish with ls_b200_matvec_sync).  mode 0 = automatic, 1 = all-gather form (x replicated: compact keys of the
+ * whole basis on every rank, pre-scaled vector all-gathered in place, pull-form kernels), 2 = all-to-all form
+ * ((representative, coefficient) records grouped by owner rank, one grouped send/recv exchange per chunk of
+ * columns, the owner ranks locally and adds with fp64 atomics). */
+int ls_b200_dist_matvec(ls_hs_operator const *op, double const *x_local_dev, double *y_local_dev, int mode);
+int ls_b200_dist_matvec_c128(ls_hs_operator const *op, ls_hs_scalar const *x_local_dev, ls_hs_scalar *y_local_dev,
+                             int mode); /* all-gather form only */
+/* out = {world, rank, dim over all ranks, first row, one past the last row of this rank,
+ *        replicated index (0 none, 1 two-level, 2 wide), its search trip count, its prefix bits}; -1 when the basis
+ * is not sharded. */
+int ls_b200_dist_info(ls_hs_basis const *basis, int64_t out[8]);
+/* Row boundaries of all ranks (world + 1 values); returns world, or -1. */
+int ls_b200_dist_bounds(ls_hs_basis const *basis, int64_t *bounds, int capacity);
+/* The same drivers for `world` VIRTUAL ranks on the current device, run in lockstep with device-to-device copies in
+ * place of the NCCL collectives (bases[r] / ops[r] / x_dev[r] / y_dev[r] belong to virtual rank r).  Exercises the
+ * sharded build, both product forms and the wide index on a single GPU. */
+int ls_b200_emu_build(ls_hs_basis **bases, ls_hs_operator const *const *balance_for, int world, int flags);
+int ls_b200_emu_matvec(ls_hs_operator const *const *ops, int world, double const *const *x_dev, double *const *y_dev,
+                       int mode, int complex_vectors);
+/* Host-side planning of the sharded build (pure functions, no device): the block plan of the candidate range, the
+ * all-to-all-v plan that turns block-cyclic pieces into contiguous row ranges, cost-balanced row boundaries. */
+int64_t ls_b200_plan_blocks(uint64_t total, int world, uint64_t *begins, uint64_t *ends, int64_t capacity);
+int64_t ls_b200_plan_redistribution(int world, int me, int64_t number_pieces, int64_t const *lengths,
+                                    int32_t const *owners, int64_t const *bounds, int64_t *scount, int64_t *sdispl,
+                                    int64_t *rcount, int64_t *rdispl, int64_t *places, int64_t capacity);
+int ls_b200_plan_balanced_bounds(int64_t number_blocks, int64_t const *edges, double const *costs, int world,
+                                 int64_t *bounds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -193,6 +193,26 @@ PROTOTYPES = {
     "ls_b200_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "ls_b200_host_malloc": (C.c_void_p, [C.c_size_t]),
     "ls_b200_host_free": (None, [C.c_void_p]),
+    "ls_b200_operator_release": (None, [C.c_void_p]),
+    # several GPUs of one node (dist.cu)
+    "ls_b200_comm_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "ls_b200_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "ls_b200_comm_finalize": (None, []),
+    "ls_b200_comm_size": (C.c_int, []),
+    "ls_b200_comm_rank": (C.c_int, []),
+    "ls_b200_comm_allreduce_f64": (C.c_int, [C.c_void_p, C.c_int]),
+    "ls_b200_dist_build": (C.c_int, [C.POINTER(ls_hs_basis), C.c_void_p, C.c_int]),
+    "ls_b200_dist_matvec": (C.c_int, [C.POINTER(ls_hs_operator), C.c_void_p, C.c_void_p, C.c_int]),
+    "ls_b200_dist_matvec_c128": (C.c_int, [C.POINTER(ls_hs_operator), C.c_void_p, C.c_void_p, C.c_int]),
+    "ls_b200_dist_info": (C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_int64)]),
+    "ls_b200_dist_bounds": (C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_int64), C.c_int]),
+    "ls_b200_emu_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "ls_b200_emu_matvec": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "ls_b200_plan_blocks": (C.c_int64, [C.c_uint64, C.c_int, u64_p, u64_p, C.c_int64]),
+    "ls_b200_plan_redistribution": (
+        C.c_int64, [C.c_int, C.c_int, C.c_int64, i64_p, C.POINTER(C.c_int32), i64_p, i64_p, i64_p, i64_p, i64_p, i64_p,
+                    C.c_int64]),
+    "ls_b200_plan_balanced_bounds": (C.c_int, [C.c_int64, i64_p, f64_p, C.c_int, i64_p]),
 }
 
 

@@ -550,19 +550,11 @@ static FlagsKernel pick_flags_kernel(int np, bool inv, bool filter) {
   return nullptr;
 }
 
-struct BuildResult {
-  uint64_t *d_reps = nullptr;
-  double *d_norms = nullptr;  // nullptr for unprojected bases
-  uint64_t count = 0;
-};
-
 // Build the representatives whose candidate index lies in one of the (ascending, disjoint)
 // ranges; the output is their concatenation, counts[i] the number found in range i.  One call
 // serves a rank's whole block-cyclic share: scratch and output are allocated once.
-using Ranges = std::vector<std::pair<uint64_t, uint64_t>>;
 static bool want_managed_view();
-static BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<uint64_t> *counts = nullptr,
-                                bool host_visible = false) {
+BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<uint64_t> *counts, bool host_visible) {
   Runtime &rt = runtime();
   BasisInfo const info = basis_info(basis);
   LSB_CHECK(info.number_bits <= 64, "bases with more than 64 bits are not supported");
@@ -880,6 +872,30 @@ void ensure_norms(IndexData &ix, GroupData const &g) {
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
 }
 
+uint64_t number_candidates(ls_hs_basis const *basis) { return make_plan(basis, basis_info(basis)).view.total; }
+
+// Installs device-resident representatives (+ norms) as the basis' list; the library takes ownership of both
+// buffers.  basis->representatives.elts (a host pointer in the reference) is served by a managed allocation that
+// doubles as the device array, unless LS_B200_NO_HOST_MIRROR is set (then elts stays NULL: device-only basis).
+void install_representatives(ls_hs_basis *basis, uint64_t *representatives_dev, double *norms_dev, uint64_t count,
+                             int cache_bits) {
+  uint64_t *host = nullptr;
+  bool const mirror = getenv("LS_B200_NO_HOST_MIRROR") == nullptr;
+  if (mirror && count > 0) host = make_host_view(representatives_dev, count);
+  void const *key = host != nullptr ? (void const *)host : (void const *)representatives_dev;
+  built_registry()[key] = BuiltReps{representatives_dev, norms_dev, count};
+  basis->representatives.elts = host;
+  basis->representatives.num_elts = count;
+  basis->representatives.freer = host != nullptr ? reinterpret_cast<void *>(&free_pinned) : nullptr;
+  int const number_bits = (basis->particle_type == LS_HS_SPINFUL_FERMION ? 2 : 1) * basis->number_sites;
+  IndexData *ix = create_index(static_cast<uint64_t const *>(key), (int64_t)count, number_bits, cache_bits);
+  ix->host_reps = host;
+  if (host == nullptr) ix->owns_d_reps = true;  // no host view whose freer would release the device array
+  ix->identity = basis->state_index_is_identity;
+  basis->kernels->state_index_data = ix;
+  basis->kernels->state_index_kernel = &ls_hs_state_index_binary_search_kernel;
+}
+
 }  // namespace lsb
 
 using namespace lsb;
@@ -975,8 +991,19 @@ void ls_hs_build_representatives(ls_hs_basis *basis, uint64_t const lower, uint6
   LSB_CHECK(kernels->enumerate_states != nullptr,
             "enumerate_states kernel is NULL, ls_chpl_init was supposed to initialize it");
   if (basis->representatives.num_elts > 0) return;  // already built
+  if (comm_world() > 1) {
+    // A communicator is active (ls_b200_comm_init): the reference's multi-locale build
+    // (chapel/src/StatesEnumeration.chpl:537-602) -- every rank scans its share of the candidates and keeps a
+    // contiguous range of the sorted representatives; basis->representatives is this rank's block.
+    if (index_of(basis) != nullptr) return;  // (a rank may own zero rows)
+    guarded(__func__, [&] { dist_build_local(basis, nullptr, 0); });
+    return;
+  }
   auto const t0 = std::chrono::steady_clock::now();
   (*kernels->enumerate_states)(basis, lower, upper, &basis->representatives);
+  // A failed enumeration (reported through ls_hs_error) leaves no freer behind: do not wire an index over the
+  // empty array, so that the basis stays "not built" and the call can be retried.
+  if (basis->representatives.freer == nullptr) return;
   auto const t1 = std::chrono::steady_clock::now();
   int const number_bits = (basis->particle_type == LS_HS_SPINFUL_FERMION ? 2 : 1) * basis->number_sites;
   int const default_cache_bits = 22;
@@ -1012,20 +1039,7 @@ int ls_b200_set_representatives_device(ls_hs_basis *basis, uint64_t *representat
   int status = -1;
   LSB_CHECK(basis->representatives.num_elts == 0, "representatives have already been set");
   guarded(__func__, [&] {
-    uint64_t *host = nullptr;
-    bool const mirror = getenv("LS_B200_NO_HOST_MIRROR") == nullptr;
-    if (mirror && count > 0) host = make_host_view(representatives_dev, count);
-    void const *key = host != nullptr ? (void const *)host : (void const *)representatives_dev;
-    built_registry()[key] = BuiltReps{representatives_dev, norms_dev, count};
-    basis->representatives.elts = host;
-    basis->representatives.num_elts = count;
-    basis->representatives.freer = host != nullptr ? reinterpret_cast<void *>(&free_pinned) : nullptr;
-    int const number_bits = (basis->particle_type == LS_HS_SPINFUL_FERMION ? 2 : 1) * basis->number_sites;
-    IndexData *ix = create_index(static_cast<uint64_t const *>(key), (int64_t)count, number_bits, cache_bits);
-    ix->host_reps = host;
-    ix->identity = basis->state_index_is_identity;
-    basis->kernels->state_index_data = ix;
-    basis->kernels->state_index_kernel = &ls_hs_state_index_binary_search_kernel;
+    install_representatives(basis, representatives_dev, norms_dev, count, cache_bits);
     status = 0;
   });
   return status;

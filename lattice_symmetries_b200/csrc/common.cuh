@@ -65,11 +65,27 @@ Runtime &runtime();
 inline void count_launch(int n = 1) { runtime().launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 // Wraps an extern "C" entry point body: serialise, translate failures.
+// The library owns ONE device per process (one rank per GPU); a caller may have another device current on the
+// calling thread (torch.cuda.device(...), a different host thread), so every entry point switches to the
+// library's device for its duration and restores the caller's choice afterwards.
+struct DeviceScope {
+  int previous = -1;
+  explicit DeviceScope(int device) {
+    if (cudaGetDevice(&previous) != cudaSuccess) previous = -1;
+    if (previous != device) cuda_check(cudaSetDevice(device), "cudaSetDevice(rt.device)", __FILE__, __LINE__);
+    else previous = -1;
+  }
+  ~DeviceScope() {
+    if (previous >= 0) cudaSetDevice(previous);
+  }
+};
+
 template <class F>
 inline void guarded(char const *name, F &&f) {
   try {
     std::lock_guard<std::mutex> lock(runtime().mutex);
     runtime().ensure();
+    DeviceScope scope(runtime().device);
     f();
   } catch (CudaFailure const &e) {
     std::string m = std::string(name) + ": " + e.what;

@@ -1,0 +1,910 @@
+// dist.cu -- the two hot paths across the GPUs of one node, INSIDE the library: one process per GPU, one NCCL
+// communicator per process (created here, not borrowed from the host language), every collective ordered on the
+// library stream.
+//
+// Replaces the multi-locale half of the Chapel driver:
+//   hash partition of the states        chapel/src/StatesEnumeration.chpl:198-212, :537-602
+//   per-locale blocks of the product    chapel/src/DistributedMatrixVector.chpl:1060-1088 (matrixVectorProduct)
+//   radix partition + remote buffers    chapel/src/DistributedMatrixVector.chpl:179-339, :545-579, :775-807
+//
+// Design (not a port).  Representatives are distributed by CONTIGUOUS SORTED RANGE, not by hash: rank r owns rows
+// [bounds[r], bounds[r+1]) of the globally sorted list, so a shard is a sorted array with its own local index, the
+// owner of a state is a binary search over world-1 splitters, and x / y are split the same way.
+//   build     candidates are dealt out in blocks (small ones first: representatives crowd into the low indices),
+//             every rank scans its blocks, ONE all-to-all-v moves each piece to the rank that owns its rows.
+//   product   (a) all-gather form, when the replicated structures fit: compact keys (2-4 B per state) + level-1
+//             table of the WHOLE basis on every rank -- not the 8-byte representatives -- and the pre-scaled vector
+//             n_j x_j replicated by an in-place all-gather-v; then the pull-form kernels run on the local rows.
+//             (b) all-to-all form: push records (representative, coefficient) grouped by owner, one grouped
+//             ncclSend/ncclRecv exchange per chunk of columns, the owner ranks locally and adds with fp64 atomics.
+// Every driver below is written against a Team: the ranks this process drives.  A real run drives one rank and the
+// collectives are NCCL calls; the emulated team (tests, one GPU) drives all `world` virtual ranks in lockstep and
+// its collectives are device-to-device copies -- the per-rank phases are the same code either way.
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: libnccl is loaded at run time, the library does not link it
+
+#include <algorithm>
+#include <numeric>
+
+#include "state.hpp"
+
+namespace lsb {
+
+// ---- NCCL, loaded at run time ---------------------------------------------------------------------------------------
+struct NcclApi {
+  void *handle = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+static NcclApi &nccl() {
+  static NcclApi api;
+  if (api.handle != nullptr) return api;
+  char const *names[] = {getenv("LS_B200_NCCL_LIBRARY"), "libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (char const *name : names) {
+    if (name == nullptr || *name == 0) continue;
+    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);  // torch's bundled copy when it is already in the process
+    if (h != nullptr) break;
+  }
+  if (h == nullptr) throw CudaFailure{"libnccl.so.2 not found (set LS_B200_NCCL_LIBRARY): multi-GPU paths need NCCL"};
+  auto load = [&](auto &fn, char const *symbol) {
+    fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(h, symbol));
+    if (fn == nullptr) throw CudaFailure{std::string("libnccl: missing symbol ") + symbol};
+  };
+  load(api.GetUniqueId, "ncclGetUniqueId");
+  load(api.CommInitRank, "ncclCommInitRank");
+  load(api.CommDestroy, "ncclCommDestroy");
+  load(api.AllGather, "ncclAllGather");
+  load(api.AllReduce, "ncclAllReduce");
+  load(api.Broadcast, "ncclBroadcast");
+  load(api.Send, "ncclSend");
+  load(api.Recv, "ncclRecv");
+  load(api.GroupStart, "ncclGroupStart");
+  load(api.GroupEnd, "ncclGroupEnd");
+  load(api.GetErrorString, "ncclGetErrorString");
+  api.handle = h;
+  return api;
+}
+
+static void nccl_check(ncclResult_t r, char const *expr, int line) {
+  if (r != ncclSuccess) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "NCCL error (%s) at dist.cu:%d: %s", nccl().GetErrorString(r), line, expr);
+    throw CudaFailure{buf};
+  }
+}
+#define NCCL_CHECK(expr) ::lsb::nccl_check((expr), #expr, __LINE__)
+
+struct Comm {
+  int world = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+};
+static Comm g_comm;
+
+int comm_world() { return g_comm.comm != nullptr ? g_comm.world : 1; }
+
+DistShard::~DistShard() {
+  cudaFree(d_splitters);
+  cudaFree(d_xs_full);
+  delete global_index;
+  delete push;
+}
+
+// ---- host-side planning (pure functions; exported for the CPU tests) ---------------------------------------------
+constexpr uint64_t kAlign = 32;  // candidate blocks start on a multiple of 32 (one bit-sliced word)
+
+// Blocks of the candidate-index range [0, total), block b scanned by rank b % world.  A representative is the
+// smallest member of its orbit, so representatives -- and the work of finding them -- crowd into the low indices
+// (kagome-36: the first 3 % of the range hold 90 % of them): the plan starts with small blocks and doubles the size
+// every 8 * world blocks, so that every rank gets an equal share of every density regime.
+std::vector<std::pair<uint64_t, uint64_t>> dist_block_plan(uint64_t total, int world) {
+  std::vector<std::pair<uint64_t, uint64_t>> plan;
+  if (total == 0) return plan;
+  uint64_t const min_block = uint64_t(1) << 20;
+  uint64_t max_block = std::max<uint64_t>(min_block, total / ((uint64_t)world * 32));
+  max_block = (max_block + kAlign - 1) / kAlign * kAlign;
+  uint64_t size = min_block;
+  uint64_t lo = 0;
+  int in_generation = 0;
+  while (lo < total) {
+    uint64_t const hi = std::min(total, lo + size);
+    plan.emplace_back(lo, hi);
+    lo = hi;
+    if (++in_generation == 8 * world && size < max_block) {
+      size = std::min(max_block, size * 2);
+      in_generation = 0;
+    }
+  }
+  return plan;
+}
+
+std::vector<int64_t> dist_even_bounds(int64_t dim, int world) {
+  std::vector<int64_t> b((size_t)world + 1);
+  for (int r = 0; r <= world; ++r) b[(size_t)r] = (int64_t)(((__int128)dim * r) / world);
+  return b;
+}
+
+struct Piece {
+  int64_t begin, length;  // global rows [begin, begin + length) of the sorted list
+  int owner;              // the rank that holds it now
+};
+struct RedistPlan {
+  std::vector<int64_t> scount, sdispl, rcount, rdispl;  // [world], in elements
+  struct Place {
+    int64_t src, dst, length;  // receive-buffer offset -> local row
+  };
+  std::vector<Place> places;
+  int64_t total_send = 0, total_recv = 0;
+};
+
+// Pieces (ascending, disjoint, covering [0, dim)) currently held by their owners in piece order; afterwards rank d
+// holds rows [bounds[d], bounds[d+1]).  What rank `me` sends (contiguous per destination: its pieces ascend) and where
+// what it receives goes.
+RedistPlan plan_redistribution(int world, int me, std::vector<Piece> const &pieces, std::vector<int64_t> const &bounds) {
+  RedistPlan p;
+  p.scount.assign((size_t)world, 0);
+  p.sdispl.assign((size_t)world, 0);
+  p.rcount.assign((size_t)world, 0);
+  p.rdispl.assign((size_t)world, 0);
+  int64_t const my_lo = bounds[(size_t)me], my_hi = bounds[(size_t)me + 1];
+  for (Piece const &pc : pieces) {
+    int64_t const lo = pc.begin, hi = pc.begin + pc.length;
+    if (pc.owner == me) {
+      for (int d = 0; d < world; ++d) {
+        int64_t const a = std::max(lo, bounds[(size_t)d]), b = std::min(hi, bounds[(size_t)d + 1]);
+        if (b > a) p.scount[(size_t)d] += b - a;
+      }
+    }
+    int64_t const a = std::max(lo, my_lo), b = std::min(hi, my_hi);
+    if (b > a) p.rcount[(size_t)pc.owner] += b - a;
+  }
+  for (int d = 1; d < world; ++d) {
+    p.sdispl[(size_t)d] = p.sdispl[(size_t)d - 1] + p.scount[(size_t)d - 1];
+    p.rdispl[(size_t)d] = p.rdispl[(size_t)d - 1] + p.rcount[(size_t)d - 1];
+  }
+  p.total_send = p.sdispl[(size_t)world - 1] + p.scount[(size_t)world - 1];
+  p.total_recv = p.rdispl[(size_t)world - 1] + p.rcount[(size_t)world - 1];
+  std::vector<int64_t> running((size_t)world, 0);
+  for (Piece const &pc : pieces) {
+    int64_t const a = std::max(pc.begin, my_lo), b = std::min(pc.begin + pc.length, my_hi);
+    if (b > a) {
+      int64_t &run = running[(size_t)pc.owner];
+      p.places.push_back({p.rdispl[(size_t)pc.owner] + run, a - my_lo, b - a});
+      run += b - a;
+    }
+  }
+  return p;
+}
+
+// Contiguous row ranges of (nearly) equal cost: `edges` are ascending row numbers (edges[0] = 0, edges.back() = dim),
+// costs[b] the cost of rows [edges[b], edges[b+1]).  Rank r ends at the block boundary closest to (r+1)/world of the
+// total (rows of the sorted basis do not cost the same: kagome-36, eight ranks, even split: 0.87x .. 1.12x the mean).
+std::vector<int64_t> dist_balanced_bounds(std::vector<int64_t> const &edges, std::vector<double> const &costs, int world) {
+  int64_t const dim = edges.back();
+  std::vector<int64_t> bounds((size_t)world + 1, dim);
+  bounds[0] = 0;
+  double total = 0;
+  for (double c : costs) total += c;
+  size_t b = 0;
+  double acc = 0;
+  for (int r = 0; r + 1 < world; ++r) {
+    double const target = total * (double)(r + 1) / (double)world;
+    while (b < costs.size() && acc + costs[b] <= target) acc += costs[b++];
+    if (b < costs.size() && target - acc > acc + costs[b] - target) acc += costs[b++];
+    bounds[(size_t)r + 1] = std::max(bounds[(size_t)r], edges[b]);
+  }
+  return bounds;
+}
+
+// ---- the team: the ranks this process drives --------------------------------------------------------------------
+__global__ void add_i64_kernel(int64_t *__restrict__ acc, int64_t const *__restrict__ other, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc[i] += other[i];
+}
+__global__ void add_f64_kernel(double *__restrict__ acc, double const *__restrict__ other, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc[i] += other[i];
+}
+
+struct Team {
+  int world = 1;
+  std::vector<int> members;  // real: {rank}; emulated: 0 .. world-1
+  bool emulated = false;
+
+  size_t size() const { return members.size(); }
+
+  // Every rank contributes k values; every rank receives the world x k table (host).  `mine[m]` belongs to members[m].
+  std::vector<uint64_t> gather_host(std::vector<std::vector<uint64_t>> const &mine, size_t k) const {
+    std::vector<uint64_t> table((size_t)world * k, 0);
+    if (emulated) {
+      for (size_t m = 0; m < members.size(); ++m)
+        std::copy(mine[m].begin(), mine[m].begin() + (ptrdiff_t)k, table.begin() + (ptrdiff_t)((size_t)members[m] * k));
+      return table;
+    }
+    Runtime &rt = runtime();
+    static DeviceBuffer<uint64_t> stage;
+    uint64_t *d = stage.reserve(table.size());
+    CUDA_CHECK(cudaMemcpyAsync(d + (size_t)g_comm.rank * k, mine[0].data(), sizeof(uint64_t) * k, cudaMemcpyHostToDevice,
+                               rt.stream));
+    NCCL_CHECK(nccl().AllGather(d + (size_t)g_comm.rank * k, d, k, ncclUint64, g_comm.comm, rt.stream));
+    CUDA_CHECK(cudaMemcpyAsync(table.data(), d, sizeof(uint64_t) * table.size(), cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    return table;
+  }
+
+  // The same for values that live on the device (k per rank).
+  std::vector<uint64_t> gather_device(std::vector<unsigned long long const *> const &mine, size_t k) const {
+    Runtime &rt = runtime();
+    std::vector<uint64_t> table((size_t)world * k, 0);
+    if (emulated) {
+      for (size_t m = 0; m < members.size(); ++m)
+        CUDA_CHECK(cudaMemcpyAsync(table.data() + (size_t)members[m] * k, mine[m], sizeof(uint64_t) * k,
+                                   cudaMemcpyDeviceToHost, rt.stream));
+      CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+      return table;
+    }
+    static DeviceBuffer<uint64_t> stage;
+    uint64_t *d = stage.reserve(table.size());
+    NCCL_CHECK(nccl().AllGather(mine[0], d, k, ncclUint64, g_comm.comm, rt.stream));
+    CUDA_CHECK(cudaMemcpyAsync(table.data(), d, sizeof(uint64_t) * table.size(), cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    return table;
+  }
+
+  // Personalised exchange; counts and displacements in bytes, [member][peer].
+  void all_to_all_v(std::vector<unsigned char const *> const &send, std::vector<std::vector<size_t>> const &sdispl,
+                    std::vector<std::vector<size_t>> const &scount, std::vector<unsigned char *> const &recv,
+                    std::vector<std::vector<size_t>> const &rdispl, std::vector<std::vector<size_t>> const &rcount) const {
+    Runtime &rt = runtime();
+    if (emulated) {
+      for (size_t dst = 0; dst < members.size(); ++dst)
+        for (size_t src = 0; src < members.size(); ++src) {
+          size_t const n = scount[src][dst];
+          LSB_CHECK(n == rcount[dst][src], "all_to_all_v: send / receive counts disagree");
+          if (n > 0)
+            CUDA_CHECK(cudaMemcpyAsync(recv[dst] + rdispl[dst][src], send[src] + sdispl[src][dst], n,
+                                       cudaMemcpyDeviceToDevice, rt.stream));
+        }
+      return;
+    }
+    int const me = g_comm.rank;
+    if (scount[0][(size_t)me] > 0)
+      CUDA_CHECK(cudaMemcpyAsync(recv[0] + rdispl[0][(size_t)me], send[0] + sdispl[0][(size_t)me], scount[0][(size_t)me],
+                                 cudaMemcpyDeviceToDevice, rt.stream));
+    NCCL_CHECK(nccl().GroupStart());
+    for (int p = 0; p < world; ++p) {
+      if (p == me) continue;
+      if (scount[0][(size_t)p] > 0)
+        NCCL_CHECK(nccl().Send(send[0] + sdispl[0][(size_t)p], scount[0][(size_t)p], ncclChar, p, g_comm.comm, rt.stream));
+      if (rcount[0][(size_t)p] > 0)
+        NCCL_CHECK(nccl().Recv(recv[0] + rdispl[0][(size_t)p], rcount[0][(size_t)p], ncclChar, p, g_comm.comm, rt.stream));
+    }
+    NCCL_CHECK(nccl().GroupEnd());
+  }
+
+  // In place: segment r = bytes [displs[r], displs[r+1]) of every buffer is valid on rank r; afterwards everywhere.
+  void all_gather_v(std::vector<unsigned char *> const &buf, std::vector<size_t> const &displs) const {
+    Runtime &rt = runtime();
+    if (emulated) {
+      for (size_t dst = 0; dst < members.size(); ++dst)
+        for (size_t src = 0; src < members.size(); ++src) {
+          size_t const r = (size_t)members[src];
+          size_t const n = displs[r + 1] - displs[r];
+          if (dst != src && n > 0)
+            CUDA_CHECK(cudaMemcpyAsync(buf[dst] + displs[r], buf[src] + displs[r], n, cudaMemcpyDeviceToDevice, rt.stream));
+        }
+      return;
+    }
+    NCCL_CHECK(nccl().GroupStart());
+    for (int root = 0; root < world; ++root) {
+      size_t const n = displs[(size_t)root + 1] - displs[(size_t)root];
+      if (n > 0)
+        NCCL_CHECK(nccl().Broadcast(buf[0] + displs[(size_t)root], buf[0] + displs[(size_t)root], n, ncclChar, root,
+                                    g_comm.comm, rt.stream));
+    }
+    NCCL_CHECK(nccl().GroupEnd());
+  }
+
+  void all_reduce_sum_i64(std::vector<int64_t *> const &buf, int64_t n) const {
+    Runtime &rt = runtime();
+    if (n <= 0) return;
+    if (!emulated) {
+      NCCL_CHECK(nccl().AllReduce(buf[0], buf[0], (size_t)n, ncclInt64, ncclSum, g_comm.comm, rt.stream));
+      return;
+    }
+    unsigned const blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 8);
+    for (size_t m = 1; m < members.size(); ++m) {
+      add_i64_kernel<<<blocks, 256, 0, rt.stream>>>(buf[0], buf[m], n);
+      count_launch();
+    }
+    for (size_t m = 1; m < members.size(); ++m)
+      CUDA_CHECK(cudaMemcpyAsync(buf[m], buf[0], sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToDevice, rt.stream));
+  }
+
+  void all_reduce_sum_f64(std::vector<double *> const &buf, int64_t n) const {
+    Runtime &rt = runtime();
+    if (n <= 0) return;
+    if (!emulated) {
+      NCCL_CHECK(nccl().AllReduce(buf[0], buf[0], (size_t)n, ncclFloat64, ncclSum, g_comm.comm, rt.stream));
+      return;
+    }
+    unsigned const blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 8);
+    for (size_t m = 1; m < members.size(); ++m) {
+      add_f64_kernel<<<blocks, 256, 0, rt.stream>>>(buf[0], buf[m], n);
+      count_launch();
+    }
+    for (size_t m = 1; m < members.size(); ++m)
+      CUDA_CHECK(cudaMemcpyAsync(buf[m], buf[0], sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, rt.stream));
+  }
+};
+
+static Team real_team() {
+  Team t;
+  t.world = comm_world();
+  t.members = {g_comm.comm != nullptr ? g_comm.rank : 0};
+  t.emulated = g_comm.comm == nullptr;  // a single rank without a communicator: its collectives are no-ops
+  return t;
+}
+static Team emulated_team(int world) {
+  Team t;
+  t.world = world;
+  t.members.resize((size_t)world);
+  std::iota(t.members.begin(), t.members.end(), 0);
+  t.emulated = true;
+  return t;
+}
+
+// ---- redistribution of sorted pieces into contiguous row ranges --------------------------------------------------
+// data[m]: the pieces owned by member m, concatenated (device); replaced by its new rows (a fresh allocation).
+static void redistribute(Team const &team, std::vector<Piece> const &pieces, std::vector<int64_t> const &bounds,
+                         std::vector<void *> &data, size_t elem) {
+  Runtime &rt = runtime();
+  size_t const M = team.size();
+  std::vector<RedistPlan> plans;
+  std::vector<unsigned char const *> send(M);
+  std::vector<unsigned char *> recv(M), fresh(M);
+  std::vector<std::vector<size_t>> sd(M), sc(M), rd(M), rc(M);
+  for (size_t m = 0; m < M; ++m) {
+    plans.push_back(plan_redistribution(team.world, team.members[m], pieces, bounds));
+    RedistPlan const &p = plans.back();
+    auto bytes = [&](std::vector<int64_t> const &v) {
+      std::vector<size_t> out(v.size());
+      for (size_t i = 0; i < v.size(); ++i) out[i] = (size_t)v[i] * elem;
+      return out;
+    };
+    sd[m] = bytes(p.sdispl);
+    sc[m] = bytes(p.scount);
+    rd[m] = bytes(p.rdispl);
+    rc[m] = bytes(p.rcount);
+    send[m] = static_cast<unsigned char const *>(data[m]);
+    void *r = nullptr, *f = nullptr;
+    CUDA_CHECK(cudaMalloc(&r, std::max<size_t>((size_t)p.total_recv * elem, 8)));
+    CUDA_CHECK(cudaMalloc(&f, std::max<size_t>((size_t)p.total_recv * elem, 8)));
+    recv[m] = static_cast<unsigned char *>(r);
+    fresh[m] = static_cast<unsigned char *>(f);
+  }
+  team.all_to_all_v(send, sd, sc, recv, rd, rc);
+  for (size_t m = 0; m < M; ++m)
+    for (auto const &pl : plans[m].places)
+      CUDA_CHECK(cudaMemcpyAsync(fresh[m] + (size_t)pl.dst * elem, recv[m] + (size_t)pl.src * elem, (size_t)pl.length * elem,
+                                 cudaMemcpyDeviceToDevice, rt.stream));
+  CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+  for (size_t m = 0; m < M; ++m) {
+    cudaFree(recv[m]);
+    cudaFree(data[m]);
+    data[m] = fresh[m];
+  }
+}
+
+// ---- distributed build ----------------------------------------------------------------------------------------------
+enum : int { kDistNoGlobalIndex = 1, kDistWideIndex = 2, kDistNoBalance = 4 };
+
+static DistShard *shard_of(ls_hs_basis const *basis) {
+  IndexData *ix = index_of(basis);
+  return ix != nullptr ? ix->dist : nullptr;
+}
+
+// Replicated state -> global row structure.  Small bases (< 2^32 states and a few GB): the representatives themselves
+// are all-gathered and the ordinary two-level index is built over them -- identical lookups to the single-GPU path.
+// Otherwise ("wide"): only the compact keys are replicated and level 1 is the SUM over ranks of the local
+// lower-bound tables (the number of states below a prefix is additive over shards).
+static void build_global_index(Team const &team, std::vector<ls_hs_basis *> const &bases, int flags) {
+  Runtime &rt = runtime();
+  size_t const M = team.size();
+  DistShard &first = *shard_of(bases[0]);
+  int64_t const dim = first.dim;
+  int const number_bits = index_of(bases[0])->number_bits;
+  if (dim == 0 || number_bits == 0 || index_of(bases[0])->identity) return;
+  bool wide = (flags & kDistWideIndex) != 0 || dim >= (int64_t(1) << 32) || (size_t)dim * 8 > (size_t(8) << 30);
+  if (char const *env = getenv("LS_B200_DIST_INDEX")) wide = strcmp(env, "wide") == 0 ? true : (dim < (int64_t(1) << 32) ? false : wide);
+  std::vector<size_t> row_displs((size_t)team.world + 1);
+  if (!wide) {
+    std::vector<unsigned char *> full(M);
+    for (size_t r = 0; r <= (size_t)team.world; ++r) row_displs[r] = (size_t)first.bounds[r] * 8;
+    for (size_t m = 0; m < M; ++m) {
+      IndexData *local = index_of(bases[m]);
+      DistShard &sh = *local->dist;
+      void *p = nullptr;
+      CUDA_CHECK(cudaMalloc(&p, (size_t)dim * 8));
+      full[m] = static_cast<unsigned char *>(p);
+      if (local->number_states > 0)
+        CUDA_CHECK(cudaMemcpyAsync(full[m] + row_displs[(size_t)sh.rank], local->d_reps, (size_t)local->number_states * 8,
+                                   cudaMemcpyDeviceToDevice, rt.stream));
+    }
+    team.all_gather_v(full, row_displs);
+    for (size_t m = 0; m < M; ++m)
+      index_of(bases[m])->dist->global_index =
+          create_index_from_device(reinterpret_cast<uint64_t *>(full[m]), dim, number_bits, 22);
+    return;
+  }
+  int const prefix_bits = index_choose_prefix_bits(dim, number_bits);
+  int const shift = number_bits - prefix_bits;
+  if (shift > 32) return;  // no compact keys: only the all-to-all form is available
+  int const key_bytes = shift <= 16 ? 2 : 4;
+  int64_t const number_offsets = (int64_t(1) << prefix_bits) + 1;
+  std::vector<unsigned char *> keys(M);
+  std::vector<int64_t *> offsets(M);
+  for (size_t r = 0; r <= (size_t)team.world; ++r) row_displs[r] = (size_t)first.bounds[r] * (size_t)key_bytes;
+  for (size_t m = 0; m < M; ++m) {
+    IndexData *local = index_of(bases[m]);
+    DistShard &sh = *local->dist;
+    void *k = nullptr;
+    CUDA_CHECK(cudaMalloc(&k, (size_t)dim * (size_t)key_bytes));
+    keys[m] = static_cast<unsigned char *>(k);
+    CUDA_CHECK(cudaMalloc(&offsets[m], sizeof(int64_t) * (size_t)number_offsets));
+    index_local_keys(local->d_reps, local->number_states, shift, keys[m] + row_displs[(size_t)sh.rank], key_bytes);
+    index_local_offsets64(local->d_reps, local->number_states, shift, number_offsets, offsets[m]);
+  }
+  team.all_gather_v(keys, row_displs);
+  team.all_reduce_sum_i64(offsets, number_offsets);
+  for (size_t m = 0; m < M; ++m) {
+    auto *g = new IndexData();
+    g->number_states = dim;
+    g->number_bits = number_bits;
+    g->prefix_bits = prefix_bits;
+    g->shift = shift;
+    g->d_reps = nullptr;
+    g->owns_d_reps = false;
+    g->d_offsets64 = offsets[m];
+    if (key_bytes == 2) g->d_lows16 = reinterpret_cast<uint16_t *>(keys[m]);
+    else g->d_lows32 = reinterpret_cast<uint32_t *>(keys[m]);
+    g->steps = index_steps_from_offsets64(offsets[m], number_offsets - 1);
+    index_of(bases[m])->dist->global_index = g;
+  }
+}
+
+static void dist_build(Team const &team, std::vector<ls_hs_basis *> const &bases,
+                       std::vector<ls_hs_operator const *> const &balance_for, int flags) {
+  Runtime &rt = runtime();
+  size_t const M = team.size();
+  int const P = team.world;
+  for (ls_hs_basis *b : bases) LSB_CHECK(b->representatives.num_elts == 0 && index_of(b) == nullptr, "basis is already built");
+  bool const with_norms = basis_info(bases[0]).has_permutation_symmetries;
+
+  // 1. every rank scans its blocks of the candidate range
+  uint64_t const total = number_candidates(bases[0]);
+  auto const plan = dist_block_plan(total, P);
+  size_t const nb = plan.size();
+  size_t const per_rank = std::max<size_t>(1, (nb + (size_t)P - 1) / (size_t)P);
+  std::vector<std::vector<uint64_t>> counts(M);
+  std::vector<void *> reps(M, nullptr), norms(M, nullptr);
+  double kernel_ms = 0;
+  for (size_t m = 0; m < M; ++m) {
+    Ranges mine;
+    for (size_t b = (size_t)team.members[m]; b < nb; b += (size_t)P) mine.push_back(plan[b]);
+    BuildResult r = build_ranges(bases[m], mine, &counts[m]);
+    kernel_ms = std::max(kernel_ms, rt.last_build_ms);
+    counts[m].resize(per_rank, 0);
+    reps[m] = r.d_reps;
+    norms[m] = r.d_norms;
+  }
+  // 2. everybody learns every block's size; the pieces in block order are the sorted list
+  std::vector<uint64_t> const table = team.gather_host(counts, per_rank);
+  std::vector<Piece> pieces;
+  int64_t dim = 0;
+  for (size_t b = 0; b < nb; ++b) {
+    int64_t const n = (int64_t)table[(b % (size_t)P) * per_rank + b / (size_t)P];
+    pieces.push_back({dim, n, (int)(b % (size_t)P)});
+    dim += n;
+  }
+  // 3. one all-to-all-v per array: every piece travels to the rank that owns its rows
+  std::vector<int64_t> bounds = dist_even_bounds(dim, P);
+  redistribute(team, pieces, bounds, reps, 8);
+  if (with_norms) redistribute(team, pieces, bounds, norms, 8);
+  // 4. optional: move the boundaries so that every rank holds the same number of matrix elements of `balance_for`
+  bool const balance = !balance_for.empty() && balance_for[0] != nullptr && (flags & kDistNoBalance) == 0 && P > 1 &&
+                       dim >= 4096 * (int64_t)P;
+  if (balance) {
+    size_t const fine = 64;
+    std::vector<std::vector<uint64_t>> mine(M, std::vector<uint64_t>(fine, 0));
+    for (size_t m = 0; m < M; ++m) {
+      int const r = team.members[m];
+      int64_t const n = bounds[(size_t)r + 1] - bounds[(size_t)r];
+      OperatorDev &od = operator_dev(balance_for[m]);
+      for (size_t k = 0; k < fine; ++k) {
+        int64_t const a = (int64_t)(((__int128)n * (int64_t)k) / (int64_t)fine), b = (int64_t)(((__int128)n * (int64_t)(k + 1)) / (int64_t)fine);
+        // 4 row-proportional units (alpha, norm, x, y traffic and the term scan) per row on top of its elements
+        mine[m][k] = b > a ? (uint64_t)(count_elements(od, static_cast<uint64_t const *>(reps[m]), a, b) + 4 * (b - a)) : 0;
+      }
+    }
+    std::vector<uint64_t> const all = team.gather_host(mine, fine);
+    std::vector<int64_t> edges{0};
+    std::vector<double> costs;
+    for (int r = 0; r < P; ++r) {
+      int64_t const n = bounds[(size_t)r + 1] - bounds[(size_t)r];
+      for (size_t k = 0; k < fine; ++k) {
+        int64_t const b = bounds[(size_t)r] + (int64_t)(((__int128)n * (int64_t)(k + 1)) / (int64_t)fine);
+        if (b > edges.back()) {
+          edges.push_back(b);
+          costs.push_back((double)all[(size_t)r * fine + k]);
+        } else if (!costs.empty()) {
+          costs.back() += (double)all[(size_t)r * fine + k];
+        }
+      }
+    }
+    std::vector<int64_t> const balanced = dist_balanced_bounds(edges, costs, P);
+    if (balanced != bounds) {
+      std::vector<Piece> held;
+      for (int r = 0; r < P; ++r) held.push_back({bounds[(size_t)r], bounds[(size_t)r + 1] - bounds[(size_t)r], r});
+      redistribute(team, held, balanced, reps, 8);
+      if (with_norms) redistribute(team, held, balanced, norms, 8);
+      bounds = balanced;
+    }
+  }
+  // 5. the local rows become the basis' representatives (host view, local index), tagged with the shard layout
+  std::vector<std::vector<uint64_t>> firsts(M, std::vector<uint64_t>(1, ~uint64_t(0)));
+  for (size_t m = 0; m < M; ++m) {
+    int const r = team.members[m];
+    int64_t const n = bounds[(size_t)r + 1] - bounds[(size_t)r];
+    if (n > 0)
+      CUDA_CHECK(cudaMemcpyAsync(firsts[m].data(), reps[m], 8, cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    install_representatives(bases[m], static_cast<uint64_t *>(reps[m]), with_norms ? static_cast<double *>(norms[m]) : nullptr,
+                            (uint64_t)n, 22);
+    IndexData *local = index_of(bases[m]);
+    auto *sh = new DistShard();
+    sh->world = P;
+    sh->rank = r;
+    sh->dim = dim;
+    sh->bounds = bounds;
+    local->dist = sh;
+  }
+  std::vector<uint64_t> const splitters = team.gather_host(firsts, 1);
+  for (size_t m = 0; m < M; ++m) {
+    DistShard &sh = *index_of(bases[m])->dist;
+    sh.splitters = splitters;
+    // an empty rank owns nothing: give it the splitter of the next non-empty rank so that the owner search skips it
+    for (int r = P - 2; r >= 0; --r)
+      if (bounds[(size_t)r + 1] == bounds[(size_t)r]) sh.splitters[(size_t)r] = sh.splitters[(size_t)r + 1];
+    CUDA_CHECK(cudaMalloc(&sh.d_splitters, sizeof(uint64_t) * (size_t)P));
+    CUDA_CHECK(cudaMemcpy(sh.d_splitters, sh.splitters.data(), sizeof(uint64_t) * (size_t)P, cudaMemcpyHostToDevice));
+    sh.push = new PushBuffers();
+  }
+  // 6. replicated lookup structure of the all-gather products
+  if ((flags & kDistNoGlobalIndex) == 0) build_global_index(team, bases, flags);
+  CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+  rt.last_build_ms = kernel_ms;
+}
+
+// ---- distributed products ---------------------------------------------------------------------------------------------
+enum : int { kProductAuto = 0, kProductAllGather = 1, kProductAllToAll = 2 };
+
+static void dist_matvec(Team const &team, std::vector<ls_hs_operator const *> const &ops,
+                        std::vector<double const *> const &x, std::vector<double *> const &y, int mode,
+                        bool complex_vectors) {
+  Runtime &rt = runtime();
+  size_t const M = team.size();
+  std::vector<IndexData *> local(M);
+  for (size_t m = 0; m < M; ++m) {
+    local[m] = index_of(ops[m]->basis);
+    LSB_CHECK(local[m] != nullptr && local[m]->dist != nullptr, "the basis was not built by the distributed build");
+  }
+  DistShard const &first = *local[0]->dist;
+  if (first.dim == 0) return;
+  bool const identity = local[0]->identity;
+  bool const have_global = first.global_index != nullptr;
+  if (mode == kProductAuto) {
+    mode = have_global ? kProductAllGather : kProductAllToAll;
+    if (char const *env = getenv("LS_B200_DIST_MATVEC")) {
+      if (strcmp(env, "alltoall") == 0) mode = kProductAllToAll;
+      if (strcmp(env, "allgather") == 0 && have_global) mode = kProductAllGather;
+    }
+  }
+  LSB_CHECK(!identity, "bases whose index is the identity are not distributed");
+  if (mode == kProductAllGather) {
+    LSB_CHECK(have_global, "all-gather products need the replicated index (built without it)");
+    size_t const scalar = complex_vectors ? 2 : 1;
+    std::vector<unsigned char *> full(M);
+    std::vector<size_t> displs((size_t)team.world + 1);
+    for (size_t r = 0; r <= (size_t)team.world; ++r) displs[r] = (size_t)first.bounds[r] * 8 * scalar;
+    for (size_t m = 0; m < M; ++m) {
+      DistShard &sh = *local[m]->dist;
+      size_t const words = (size_t)sh.dim * scalar;
+      if (sh.xs_full_words < words) {
+        cudaFree(sh.d_xs_full);
+        sh.d_xs_full = nullptr;
+        CUDA_CHECK(cudaMalloc(&sh.d_xs_full, sizeof(double) * words));
+        sh.xs_full_words = words;
+      }
+      full[m] = reinterpret_cast<unsigned char *>(sh.d_xs_full);
+      // n_j x_j of the local rows, straight into their slot of the replicated vector
+      launch_prescale(local[m]->number_states, complex_vectors, local[m]->d_norms, x[m],
+                      sh.d_xs_full + (size_t)sh.bounds[(size_t)sh.rank] * scalar);
+    }
+    team.all_gather_v(full, displs);
+    for (size_t m = 0; m < M; ++m) {
+      DistShard &sh = *local[m]->dist;
+      MvTarget t{};
+      t.index = sh.global_index->view();
+      t.rows = local[m]->d_reps;
+      t.norms = local[m]->d_norms;
+      t.number_rows = local[m]->number_states;
+      t.xs = sh.d_xs_full;
+      if (t.number_rows > 0)
+        matvec_device(ops[m], 0, t.number_rows, x[m], y[m], complex_vectors, 1, 0, 0, nullptr, 0, &t);
+    }
+    return;
+  }
+  LSB_CHECK(!complex_vectors, "all-to-all products take real vectors (as the reference's matvec)");
+  LSB_CHECK(team.world <= 64, "at most 64 ranks");
+  int64_t const chunk_rows = push_chunk_rows(ops[0], 0);
+  int64_t rounds = 0;
+  for (int r = 0; r < team.world; ++r)
+    rounds = std::max(rounds, (first.bounds[(size_t)r + 1] - first.bounds[(size_t)r] + chunk_rows - 1) / chunk_rows);
+  for (size_t m = 0; m < M; ++m) push_begin(ops[m], *local[m], x[m], y[m]);
+  size_t const P = (size_t)team.world;
+  for (int64_t c = 0; c < rounds; ++c) {
+    std::vector<unsigned long long const *> displs(M);
+    for (size_t m = 0; m < M; ++m) {
+      int64_t const begin = c * chunk_rows;
+      int64_t const nrows = std::max<int64_t>(0, std::min(chunk_rows, local[m]->number_states - begin));
+      push_produce(ops[m], *local[m], *local[m]->dist, begin, nrows, x[m]);
+      displs[m] = local[m]->dist->push->displs.ptr;
+    }
+    std::vector<uint64_t> const table = team.gather_device(displs, P + 1);  // [rank][owner] record displacements
+    std::vector<unsigned char const *> send(M);
+    std::vector<unsigned char *> recv(M);
+    std::vector<std::vector<size_t>> sd(M, std::vector<size_t>(P)), sc(M, std::vector<size_t>(P)),
+        rd(M, std::vector<size_t>(P)), rc(M, std::vector<size_t>(P));
+    std::vector<size_t> received(M, 0);
+    for (size_t m = 0; m < M; ++m) {
+      size_t const r = (size_t)team.members[m];
+      size_t at = 0;
+      for (size_t p = 0; p < P; ++p) {
+        sd[m][p] = (size_t)table[r * (P + 1) + p] * sizeof(PushRecord);
+        sc[m][p] = (size_t)(table[r * (P + 1) + p + 1] - table[r * (P + 1) + p]) * sizeof(PushRecord);
+        rc[m][p] = (size_t)(table[p * (P + 1) + r + 1] - table[p * (P + 1) + r]) * sizeof(PushRecord);
+        rd[m][p] = at;
+        at += rc[m][p];
+      }
+      received[m] = at / sizeof(PushRecord);
+      PushBuffers &pb = *local[m]->dist->push;
+      send[m] = reinterpret_cast<unsigned char const *>(pb.send.ptr);
+      recv[m] = reinterpret_cast<unsigned char *>(pb.recv.reserve(received[m] + 1));
+    }
+    team.all_to_all_v(send, sd, sc, recv, rd, rc);
+    for (size_t m = 0; m < M; ++m)
+      push_consume(ops[m], *local[m], local[m]->dist->push->recv.ptr, (int64_t)received[m], y[m]);
+  }
+  (void)rt;
+}
+
+// Entry points for the rest of the library: the product of a basis that carries a shard layout.
+bool dist_is_sharded(ls_hs_basis const *basis) { return shard_of(basis) != nullptr; }
+
+void dist_matvec_local(ls_hs_operator const *op, double const *d_x, double *d_y, int mode, bool complex_vectors) {
+  DistShard *sh = shard_of(op->basis);
+  LSB_CHECK(sh != nullptr, "not a distributed basis");
+  LSB_CHECK(sh->world == comm_world(), "the basis was sharded over a different communicator");
+  Team const team = real_team();
+  dist_matvec(team, {op}, {d_x}, {d_y}, mode, complex_vectors);
+}
+
+void dist_build_local(ls_hs_basis *basis, ls_hs_operator const *balance_for, int flags) {
+  Team const team = real_team();
+  dist_build(team, {basis}, {balance_for}, flags);
+}
+
+}  // namespace lsb
+
+using namespace lsb;
+
+extern "C" {
+
+int ls_b200_comm_unique_id(void *out, size_t bytes) {
+  int status = -1;
+  guarded(__func__, [&] {
+    LSB_CHECK(out != nullptr && bytes >= sizeof(ncclUniqueId), "ls_b200_comm_unique_id: need a 128-byte buffer");
+    ncclUniqueId id;
+    NCCL_CHECK(nccl().GetUniqueId(&id));
+    memcpy(out, &id, sizeof id);
+    status = 0;
+  });
+  return status;
+}
+
+int ls_b200_comm_init(int world, int rank, void const *unique_id) {
+  int status = -1;
+  guarded(__func__, [&] {
+    LSB_CHECK(world >= 1 && rank >= 0 && rank < world, "ls_b200_comm_init: invalid world / rank");
+    if (g_comm.comm != nullptr) {
+      LSB_CHECK(g_comm.world == world && g_comm.rank == rank, "a different communicator is already active");
+      status = 0;
+      return;
+    }
+    if (world == 1) {  // nothing to talk to
+      status = 0;
+      return;
+    }
+    LSB_CHECK(unique_id != nullptr, "ls_b200_comm_init: unique id missing");
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    ncclComm_t comm = nullptr;
+    NCCL_CHECK(nccl().CommInitRank(&comm, world, id, rank));
+    g_comm.comm = comm;
+    g_comm.world = world;
+    g_comm.rank = rank;
+    status = 0;
+  });
+  return status;
+}
+
+void ls_b200_comm_finalize(void) {
+  if (g_comm.comm == nullptr) return;
+  std::lock_guard<std::mutex> lock(runtime().mutex);
+  cudaStreamSynchronize(runtime().stream);
+  nccl().CommDestroy(g_comm.comm);
+  g_comm = Comm{};
+}
+
+int ls_b200_comm_size(void) { return comm_world(); }
+int ls_b200_comm_rank(void) { return g_comm.comm != nullptr ? g_comm.rank : 0; }
+
+int ls_b200_comm_allreduce_f64(double *values_dev, int count) {
+  int status = -1;
+  guarded(__func__, [&] {
+    if (g_comm.comm != nullptr && count > 0)
+      NCCL_CHECK(nccl().AllReduce(values_dev, values_dev, (size_t)count, ncclFloat64, ncclSum, g_comm.comm, runtime().stream));
+    status = 0;
+  });
+  return status;
+}
+
+int ls_b200_dist_build(ls_hs_basis *basis, ls_hs_operator const *balance_for, int flags) {
+  int status = -1;
+  guarded(__func__, [&] {
+    dist_build_local(basis, balance_for, flags);
+    status = 0;
+  });
+  return status;
+}
+
+int ls_b200_dist_matvec(ls_hs_operator const *op, double const *x_local_dev, double *y_local_dev, int mode) {
+  int status = -1;
+  guarded(__func__, [&] {
+    dist_matvec_local(op, x_local_dev, y_local_dev, mode, false);
+    status = 0;
+  });
+  return status;
+}
+
+int ls_b200_dist_matvec_c128(ls_hs_operator const *op, ls_hs_scalar const *x_local_dev, ls_hs_scalar *y_local_dev,
+                             int mode) {
+  int status = -1;
+  guarded(__func__, [&] {
+    dist_matvec_local(op, reinterpret_cast<double const *>(x_local_dev), reinterpret_cast<double *>(y_local_dev), mode, true);
+    status = 0;
+  });
+  return status;
+}
+
+int ls_b200_dist_info(ls_hs_basis const *basis, int64_t out[8]) {
+  DistShard const *sh = shard_of(basis);
+  if (sh == nullptr || out == nullptr) return -1;
+  out[0] = sh->world;
+  out[1] = sh->rank;
+  out[2] = sh->dim;
+  out[3] = sh->bounds[(size_t)sh->rank];
+  out[4] = sh->bounds[(size_t)sh->rank + 1];
+  out[5] = sh->global_index == nullptr ? 0 : (sh->global_index->d_offsets64 != nullptr ? 2 : 1);
+  out[6] = sh->global_index != nullptr ? sh->global_index->steps : 0;
+  out[7] = sh->global_index != nullptr ? sh->global_index->prefix_bits : 0;
+  return 0;
+}
+
+int ls_b200_dist_bounds(ls_hs_basis const *basis, int64_t *bounds, int capacity) {
+  DistShard const *sh = shard_of(basis);
+  if (sh == nullptr || bounds == nullptr || capacity < sh->world + 1) return -1;
+  for (int r = 0; r <= sh->world; ++r) bounds[r] = sh->bounds[(size_t)r];
+  return sh->world;
+}
+
+// ---- emulated team: `world` virtual ranks on the current device, driven in lockstep (tests; also a way to run a
+// basis through the sharded code paths on one GPU) --------------------------------------------------------------------
+int ls_b200_emu_build(ls_hs_basis **bases, ls_hs_operator const *const *balance_for, int world, int flags) {
+  int status = -1;
+  guarded(__func__, [&] {
+    LSB_CHECK(world >= 1 && bases != nullptr, "ls_b200_emu_build: invalid arguments");
+    std::vector<ls_hs_basis *> b(bases, bases + world);
+    std::vector<ls_hs_operator const *> ops;
+    if (balance_for != nullptr) ops.assign(balance_for, balance_for + world);
+    dist_build(emulated_team(world), b, ops, flags);
+    status = 0;
+  });
+  return status;
+}
+
+int ls_b200_emu_matvec(ls_hs_operator const *const *ops, int world, double const *const *x_dev, double *const *y_dev,
+                       int mode, int complex_vectors) {
+  int status = -1;
+  guarded(__func__, [&] {
+    LSB_CHECK(world >= 1 && ops != nullptr, "ls_b200_emu_matvec: invalid arguments");
+    std::vector<ls_hs_operator const *> o(ops, ops + world);
+    std::vector<double const *> x(x_dev, x_dev + world);
+    std::vector<double *> y(y_dev, y_dev + world);
+    dist_matvec(emulated_team(world), o, x, y, mode, complex_vectors != 0);
+    status = 0;
+  });
+  return status;
+}
+
+// ---- planning functions, exported for the CPU tests (no device needed) --------------------------------------------
+int64_t ls_b200_plan_blocks(uint64_t total, int world, uint64_t *begins, uint64_t *ends, int64_t capacity) {
+  auto const plan = dist_block_plan(total, world);
+  if (begins != nullptr && ends != nullptr)
+    for (size_t b = 0; b < plan.size() && (int64_t)b < capacity; ++b) {
+      begins[b] = plan[b].first;
+      ends[b] = plan[b].second;
+    }
+  return (int64_t)plan.size();
+}
+
+// pieces: lengths[i] rows held by owners[i], ascending global order.  Outputs: send / receive counts and displacements
+// [world] (elements), places[3 k] = (receive offset, local row, length); returns the number of places (or -1 when
+// `capacity` places do not suffice).
+int64_t ls_b200_plan_redistribution(int world, int me, int64_t number_pieces, int64_t const *lengths, int32_t const *owners,
+                                    int64_t const *bounds, int64_t *scount, int64_t *sdispl, int64_t *rcount,
+                                    int64_t *rdispl, int64_t *places, int64_t capacity) {
+  std::vector<Piece> pieces;
+  int64_t at = 0;
+  for (int64_t i = 0; i < number_pieces; ++i) {
+    pieces.push_back({at, lengths[i], (int)owners[i]});
+    at += lengths[i];
+  }
+  std::vector<int64_t> b(bounds, bounds + world + 1);
+  RedistPlan const p = plan_redistribution(world, me, pieces, b);
+  for (int d = 0; d < world; ++d) {
+    scount[d] = p.scount[(size_t)d];
+    sdispl[d] = p.sdispl[(size_t)d];
+    rcount[d] = p.rcount[(size_t)d];
+    rdispl[d] = p.rdispl[(size_t)d];
+  }
+  if ((int64_t)p.places.size() > capacity) return -1;
+  for (size_t k = 0; k < p.places.size(); ++k) {
+    places[3 * k] = p.places[k].src;
+    places[3 * k + 1] = p.places[k].dst;
+    places[3 * k + 2] = p.places[k].length;
+  }
+  return (int64_t)p.places.size();
+}
+
+int ls_b200_plan_balanced_bounds(int64_t number_blocks, int64_t const *edges, double const *costs, int world,
+                                 int64_t *bounds) {
+  std::vector<int64_t> e(edges, edges + number_blocks + 1);
+  std::vector<double> c(costs, costs + number_blocks);
+  auto const b = dist_balanced_bounds(e, c, world);
+  for (int r = 0; r <= world; ++r) bounds[r] = b[(size_t)r];
+  return 0;
+}
+
+}  // extern "C"

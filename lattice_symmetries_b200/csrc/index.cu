@@ -29,6 +29,7 @@ IndexView IndexData::view() const {
 
 IndexData::~IndexData() {
   matvec_forget_index(this);
+  delete dist;
   if (owns_d_reps) cudaFree(d_reps);
   cudaFree(d_offsets32);
   cudaFree(d_offsets64);
@@ -319,6 +320,64 @@ IndexData *create_index(uint64_t const *host_reps, int64_t count, int number_bit
     CUDA_CHECK(cudaMemcpyAsync(ix->d_reps, host_reps, sizeof(uint64_t) * (size_t)count,
                                cudaMemcpyHostToDevice, runtime().stream));
   }
+  if (count > 0 && number_bits > 0) {
+    build_bucket_table(*ix, prefix_bits);
+  } else {
+    while ((ix->number_states >> ix->steps) != 0) ++ix->steps;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(runtime().stream));
+  return ix;
+}
+
+// ---- pieces of the table build used by the replicated index of a sharded basis (dist.cu) ----------------------
+int index_choose_prefix_bits(int64_t n, int number_bits) { return choose_prefix_bits(n, number_bits, 0); }
+
+// keys[i] = low `shift` bits of reps[i], as 2- or 4-byte keys
+void index_local_keys(uint64_t const *d_reps, int64_t n, int shift, void *d_keys, int key_bytes) {
+  if (n <= 0) return;
+  Runtime &rt = runtime();
+  uint64_t const mask = shift >= 64 ? ~uint64_t(0) : ((uint64_t(1) << shift) - 1);
+  unsigned const blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 16);
+  if (key_bytes == 2) low_bits_kernel<uint16_t><<<blocks, 256, 0, rt.stream>>>(d_reps, n, mask, static_cast<uint16_t *>(d_keys));
+  else low_bits_kernel<uint32_t><<<blocks, 256, 0, rt.stream>>>(d_reps, n, mask, static_cast<uint32_t *>(d_keys));
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// out[p] = number of LOCAL representatives whose prefix is below p (p = 0 .. number_offsets - 1; the last entry is
+// n): summed over the ranks this is the level-1 table of the whole basis.
+void index_local_offsets64(uint64_t const *d_reps, int64_t n, int shift, int64_t number_offsets, int64_t *d_out) {
+  Runtime &rt = runtime();
+  unsigned const blocks = (unsigned)std::min<int64_t>((number_offsets + 255) / 256, (int64_t)rt.sm_count * 16);
+  bucket_offsets_kernel<int64_t><<<blocks, 256, 0, rt.stream>>>(d_reps, n, shift, number_offsets, d_out);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+int index_steps_from_offsets64(int64_t const *d_offsets, int64_t number_buckets) {
+  Runtime &rt = runtime();
+  static DeviceBuffer<unsigned long long> max_buffer;
+  unsigned long long *d_max = max_buffer.reserve(1), h_max = 0;
+  CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof h_max, rt.stream));
+  unsigned const blocks = (unsigned)std::min<int64_t>((number_buckets + 255) / 256, (int64_t)rt.sm_count * 16);
+  max_bucket_kernel<int64_t><<<blocks, 256, 0, rt.stream>>>(d_offsets, number_buckets, d_max);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof h_max, cudaMemcpyDeviceToHost, rt.stream));
+  CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+  int steps = 0;
+  while ((h_max >> steps) != 0) ++steps;
+  return steps;
+}
+
+// Index over a device-resident sorted list the object takes ownership of (no host view).
+IndexData *create_index_from_device(uint64_t *d_reps, int64_t count, int number_bits, int prefix_bits) {
+  auto *ix = new IndexData();
+  ix->number_states = count;
+  ix->host_reps = nullptr;
+  ix->number_bits = number_bits;
+  ix->d_reps = d_reps;
+  ix->owns_d_reps = true;
   if (count > 0 && number_bits > 0) {
     build_bucket_table(*ix, prefix_bits);
   } else {

@@ -104,8 +104,13 @@ void TermsDev::upload(ls_hs_nonbranching_terms const *t) {
 
 TermsView TermsDev::view() const { return TermsView{number_terms, d_v, d_m, d_l, d_r, d_x, d_s}; }
 
-OperatorDev &operator_dev(ls_hs_operator const *op) {
+static std::unordered_map<ls_hs_operator const *, std::unique_ptr<OperatorDev>> &operator_cache() {
   static std::unordered_map<ls_hs_operator const *, std::unique_ptr<OperatorDev>> cache;
+  return cache;
+}
+
+OperatorDev &operator_dev(ls_hs_operator const *op) {
+  auto &cache = operator_cache();
   auto &slot = cache[op];
   if (!slot) slot = std::make_unique<OperatorDev>();
   OperatorDev &d = *slot;
@@ -139,7 +144,7 @@ row_count_kernel(MatvecArgs const a) {
   if (r > a.chunk_rows) return;
   uint32_t c = 0;
   if (r < a.chunk_rows) {
-    uint64_t const alpha = __ldg(a.ix.reps + a.chunk_begin + r);
+    uint64_t const alpha = __ldg(a.rows + a.chunk_begin + r);
     for (int t = 0; t < terms.T; ++t) c += ((alpha & terms.m[t]) == terms.l[t]) ? 1u : 0u;
   }
   a.counts[r] = c;
@@ -166,7 +171,7 @@ row_sum_kernel(MatvecArgs const a) {
   if (r >= a.chunk_rows) return;
   int64_t const vec = blockIdx.y;  // block matvec: one grid row per vector
   int64_t const row = a.chunk_begin + r;
-  uint64_t const alpha = __ldg(a.ix.reps + row);
+  uint64_t const alpha = __ldg(a.rows + row);
   uint32_t const qa = __ldg(a.offsets + r), qb = __ldg(a.offsets + r + 1);
   double acc_r = 0.0, acc_i = 0.0;
   for (uint32_t q = qa; q < qb; ++q) {
@@ -215,7 +220,7 @@ constexpr int kRankThreads = 256;
 constexpr int kRankBatch = LS_RANK_BATCH;
 constexpr unsigned long long kMissBits = 0x7ff8dead00000001ull;  // a quiet NaN no computation produces
 
-template <class Low>
+template <class Low, bool Wide = false>
 __global__ void __launch_bounds__(kRankThreads, LS_RANK_MINBLOCKS)  // register cap, also for the (rare) noinline norm check
 rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -253,7 +258,7 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
 #pragma unroll
     for (int u = 0; u < kRankBatch; ++u) j[u] = (int64_t)(needle[u] % (uint64_t)a.ix.number_states);
   } else if constexpr (std::is_void<Low>::value) index_find<kRankBatch>(a.ix, needle, live, j);
-  else index_find32<Low, kRankBatch>(a.ix, needle, live, j);
+  else index_find32<Low, kRankBatch, Wide>(a.ix, needle, live, j);
   if (a.debug_skip & 4) {  // profiling only: no random gather
 #pragma unroll
     for (int u = 0; u < kRankBatch; ++u) j[u] = j[u] >= 0 ? (j[u] & 1023) : j[u];
@@ -334,7 +339,7 @@ row_combine_kernel(__grid_constant__ MatvecArgs const a) {
   int const r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.chunk_rows) return;
   int64_t const row = a.chunk_begin + r;
-  uint64_t const alpha = __ldg(a.ix.reps + row);
+  uint64_t const alpha = __ldg(a.rows + row);
   int const T = terms.T;
   bool const have_cidx = a.number_idx_planes > 0;
   double acc_r = 0.0, acc_i = 0.0;
@@ -399,7 +404,7 @@ orbit_scalar_kernel(MatvecArgs const a) {
   __syncthreads();
   int const r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.chunk_rows) return;
-  uint64_t const alpha = __ldg(a.ix.reps + a.chunk_begin + r);
+  uint64_t const alpha = __ldg(a.rows + a.chunk_begin + r);
   uint32_t q = a.offsets[r];
   for (int t = 0; t < terms.T; ++t)
     if ((alpha & terms.m[t]) == terms.l[t]) {
@@ -446,7 +451,7 @@ gather_kernel(MatvecArgs const a) {
   int const r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.chunk_rows) return;
   int64_t const row = a.chunk_begin + r;
-  uint64_t const alpha = __ldg(a.ix.reps + row);
+  uint64_t const alpha = __ldg(a.rows + row);
   IndexView const ix = a.ix;
   int const T = terms.T;
   double acc_r = 0.0, acc_i = 0.0;
@@ -553,7 +558,7 @@ __global__ void __launch_bounds__(256)
 prescale_kernel(int64_t n, int complex_vectors, double const *__restrict__ norms,
                 double const *__restrict__ x, double *__restrict__ xs) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double const s = norms[i];
+    double const s = norms != nullptr ? norms[i] : 1.0;
     if (complex_vectors) {
       double2 const v = reinterpret_cast<double2 const *>(x)[i];
       reinterpret_cast<double2 *>(xs)[i] = make_double2(s * v.x, s * v.y);
@@ -583,8 +588,17 @@ count_elements_kernel(TermsView off, uint64_t const *__restrict__ reps, int64_t 
 
 void ensure_norms(IndexData &ix, GroupData const &g);
 
+void launch_prescale(int64_t n, bool complex_vectors, double const *norms, double const *x, double *xs) {
+  if (n <= 0) return;
+  Runtime &rt = runtime();
+  unsigned const blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 16);
+  prescale_kernel<<<blocks, 256, 0, rt.stream>>>(n, complex_vectors ? 1 : 0, norms, x, xs);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
 
-static int64_t count_elements(OperatorDev &od, IndexData const &ix, int64_t row_begin, int64_t row_end) {
+
+int64_t count_elements(OperatorDev &od, uint64_t const *d_rows, int64_t row_begin, int64_t row_end) {
   Runtime &rt = runtime();
   if (od.off.number_terms == 0 || row_end <= row_begin) return 0;
   static unsigned long long *d_counter = nullptr;
@@ -592,7 +606,7 @@ static int64_t count_elements(OperatorDev &od, IndexData const &ix, int64_t row_
   CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), rt.stream));
   int64_t const n = row_end - row_begin;
   unsigned const blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 8);
-  count_elements_kernel<<<blocks, 256, 0, rt.stream>>>(od.off.view(), ix.d_reps, row_begin, row_end, d_counter);
+  count_elements_kernel<<<blocks, 256, 0, rt.stream>>>(od.off.view(), d_rows, row_begin, row_end, d_counter);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
   unsigned long long h = 0;
@@ -649,7 +663,18 @@ void matvec_forget_index(IndexData const *ix) {
     sc.phase_op = nullptr;
     sc.phase_ready = false;
     sc.phase_elements.clear();
+    sc.phase_slots.clear();  // the canonicalised elements of a basis that is going away: give the memory back
   }
+}
+
+// Frees the per-chunk buffers of the phased product (they are sized for one operator on one basis).
+static void release_phase_slots() {
+  MatvecScratch &sc = mv_scratch();
+  sc.phase_slots.clear();
+  sc.phase_elements.clear();
+  sc.phase_op = nullptr;
+  sc.phase_index = nullptr;
+  sc.phase_ready = false;
 }
 
 template <class K>
@@ -671,9 +696,13 @@ static cudaEvent_t next_event(MatvecScratch &sc) {
 // number_vectors > 1 (block matvec, an extension: the reference halts, DistributedMatrixVector.chpl:1096-1097):
 // vector v is x + v x_stride -> y + v y_stride (strides in scalars of the vector type).  On the split path all
 // vectors share ONE canonicalisation + ranking pass -- the integer work is per matrix element, not per vector.
-static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end, double const *d_x,
-                          double *d_y, bool complex_vectors, int number_vectors = 1, int64_t x_stride = 0,
-                          int64_t y_stride = 0, double *host_y = nullptr, int phase = 0) {
+//
+// target (distributed products, dist.cu): the rows are the caller's local shard (row numbers, x and y are LOCAL),
+// while representatives are ranked against target->index -- the replicated index of the whole basis -- and the
+// gathered values come from target->xs, the replicated pre-scaled vector n_j x_j.
+void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end, double const *d_x,
+                   double *d_y, bool complex_vectors, int number_vectors, int64_t x_stride,
+                   int64_t y_stride, double *host_y, int phase, MvTarget const *target) {
   // phase (split path, one vector): 1 = canonicalise only -- row counts, offsets, representatives of every chunk,
   // none of which depends on x -- into per-chunk buffers that persist; 2 = rank + gather + row sums from them.
   // A multi-GPU caller runs phase 1 of the NEXT product while NCCL all-gathers the result of this one.
@@ -681,7 +710,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   ls_hs_basis const *basis = op->basis;
   IndexData *ix = index_of(basis);
   LSB_CHECK(ix != nullptr, "basis is not built: call ls_hs_basis_build / ls_hs_build_representatives first");
-  int64_t const dim = ix->number_states;
+  int64_t const dim = target != nullptr ? target->number_rows : ix->number_states;  // rows addressable by this call
   LSB_CHECK(0 <= row_begin && row_begin <= row_end && row_end <= dim, "invalid row range");
   if (row_begin == row_end) return;
   OperatorDev &od = operator_dev(op);
@@ -700,7 +729,8 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   CUDA_CHECK(cudaEventRecord(rt.ev0, rt.stream));
 
   MatvecArgs a{};
-  a.ix = ix->view();
+  a.ix = target != nullptr ? target->index : ix->view();
+  a.rows = target != nullptr ? target->rows : ix->d_reps;
   a.off = od.off.view();
   a.diag = od.diag.view();
   a.complex_vectors = complex_vectors ? 1 : 0;
@@ -719,9 +749,9 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
   bool inv = false;
   if (info.has_permutation_symmetries) {
     GroupData const &g = *info.group;
-    ensure_norms(*ix, g);
+    if (target == nullptr) ensure_norms(*ix, g);
     a.g = g.view();
-    a.norms = ix->d_norms;
+    a.norms = target != nullptr ? target->norms : ix->d_norms;
     np = std::max(4, (g.number_bits + 3) / 4 * 4);
     inv = g.spin_inversion != 0;
     char const *env = getenv("LS_B200_MATVEC");
@@ -733,24 +763,31 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     bool const bitsliced = !want_scalar && orbit_prepare(g, np);
     a.mode = bitsliced ? kModeGroup : kModeGroupScalar;
     if (!bitsliced) a.number_idx_planes = std::max(a.number_idx_planes, 1);  // the scalar kernel always writes q_cidx
-    // pre-scaled copy of x
-    size_t const words = (size_t)dim * (complex_vectors ? 2 : 1);
-    double *xs = sc.xs.reserve(words * (size_t)number_vectors);
-    unsigned const blocks = (unsigned)std::min<int64_t>((dim + 255) / 256, (int64_t)rt.sm_count * 16);
-    for (int v = 0; v < number_vectors && phase != 1; ++v) {
-      // (xs is packed: vector v at xs + v dim, whatever the caller's stride)
-      prescale_kernel<<<blocks, 256, 0, rt.stream>>>(dim, a.complex_vectors, ix->d_norms,
-                                                     d_x + (size_t)v * (size_t)x_stride * (complex_vectors ? 2 : 1),
-                                                     xs + (size_t)v * words);
-      count_launch();
+    if (target == nullptr) {
+      // pre-scaled copy of x
+      size_t const words = (size_t)dim * (complex_vectors ? 2 : 1);
+      double *xs = sc.xs.reserve(words * (size_t)number_vectors);
+      unsigned const blocks = (unsigned)std::min<int64_t>((dim + 255) / 256, (int64_t)rt.sm_count * 16);
+      for (int v = 0; v < number_vectors && phase != 1; ++v) {
+        // (xs is packed: vector v at xs + v dim, whatever the caller's stride)
+        prescale_kernel<<<blocks, 256, 0, rt.stream>>>(dim, a.complex_vectors, ix->d_norms,
+                                                       d_x + (size_t)v * (size_t)x_stride * (complex_vectors ? 2 : 1),
+                                                       xs + (size_t)v * words);
+        count_launch();
+      }
+      CUDA_CHECK(cudaGetLastError());
+      a.xs = xs;
     }
-    CUDA_CHECK(cudaGetLastError());
-    a.xs = xs;
   } else if (info.has_spin_inversion) {
     a.mode = kModeInversion;
     // cidx 1 = the spin-inversion character: entry 1 of the plain table is +1, entry 2 is -1
     a.cvals = sc.d_plain_chars + (basis->spin_inversion < 0 ? 1 : 0);
     a.number_chars = 2;
+  }
+  if (target != nullptr) {
+    LSB_CHECK(phase == 0 && number_vectors == 1 && host_y == nullptr,
+              "distributed products take one device-resident vector at a time");
+    a.xs = target->xs;  // the replicated vector (already multiplied by the norms where the basis has them)
   }
   LSB_CHECK(a.off.number_terms < 0x8000, "too many off-diagonal terms");
 
@@ -861,6 +898,9 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
     rank_gather = a.ix.lows16 != nullptr   ? rank_gather_kernel<uint16_t>
                   : a.ix.lows32 != nullptr ? rank_gather_kernel<uint32_t>
                                            : rank_gather_kernel<uint64_t>;
+  else if (a.ix.offsets64 != nullptr && !a.ix.identity && (a.ix.lows16 != nullptr || a.ix.lows32 != nullptr))
+    // 2^32 states or more (the replicated index of a distributed basis): 64-bit bucket starts, 32-bit windows
+    rank_gather = a.ix.lows16 != nullptr ? rank_gather_kernel<uint16_t, true> : rank_gather_kernel<uint32_t, true>;
 
   // rank_gather runs as a persistent grid sized to the machine (tables staged once, no empty CTAs: 8 % faster);
   // the orbit kernel keeps one CTA per four blocks (see there).
@@ -910,7 +950,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
       sc.phase_elements.assign((size_t)number_chunks, 0);
       for (int64_t c = 0; c < number_chunks; ++c) {
         int64_t const begin = row_begin + c * chunk_rows;
-        sc.phase_elements[(size_t)c] = count_elements(od, *ix, begin, std::min(row_end, begin + chunk_rows));
+        sc.phase_elements[(size_t)c] = count_elements(od, a.rows, begin, std::min(row_end, begin + chunk_rows));
       }
       sc.phase_op = op;
       sc.phase_index = ix;
@@ -1078,7 +1118,7 @@ static void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t r
 }
 
 // Blocks until the stream drains, then reports kernel time and sector errors.
-static bool matvec_finish() {
+bool matvec_finish() {
   Runtime &rt = runtime();
   MatvecScratch &sc = mv_scratch();
   int flag = 0;
@@ -1102,9 +1142,362 @@ static bool matvec_finish() {
   return true;
 }
 
-static char const *kInvalidIndexMessage =
+char const *kInvalidIndexMessage =
     "matrix_vector_product: the operator maps a basis state outside of the basis with a non-zero "
     "coefficient (invalid index); it does not respect the symmetries of the basis";
+
+
+// ---- push form: all-to-all products of a basis sharded over ranks -----------------------------------------
+// The rank that owns COLUMN i applies the forward terms to alpha_i, canonicalises every beta (same orbit kernel as the
+// pull form) and emits records (rep_j, chi_g v_t sign x_i / n_i) grouped by the rank that owns rep_j
+// (BatchedOperator.chpl:207-253 for the coefficient; owner = contiguous range instead of the hash of
+// StatesEnumeration.chpl:198-212); the owner ranks the representative locally and adds n_j times the coefficient
+// into y with fp64 atomics (ConcurrentAccessor.chpl:31-33).
+constexpr int kPushThreads = 256;
+constexpr int kPushMaxWorld = 64;
+
+struct PushArgs {
+  MatvecArgs a;             // rows, chunk, offsets, q_rep, q_cidx; a.off = the operator's terms (forward use: match on r)
+  double const *x;          // local vector (row numbering of a.rows)
+  uint64_t const *splitters;  // [world] first representative of every rank
+  int world;
+  int nblocks;
+  uint32_t *hist;           // [world][nblocks] records per (owner, block)
+  uint32_t const *base;     // exclusive scan of hist
+  PushRecord *send;
+};
+
+__device__ __forceinline__ int push_owner(uint64_t const *splitters, int world, uint64_t rep) {
+  int d = 0;
+  for (int k = 1; k < world; ++k) d += (splitters[k] <= rep) ? 1 : 0;  // splitters ascend; empty ranks carry ~0
+  return d;
+}
+
+// Thread per column.  SCATTER = false: count the records per owner; true: write them.
+template <bool SCATTER>
+__global__ void __launch_bounds__(kPushThreads)
+push_emit_kernel(PushArgs const p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  MatvecArgs const &a = p.a;
+  int const T = a.off.number_terms;
+  double2 *t_v = reinterpret_cast<double2 *>(smem);
+  uint64_t *t_m = reinterpret_cast<uint64_t *>(t_v + T);
+  uint64_t *t_r = t_m + T;
+  uint64_t *t_x = t_r + T;
+  uint64_t *t_s = t_x + T;
+  double2 *chars = reinterpret_cast<double2 *>(t_s + T);
+  uint64_t *split = reinterpret_cast<uint64_t *>(chars + a.number_chars);
+  unsigned *counters = reinterpret_cast<unsigned *>(split + p.world);
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    t_v[t] = a.off.v[t];
+    t_m[t] = a.off.m[t];
+    t_r[t] = a.off.r[t];
+    t_x[t] = a.off.x[t];
+    t_s[t] = a.off.s[t];
+  }
+  for (int j = threadIdx.x; j < a.number_chars; j += blockDim.x) chars[j] = a.cvals[j];
+  for (int d = threadIdx.x; d < p.world; d += blockDim.x) {
+    split[d] = p.splitters[d];
+    counters[d] = SCATTER ? p.base[(size_t)d * p.nblocks + blockIdx.x] : 0u;
+  }
+  __syncthreads();
+  int const r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < a.chunk_rows) {
+    int64_t const row = a.chunk_begin + r;
+    uint64_t const alpha = __ldg(a.rows + row);
+    double const xi = __ldg(p.x + row);
+    double const scale = a.norms != nullptr ? xi / __ldg(a.norms + row) : xi;
+    bool const queued = a.mode == kModeGroup || a.mode == kModeGroupScalar;
+    uint32_t q = queued ? __ldg(a.offsets + r) : 0u;
+    if (scale != 0.0) {
+      for (int t = 0; t < T; ++t) {
+        if ((alpha & t_m[t]) != t_r[t]) continue;
+        uint64_t rep;
+        unsigned c = 0;
+        if (queued) {
+          rep = __ldg(a.q_rep + q);
+          c = a.number_idx_planes > 0 ? __ldg(a.q_cidx + q) : 0u;
+          ++q;
+        } else {
+          rep = alpha ^ t_x[t];
+          if (a.mode == kModeInversion) {  // BatchedOperator.chpl:187-199
+            uint64_t const inverted = rep ^ a.inversion_mask;
+            if (inverted < rep) { rep = inverted; c = 1; }
+          }
+        }
+        double2 const ch = chars[c];
+        double2 const v = t_v[t];
+        double fr = ch.x * v.x - ch.y * v.y;  // Re(chi v): real vectors take the real part (DistributedMatrixVector.chpl:124)
+        if (__popcll(alpha & t_s[t]) & 1) fr = -fr;
+        double const coeff = fr * scale;
+        if (coeff == 0.0) continue;  // :127 `if c != 0`
+        int const d = push_owner(split, p.world, rep);
+        unsigned const pos = atomicAdd(&counters[d], 1u);
+        if (SCATTER) {
+          PushRecord rec;
+          rec.rep = rep;
+          rec.c = coeff;
+          p.send[pos] = rec;
+        }
+      }
+    }
+  }
+  if (!SCATTER) {
+    __syncthreads();
+    for (int d = threadIdx.x; d < p.world; d += blockDim.x) p.hist[(size_t)d * p.nblocks + blockIdx.x] = counters[d];
+  }
+}
+
+// displs[d] = start of owner d's records in the send buffer, displs[world] = their total
+__global__ void push_displs_kernel(uint32_t const *__restrict__ base, int world, int nblocks,
+                                   unsigned long long *__restrict__ displs) {
+  int const d = threadIdx.x;
+  if (d <= world) displs[d] = base[(size_t)d * nblocks];
+}
+
+// y[r] = sum_t [alpha_r & m_t == r_t] Re(v_t) sign_t x[r]  (kernels/reference.c:67-95): also what zero-initialises y
+__global__ void __launch_bounds__(256)
+push_diag_kernel(TermsView diag, uint64_t const *__restrict__ rows, int64_t n, double const *__restrict__ x,
+                 double *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t const alpha = rows[i];
+    double d = 0.0;
+    for (int t = 0; t < diag.number_terms; ++t)
+      if ((alpha & __ldg(diag.m + t)) == __ldg(diag.r + t)) {
+        double const v = __ldg(&diag.v[t].x);
+        d += (__popcll(alpha & __ldg(diag.s + t)) & 1) ? -v : v;
+      }
+    y[i] = d * x[i];
+  }
+}
+
+// Thread per received record: rank the representative among the LOCAL rows, y[j] += n_j c.
+template <class Low>
+__global__ void __launch_bounds__(256, 4)
+push_consume_kernel(IndexView ix, GroupView g, int check_norm, double const *__restrict__ norms,
+                    PushRecord const *__restrict__ records, int64_t count, double *__restrict__ y, int *error_flag) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+    ulonglong2 const raw = __ldcs(reinterpret_cast<ulonglong2 const *>(records) + k);
+    uint64_t const needle[1] = {raw.x};
+    double const c = __longlong_as_double((long long)raw.y);
+    bool const live[1] = {true};
+    int64_t j[1];
+    if constexpr (std::is_void<Low>::value) index_find<1>(ix, needle, live, j);
+    else index_find32<Low, 1>(ix, needle, live, j);
+    if (j[0] >= 0) {
+      atomicAdd(y + j[0], norms != nullptr ? __ldg(norms + j[0]) * c : c);
+    } else {
+      // not a row of this rank: fine when the state's norm vanishes, the reference's "invalid index" halt otherwise
+      // (DistributedMatrixVector.chpl:127-135)
+      bool bad = true;
+      if (check_norm) bad = stabiliser_sum_global(g, raw.x) > kNormThreshold;
+      if (bad) atomicOr(error_flag, 1);
+    }
+  }
+}
+
+struct PushSetup {
+  MatvecArgs a{};
+  int np = 4;
+  bool inv = false;
+  size_t count_smem = 0, orbit_smem = 0, emit_smem = 0;
+  int64_t capacity = 0;
+};
+
+static void ensure_error_flag(MatvecScratch &sc) {
+  Runtime &rt = runtime();
+  if (sc.d_error == nullptr) {
+    CUDA_CHECK(cudaMalloc(&sc.d_error, sizeof(int)));
+    CUDA_CHECK(cudaMemsetAsync(sc.d_error, 0, sizeof(int), rt.stream));
+    double const plain[6] = {1.0, 0.0, 1.0, 0.0, -1.0, 0.0};
+    CUDA_CHECK(cudaMalloc(&sc.d_plain_chars, sizeof plain));
+    CUDA_CHECK(cudaMemcpy(sc.d_plain_chars, plain, sizeof plain, cudaMemcpyHostToDevice));
+  }
+}
+
+// The forward use of the term tables by the canonicalisation kernels: they match on `l` (adjoint form), so hand
+// them a view with l and r exchanged.
+static TermsView forward_view(TermsView t) {
+  std::swap(t.l, t.r);
+  return t;
+}
+
+static PushSetup push_setup(ls_hs_operator const *op, IndexData const &local) {
+  Runtime &rt = runtime();
+  MatvecScratch &sc = mv_scratch();
+  ensure_error_flag(sc);
+  ls_hs_basis const *basis = op->basis;
+  OperatorDev &od = operator_dev(op);
+  BasisInfo const info = basis_info(basis);
+  PushSetup su;
+  MatvecArgs &a = su.a;
+  a.ix = local.view();
+  a.rows = local.d_reps;
+  a.off = od.off.view();
+  a.diag = od.diag.view();
+  a.error_flag = sc.d_error;
+  a.spin_inversion = basis->spin_inversion;
+  a.inversion_mask = basis->number_sites >= 64 ? ~uint64_t(0) : ((uint64_t(1) << basis->number_sites) - 1);
+  a.mode = kModeNone;
+  a.cvals = sc.d_plain_chars;
+  a.number_chars = 1;
+  a.number_vectors = 1;
+  if (info.has_permutation_symmetries) {
+    GroupData const &g = *info.group;
+    LSB_CHECK(local.d_norms != nullptr || local.number_states == 0, "the local rows carry no norms");
+    a.g = g.view();
+    a.norms = local.d_norms;
+    su.np = std::max(4, (g.number_bits + 3) / 4 * 4);
+    su.inv = g.spin_inversion != 0;
+    LSB_CHECK(!g.cinfo.empty(), "symmetry sectors with more than 256 distinct character values are not supported");
+    a.cvals = g.d_cvals;
+    a.number_chars = (int)(g.cvals.size() / 2);
+    while ((1 << a.number_idx_planes) < a.number_chars) ++a.number_idx_planes;
+    char const *env = getenv("LS_B200_MATVEC");
+    bool const want_scalar = env != nullptr && strcmp(env, "scalar") == 0;
+    bool const bitsliced = !want_scalar && orbit_prepare(g, su.np);
+    a.mode = bitsliced ? kModeGroup : kModeGroupScalar;
+    if (!bitsliced) a.number_idx_planes = std::max(a.number_idx_planes, 1);
+  } else if (info.has_spin_inversion) {
+    a.mode = kModeInversion;
+    a.cvals = sc.d_plain_chars + (basis->spin_inversion < 0 ? 1 : 0);
+    a.number_chars = 2;
+  }
+  int const T = a.off.number_terms;
+  LSB_CHECK(T < 0x8000, "too many off-diagonal terms");
+  su.count_smem = AdjointTerms::bytes(T, false);
+  su.orbit_smem = ((su.count_smem + 15) & ~size_t(15)) + (size_t)(kOrbitThreads / 32) * kWarpSlabBytes;
+  su.capacity = int64_t(1) << 26;
+  if (char const *env = getenv("LS_B200_MV_CHUNK")) su.capacity = std::max<int64_t>(4096, atoll(env));
+  LSB_CHECK(su.orbit_smem <= rt.smem_optin, "operator / symmetry tables do not fit in shared memory");
+  return su;
+}
+
+// Rows per chunk: a function of the operator alone, so that every rank cuts its columns the same way and all ranks
+// agree on the number of exchange rounds.
+int64_t push_chunk_rows(ls_hs_operator const *op, int64_t local_rows) {
+  OperatorDev &od = operator_dev(op);
+  int64_t capacity = int64_t(1) << 26;
+  if (char const *env = getenv("LS_B200_MV_CHUNK")) capacity = std::max<int64_t>(4096, atoll(env));
+  int const T = std::max(1, od.off.number_terms);
+  (void)local_rows;
+  return std::max<int64_t>(1, capacity / T);
+}
+
+void push_begin(ls_hs_operator const *op, IndexData const &local, double const *d_x, double *d_y) {
+  Runtime &rt = runtime();
+  OperatorDev &od = operator_dev(op);
+  int64_t const n = local.number_states;
+  if (n == 0) return;
+  unsigned const blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 16);
+  push_diag_kernel<<<blocks, 256, 0, rt.stream>>>(od.diag.view(), local.d_reps, n, d_x, d_y);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void push_produce(ls_hs_operator const *op, IndexData const &local, DistShard &shard, int64_t chunk_begin,
+                  int64_t chunk_rows, double const *d_x) {
+  Runtime &rt = runtime();
+  MatvecScratch &sc = mv_scratch();
+  LSB_CHECK(shard.push != nullptr && shard.world <= kPushMaxWorld, "push buffers missing / too many ranks");
+  PushBuffers &pb = *shard.push;
+  int const world = shard.world;
+  unsigned long long *displs = pb.displs.reserve((size_t)world + 1);
+  if (chunk_rows <= 0) {
+    CUDA_CHECK(cudaMemsetAsync(displs, 0, sizeof(unsigned long long) * ((size_t)world + 1), rt.stream));
+    return;
+  }
+  PushSetup su = push_setup(op, local);
+  MatvecArgs &a = su.a;
+  int const T = a.off.number_terms;
+  bool const queued = (a.mode == kModeGroup || a.mode == kModeGroupScalar) && T > 0;
+  a.chunk_begin = chunk_begin;
+  a.chunk_rows = (int)chunk_rows;
+  ChunkSlot &slot = sc.slot[0];
+  size_t const capacity = (size_t)chunk_rows * (size_t)std::max(T, 1);
+  if (queued) {
+    a.counts = slot.counts.reserve((size_t)chunk_rows + 1);
+    a.offsets = slot.offsets.reserve((size_t)chunk_rows + 1);
+    a.q_rep = slot.q_rep.reserve(capacity + 32);
+    a.q_cidx = slot.q_cidx.reserve(capacity + 32);
+    a.q_tsign = nullptr;
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(chunk_rows + 1), rt.stream);
+    if (tmp > sc.scan_tmp_bytes) {
+      sc.scan_tmp.reserve(tmp);
+      sc.scan_tmp_bytes = sc.scan_tmp.capacity;
+    }
+    // canonicalise with the FORWARD terms (the kernels match on `l`)
+    MatvecArgs fa = a;
+    fa.off = forward_view(a.off);
+    allow_dynamic_smem(row_count_kernel, su.count_smem);
+    row_count_kernel<<<ceil_div((size_t)chunk_rows + 1, 256), 256, su.count_smem, rt.stream>>>(fa);
+    tmp = sc.scan_tmp_bytes;
+    cub::DeviceScan::ExclusiveSum(sc.scan_tmp.ptr, tmp, fa.counts, fa.offsets, (int)(chunk_rows + 1), rt.stream);
+    count_launch(2);
+    if (a.mode == kModeGroup) {
+      size_t const max_words = ((capacity + 1023) / 1024) * 32;
+      orbit_launch(su.np, su.inv, false, max_words, su.orbit_smem, rt.stream, fa);
+    } else {
+      allow_dynamic_smem(orbit_scalar_kernel, su.count_smem);
+      orbit_scalar_kernel<<<ceil_div((size_t)chunk_rows, 128), 128, su.count_smem, rt.stream>>>(fa);
+    }
+    count_launch();
+    CUDA_CHECK(cudaGetLastError());
+  }
+  // group the records by owner: count -> scan -> scatter
+  int const nblocks = (int)ceil_div((size_t)chunk_rows, kPushThreads);
+  size_t const cells = (size_t)world * (size_t)nblocks + 1;
+  PushArgs p{};
+  p.a = a;
+  p.x = d_x;
+  p.splitters = shard.d_splitters;
+  p.world = world;
+  p.nblocks = nblocks;
+  p.hist = pb.hist.reserve(cells);
+  uint32_t *base = pb.base.reserve(cells);
+  p.base = base;
+  p.send = pb.send.reserve(capacity + 1);
+  size_t const emit_smem = (size_t)T * 48 + (size_t)a.number_chars * 16 + (size_t)world * 12 + 16;
+  LSB_CHECK(emit_smem <= rt.smem_optin, "operator tables do not fit in shared memory");
+  allow_dynamic_smem(push_emit_kernel<false>, emit_smem);
+  allow_dynamic_smem(push_emit_kernel<true>, emit_smem);
+  CUDA_CHECK(cudaMemsetAsync(p.hist + cells - 1, 0, sizeof(uint32_t), rt.stream));
+  push_emit_kernel<false><<<nblocks, kPushThreads, emit_smem, rt.stream>>>(p);
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, p.hist, base, (int)cells, rt.stream);
+  void *d_tmp = pb.scan_tmp.reserve(tmp);
+  cub::DeviceScan::ExclusiveSum(d_tmp, tmp, p.hist, base, (int)cells, rt.stream);
+  push_emit_kernel<true><<<nblocks, kPushThreads, emit_smem, rt.stream>>>(p);
+  push_displs_kernel<<<1, kPushMaxWorld + 32, 0, rt.stream>>>(base, world, nblocks, displs);
+  count_launch(4);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void push_consume(ls_hs_operator const *op, IndexData const &local, PushRecord const *records, int64_t count,
+                  double *d_y) {
+  if (count <= 0) return;
+  Runtime &rt = runtime();
+  MatvecScratch &sc = mv_scratch();
+  ensure_error_flag(sc);
+  BasisInfo const info = basis_info(op->basis);
+  GroupView g{};
+  int check_norm = 0;
+  if (info.has_permutation_symmetries) {
+    g = info.group->view();
+    check_norm = 1;
+  }
+  IndexView const ix = local.view();
+  unsigned const blocks = (unsigned)std::min<int64_t>((count + 255) / 256, (int64_t)rt.sm_count * 8);
+  auto kernel = push_consume_kernel<void>;
+  if (ix.offsets32 != nullptr && !ix.identity)
+    kernel = ix.lows16 != nullptr   ? push_consume_kernel<uint16_t>
+             : ix.lows32 != nullptr ? push_consume_kernel<uint32_t>
+                                    : push_consume_kernel<uint64_t>;
+  kernel<<<blocks, 256, 0, rt.stream>>>(ix, g, check_norm, local.d_norms, records, count, d_y, sc.d_error);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
 
 }  // namespace lsb
 
@@ -1130,10 +1523,22 @@ void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors, double c
     IndexData *ix = index_of(op->basis);
     LSB_CHECK(ix != nullptr, "basis is not built");
     int64_t const dim = ix->number_states;
-    if (dim == 0) return;
     MatvecScratch &sc = mv_scratch();
     cudaStream_t s = runtime().stream;
     size_t const n = (size_t)dim * (size_t)num_vectors;
+    if (ix->dist != nullptr) {
+      // The reference's per-locale block of the distributed product (DistributedMatrixVector.chpl:1060-1088): x and y
+      // are THIS rank's blocks of the vectors; every rank of the communicator makes the same call.
+      LSB_CHECK(num_vectors == 1, "distributed products take one vector at a time");
+      double *d_x = sc.x.reserve(n + 1);
+      double *d_y = sc.y.reserve(n + 1);
+      if (n > 0) CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+      dist_matvec_local(op, d_x, d_y, 0, false);
+      if (n > 0) CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+      ok = matvec_finish();
+      return;
+    }
+    if (dim == 0) return;
     double *d_x = sc.x.reserve(n);
     double *d_y = sc.y.reserve(n);
     // pinned y: finished row chunks drain on a copy stream behind the next chunks' kernels; pageable y (where an
@@ -1145,12 +1550,20 @@ void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors, double c
     // does not read x); needs the canonicalised elements of ALL chunks at once (11 B each), so only below 24 GB.
     OperatorDev &od = operator_dev(op);
     if (od.stats_index != ix || od.stats_rows != dim) {
-      od.stats_elements = count_elements(od, *ix, 0, dim);
+      od.stats_elements = count_elements(od, ix->d_reps, 0, dim);
       od.stats_index = ix;
       od.stats_rows = dim;
     }
-    bool const two_phases = pinned && num_vectors == 1 && od.stats_elements > 0 &&
-                            od.stats_elements * 11 <= (int64_t(24) << 30) && getenv("LS_B200_NO_PHASED_E2E") == nullptr;
+    bool two_phases = pinned && num_vectors == 1 && od.stats_elements > 0 &&
+                      od.stats_elements * 11 <= (int64_t(24) << 30) && getenv("LS_B200_NO_PHASED_E2E") == nullptr;
+    if (two_phases && !(sc.phase_op == op && sc.phase_index == ix && !sc.phase_slots.empty())) {
+      // First phased product of this operator: the persistent buffers (11 B per element, +25 % growth slack of
+      // DeviceBuffer::reserve, + the 8 B values of the largest chunk) must fit next to everything already resident.
+      size_t free_bytes = 0, total_bytes = 0;
+      CUDA_CHECK(cudaMemGetInfo(&free_bytes, &total_bytes));
+      size_t const needed = (size_t)((double)od.stats_elements * 11.0 * 1.25) + (size_t(3) << 30);
+      if (needed > free_bytes) two_phases = false;
+    }
     if (two_phases) {
       MatvecScratch &scr = mv_scratch();
       if (scr.copy_stream == nullptr) {
@@ -1160,9 +1573,17 @@ void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors, double c
       if (scr.x_uploaded == nullptr) CUDA_CHECK(cudaEventCreateWithFlags(&scr.x_uploaded, cudaEventDisableTiming));
       CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, scr.copy_stream));
       CUDA_CHECK(cudaEventRecord(scr.x_uploaded, scr.copy_stream));
-      matvec_device(op, 0, dim, nullptr, nullptr, false, 1, 0, 0, nullptr, 1);
+      // an allocation failure inside the phased path is not fatal: release its buffers and take the chunked path
+      try {
+        matvec_device(op, 0, dim, nullptr, nullptr, false, 1, 0, 0, nullptr, 1);
+      } catch (CudaFailure const &) {
+        (void)cudaGetLastError();
+        release_phase_slots();
+        two_phases = false;
+      }
       CUDA_CHECK(cudaStreamWaitEvent(s, scr.x_uploaded, 0));
-      matvec_device(op, 0, dim, d_x, d_y, false, 1, 0, 0, y, 2);
+      if (two_phases) matvec_device(op, 0, dim, d_x, d_y, false, 1, 0, 0, y, 2);
+      else matvec_device(op, 0, dim, d_x, d_y, false, 1, dim, dim, y);
     } else {
       CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
       matvec_device(op, 0, dim, d_x, d_y, false, num_vectors, dim, dim, pinned ? y : nullptr);
@@ -1235,12 +1656,20 @@ int ls_b200_matvec_sync(void) {
   return status;
 }
 
+void ls_b200_operator_release(ls_hs_operator const *op) {
+  if (op == nullptr) return;
+  std::lock_guard<std::mutex> lock(runtime().mutex);
+  MatvecScratch &sc = mv_scratch();
+  if (sc.phase_op == op) release_phase_slots();
+  operator_cache().erase(op);
+}
+
 int64_t ls_b200_count_matrix_elements(ls_hs_operator const *op, int64_t row_begin, int64_t row_end) {
   int64_t n = -1;
   guarded(__func__, [&] {
     IndexData *ix = index_of(op->basis);
     LSB_CHECK(ix != nullptr, "basis is not built");
-    n = count_elements(operator_dev(op), *ix, row_begin, row_end);
+    n = count_elements(operator_dev(op), ix->d_reps, row_begin, row_end);
   });
   return n;
 }

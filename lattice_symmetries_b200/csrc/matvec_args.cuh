@@ -24,6 +24,8 @@ enum : int { kModeNone = 0, kModeInversion = 1, kModeGroup = 2, kModeGroupScalar
 struct MatvecArgs {
   GroupView g;
   IndexView ix;
+  uint64_t const *rows;  // representatives of the rows, rows[chunk_begin + r] (a distributed product reads its local
+                         // shard here while ix ranks against the whole basis; otherwise == ix.reps)
   TermsView off, diag;
   int mode;
   int number_idx_planes;  // ceil(log2(number of distinct characters))

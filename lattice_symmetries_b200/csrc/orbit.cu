@@ -51,7 +51,7 @@ orbit_kernel(MatvecArgs const a) {
       bool const mine = row < a.chunk_rows && q < warp_q1;
       if (!__any_sync(0xffffffffu, mine)) break;
       if (mine) {
-        uint64_t const alpha = __ldg(a.ix.reps + a.chunk_begin + row);
+        uint64_t const alpha = __ldg(a.rows + a.chunk_begin + row);
         for (int t = 0; t < T; ++t)
           if ((alpha & terms.m[t]) == terms.l[t]) {
             if (q >= warp_q0 && q < warp_q1) {
@@ -325,7 +325,7 @@ orbit_gather_kernel(__grid_constant__ MatvecArgs const a) {
       bool const mine = row < a.chunk_rows && q < warp_q1;
       if (!__any_sync(0xffffffffu, mine)) break;
       if (mine) {
-        uint64_t const alpha = __ldg(a.ix.reps + a.chunk_begin + row);
+        uint64_t const alpha = __ldg(a.rows + a.chunk_begin + row);
         for (int t = 0; t < T; ++t)
           if ((alpha & terms.m[t]) == terms.l[t]) {
             if (q >= warp_q0 && q < warp_q1) {

@@ -20,13 +20,26 @@ void Runtime::ensure() {
     throw CudaFailure{"no CUDA device available: liblattice_symmetries_b200 has no CPU fallback"};
   // One rank per GPU: honour the device already selected by the process
   // (torch.cuda.set_device / CUDA_VISIBLE_DEVICES), else LOCAL_RANK.
+  // Was a device selected on this thread already?  cudaGetDevice() says 0 either way, so ask the driver whether a
+  // context is current (cudaSetDevice binds the primary context since CUDA 12) BEFORE any runtime call creates one.
+  bool selected = false;
+  {
+    using CtxGetCurrent = int (*)(void **);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr) {
+      void *ctx = nullptr;
+      if (reinterpret_cast<CtxGetCurrent>(fn)(&ctx) == 0 && ctx != nullptr) selected = true;
+    }
+    (void)cudaGetLastError();
+  }
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   if (char const *s = getenv("LS_B200_DEVICE")) dev = atoi(s) % count;
   else if (char const *r = getenv("LOCAL_RANK")) {
-    // torchrun: nothing selected a device yet (still the default 0) -> this rank's own GPU, so that the library
-    // lands on the same device a later torch.cuda.set_device(LOCAL_RANK) picks
-    if (dev == 0 && count > 1) dev = atoi(r) % count;
+    // torchrun, and nothing selected a device on this thread yet -> this rank's own GPU, so that the library lands on
+    // the same device a later torch.cuda.set_device(LOCAL_RANK) picks.  An explicit earlier choice (device 0 included) wins.
+    if (!selected && count > 1) dev = atoi(r) % count;
   }
   CUDA_CHECK(cudaSetDevice(dev));
   device = dev;

@@ -61,9 +61,38 @@ struct IndexData {
   uint32_t *d_subtab = nullptr;
   uint2 *d_entry8 = nullptr;       // level 1 packed for the hot kernels (IndexView::entry8)
   double *d_norms = nullptr;  // state_info norms of the representatives (lazy)
+  struct DistShard *dist = nullptr;  // set when these are the LOCAL rows of a basis sharded over ranks (dist.cu); owned
 
   IndexView view() const;
   ~IndexData();
+};
+
+// A basis sharded over the ranks of a communicator (dist.cu): rank r owns the contiguous range
+// [bounds[r], bounds[r + 1]) of the globally sorted representatives -- its IndexData holds exactly those rows.
+// Replaces the hash distribution of chapel/src/StatesEnumeration.chpl:198-212.
+struct DistShard {
+  int world = 1, rank = 0;
+  int64_t dim = 0;                  // representatives over all ranks
+  std::vector<int64_t> bounds;      // [world + 1]
+  std::vector<uint64_t> splitters;  // [world] first representative of every rank (~0 for an empty rank)
+  uint64_t *d_splitters = nullptr;
+  // all-gather products: state -> GLOBAL row over the whole basis (compact keys + level 1 only, replicated on every
+  // rank) and the replicated pre-scaled vector.  nullptr: not built (does not fit, or all-to-all was asked for).
+  IndexData *global_index = nullptr;
+  double *d_xs_full = nullptr;
+  size_t xs_full_words = 0;
+  // all-to-all products: records grouped by owner, their per-owner displacements, the received records
+  struct PushBuffers *push = nullptr;
+  ~DistShard();
+};
+
+// What the rows and the lookups of a product refer to (matvec_device).  nullptr = the basis' own list for both.
+struct MvTarget {
+  IndexView index;        // ranks a representative -> position in xs
+  uint64_t const *rows;   // [number_rows] representatives of the rows of this call
+  double const *norms;    // [number_rows], or nullptr when all 1
+  int64_t number_rows;
+  double const *xs;       // replicated n_j x_j (x_j when norms == nullptr), indexed by `index`
 };
 
 // Device copies adopted from a basis build, keyed by the host pointer handed
@@ -102,6 +131,59 @@ struct OperatorDev {
   int64_t stats_elements = 0;
 };
 OperatorDev &operator_dev(ls_hs_operator const *op);
+
+// ---- entry points of matvec.cu used by the distributed drivers (dist.cu) --------------------------------------
+void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end, double const *d_x, double *d_y,
+                   bool complex_vectors, int number_vectors = 1, int64_t x_stride = 0, int64_t y_stride = 0,
+                   double *host_y = nullptr, int phase = 0, MvTarget const *target = nullptr);
+bool matvec_finish();
+extern char const *kInvalidIndexMessage;
+void launch_prescale(int64_t n, bool complex_vectors, double const *norms, double const *x, double *xs);
+int64_t count_elements(OperatorDev &od, uint64_t const *d_rows, int64_t row_begin, int64_t row_end);
+
+// Push form (all-to-all products, mirrors chapel/src/DistributedMatrixVector.chpl:545-579, 775-807): records
+// (representative, coefficient) grouped by the rank that owns the representative.
+struct PushRecord {
+  uint64_t rep;
+  double c;
+};
+struct PushBuffers {
+  DeviceBuffer<PushRecord> send, recv;
+  DeviceBuffer<uint32_t> hist, base;
+  DeviceBuffer<unsigned char> scan_tmp;
+  DeviceBuffer<unsigned long long> displs;  // [world + 1] start of every owner's records in `send`
+};
+int64_t push_chunk_rows(ls_hs_operator const *op, int64_t local_rows);
+void push_begin(ls_hs_operator const *op, IndexData const &local, double const *d_x, double *d_y);
+void push_produce(ls_hs_operator const *op, IndexData const &local, DistShard &shard, int64_t chunk_begin,
+                  int64_t chunk_rows, double const *d_x);
+void push_consume(ls_hs_operator const *op, IndexData const &local, PushRecord const *records, int64_t count,
+                  double *d_y);
+
+// ---- entry points of basis_build.cu / index.cu used by dist.cu -------------------------------------------------
+struct BuildResult {
+  uint64_t *d_reps = nullptr;
+  double *d_norms = nullptr;  // nullptr for unprojected bases
+  uint64_t count = 0;
+};
+using Ranges = std::vector<std::pair<uint64_t, uint64_t>>;
+BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<uint64_t> *counts = nullptr,
+                         bool host_visible = false);
+uint64_t number_candidates(ls_hs_basis const *basis);
+// Installs device-resident representatives (+ norms) as the basis' list: host view, index, kernels.
+void install_representatives(ls_hs_basis *basis, uint64_t *d_reps, double *d_norms, uint64_t count, int cache_bits);
+int index_choose_prefix_bits(int64_t n, int number_bits);
+void index_local_keys(uint64_t const *d_reps, int64_t n, int shift, void *d_keys, int key_bytes);
+void index_local_offsets64(uint64_t const *d_reps, int64_t n, int shift, int64_t number_offsets, int64_t *d_out);
+int index_steps_from_offsets64(int64_t const *d_offsets, int64_t number_buckets);
+IndexData *create_index_from_device(uint64_t *d_reps, int64_t count, int number_bits, int prefix_bits);
+
+// ---- entry points of dist.cu ------------------------------------------------------------------------------------------
+int comm_world();  // ranks of the active communicator (1 without one)
+bool dist_is_sharded(ls_hs_basis const *basis);
+// y_local = (H x)_local on this rank's rows; x, y device-resident, local length.  mode: 0 auto, 1 all-gather, 2 all-to-all.
+void dist_matvec_local(ls_hs_operator const *op, double const *d_x, double *d_y, int mode, bool complex_vectors);
+void dist_build_local(ls_hs_basis *basis, ls_hs_operator const *balance_for, int flags);
 
 // Basis predicates the Chapel side asks the Haskell host for
 // (haskell/src/LatticeSymmetries/Basis.hs:701-774), derived from the struct.

@@ -170,36 +170,46 @@ template <> __device__ __forceinline__ uint16_t const *index_keys<uint16_t>(Inde
 template <> __device__ __forceinline__ uint32_t const *index_keys<uint32_t>(IndexView const &ix) { return ix.lows32; }
 template <> __device__ __forceinline__ uint64_t const *index_keys<uint64_t>(IndexView const &ix) { return ix.reps; }
 
-template <class Low, int B>
+// Wide = true: the index of a basis with 2^32 or more states (level 1 = offsets64, no second level): window
+// positions stay 32-bit, relative to the 64-bit start of the needle's bucket.
+template <class Low, int B, bool Wide = false>
 __device__ __forceinline__ void index_find32(IndexView const &ix, uint64_t const (&needle)[B], bool const (&live)[B],
                                              int64_t (&found)[B]) {
   Low const *__restrict__ keys = index_keys<Low>(ix);
   uint32_t lo[B], pos[B], end[B];
+  int64_t base[B];
   Low key[B], val[B];
 #pragma unroll
   for (int u = 0; u < B; ++u) {
     uint64_t const p = needle[u] >> ix.shift;
     uint32_t l = 0, n = 0;
+    base[u] = 0;
     if (live[u] && p < ix.number_buckets) {
-      uint32_t s = 0;
-      if (ix.entry8 != nullptr) {
-        uint2 const e = __ldg(ix.entry8 + p);
-        l = e.x;
-        n = e.y;
-        s = (e.y >> 27) != 0 ? e.y : 0u;  // p2 >= 1 sits in the top five bits; plain lengths are < 2^27
+      if constexpr (Wide) {
+        int64_t const b0 = __ldg(ix.offsets64 + p);
+        base[u] = b0;
+        n = (uint32_t)(__ldg(ix.offsets64 + p + 1) - b0);
       } else {
-        l = __ldg(ix.offsets32 + p);
-        n = __ldg(ix.offsets32 + p + 1) - l;
-        s = ix.sub_info != nullptr ? __ldg(ix.sub_info + p) : 0u;
-      }
-      if (s != 0) {
-        int const p2 = (int)(s >> 27);
-        uint32_t const k2 = (uint32_t)(needle[u] >> (ix.shift - p2)) & ((1u << p2) - 1u);
-        uint32_t const *t = ix.subtab + (size_t)(s & 0x7ffffffu) * 8 + k2;
-        uint32_t const v = __ldg(t);
-        n = v & 63u;
-        if (n == 63u) n = (__ldg(t + 1) >> 6) - (v >> 6);
-        l += v >> 6;
+        uint32_t s = 0;
+        if (ix.entry8 != nullptr) {
+          uint2 const e = __ldg(ix.entry8 + p);
+          l = e.x;
+          n = e.y;
+          s = (e.y >> 27) != 0 ? e.y : 0u;  // p2 >= 1 sits in the top five bits; plain lengths are < 2^27
+        } else {
+          l = __ldg(ix.offsets32 + p);
+          n = __ldg(ix.offsets32 + p + 1) - l;
+          s = ix.sub_info != nullptr ? __ldg(ix.sub_info + p) : 0u;
+        }
+        if (s != 0) {
+          int const p2 = (int)(s >> 27);
+          uint32_t const k2 = (uint32_t)(needle[u] >> (ix.shift - p2)) & ((1u << p2) - 1u);
+          uint32_t const *t = ix.subtab + (size_t)(s & 0x7ffffffu) * 8 + k2;
+          uint32_t const v = __ldg(t);
+          n = v & 63u;
+          if (n == 63u) n = (__ldg(t + 1) >> 6) - (v >> 6);
+          l += v >> 6;
+        }
       }
     }
     lo[u] = pos[u] = l;
@@ -213,7 +223,7 @@ __device__ __forceinline__ void index_find32(IndexView const &ix, uint64_t const
     for (int u = 0; u < B; ++u) {
       uint32_t const cand = pos[u] + s;
       if (cand <= end[u]) {
-        Low const v = __ldg(keys + (cand - 1));
+        Low const v = Wide ? __ldg(keys + base[u] + (cand - 1)) : __ldg(keys + (cand - 1));
         if (v <= key[u]) {
           pos[u] = cand;
           val[u] = v;
@@ -222,7 +232,9 @@ __device__ __forceinline__ void index_find32(IndexView const &ix, uint64_t const
     }
   }
 #pragma unroll
-  for (int u = 0; u < B; ++u) found[u] = (pos[u] > lo[u] && val[u] == key[u]) ? (int64_t)(pos[u] - 1) : (int64_t)-1;
+  for (int u = 0; u < B; ++u)
+    found[u] = (pos[u] > lo[u] && val[u] == key[u]) ? (Wide ? base[u] + (int64_t)(pos[u] - 1) : (int64_t)(pos[u] - 1))
+                                                    : (int64_t)-1;
 }
 
 __device__ __forceinline__ int64_t state_index(IndexView const &ix, uint64_t needle) {

@@ -1,41 +1,47 @@
-"""Multi-GPU sharding of the two hot paths: one process per GPU, ``torch.distributed``
-for the plumbing (NCCL over NVLink on the GPUs, gloo in the CPU tests).
+"""Several GPUs of one node: one process per GPU, the sharding itself lives INSIDE the C library
+(csrc/dist.cu) behind the reference's own entry points.
 
 The reference distributes basis states over Chapel locales by *hash*
-(chapel/src/StatesEnumeration.chpl:198-212) and pushes (state, coefficient)
-pairs to their owners through GASNet PUTs
-(chapel/src/DistributedMatrixVector.chpl:226-339, :545-579).  Here:
+(chapel/src/StatesEnumeration.chpl:198-212) and pushes (state, coefficient) pairs to their owners through
+GASNet PUTs (chapel/src/DistributedMatrixVector.chpl:226-339, :545-579); each locale then works on its own
+block of the representatives and of x / y (:1060-1088).  Here a rank owns a *contiguous range of the sorted
+representatives*; once ``init_communicator`` has run,
 
-* **basis build** -- candidates are addressed by their combinadic index, rank r
-  scans the contiguous index range ``shard_bounds(total, P, r)``; the shards are
-  already globally ordered, so assembling the basis is one all-gather of the
-  counts plus one broadcast of every shard into its slot of the full array.  No
-  collective on the data path of the scan itself.
-* **matvec** -- rows (= contiguous ranges of sorted representatives) are split
-  evenly; the pull-form kernel writes only its own rows, so the single exchange
-  step is the all-gather of the x shards (``all_gather_into_tensor`` straight
-  into the replicated, padded vector).  y needs no reduction.
+* ``basis.build()`` (= ``ls_hs_build_representatives``) scans this rank's blocks of the candidate range and
+  one all-to-all-v leaves every rank with its range -- ``basis.states`` is the local block;
+* ``operator.apply_to_state_vector`` (= ``ls_chpl_matrix_vector_product``) takes the local blocks of x and y;
+* :class:`DistributedOperator` is the same product with device-resident local vectors, in either form:
+  *all-gather* (compact keys of the whole basis + the pre-scaled vector replicated, pull-form kernels) or
+  *all-to-all* ((representative, coefficient) records grouped by owner, mirroring the Chapel design).
 
-The exchange logic below is independent of where the shard was computed: it
-takes tensors (CPU or CUDA), so the world_size-2 gloo tests drive it with
-shards produced on the CPU.
+``torch.distributed`` is only plumbing here: it carries the 128-byte NCCL id to the other ranks; the
+collectives on the data path are issued by the library on its own communicator and stream.
+
+:class:`EmulatedRanks` drives the same code for ``world`` *virtual* ranks on one GPU (device-to-device
+copies in place of NCCL) -- that is how the single-GPU test tier covers the multi-rank algorithms.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["shard_bounds", "block_plan", "row_bounds", "balanced_row_bounds", "exchange_shards", "exchange_blocks",
-           "ShardedOperator",
-           "build_sharded", "init_process"]
+__all__ = [
+    "shard_bounds", "row_bounds", "plan_blocks", "plan_redistribution", "even_bounds", "balanced_bounds",
+    "init_process", "init_communicator", "Layout", "build_distributed", "DistributedOperator", "EmulatedRanks",
+    "hashed_vector", "ALLGATHER", "ALLTOALL", "AUTO", "NO_GLOBAL_INDEX", "WIDE_INDEX", "NO_BALANCE",
+]
 
 ALIGN = 32  # candidate shards start on a multiple of 32 (one bit-sliced word)
+AUTO, ALLGATHER, ALLTOALL = 0, 1, 2                    # product forms (ls_b200_dist_matvec ``mode``)
+NO_GLOBAL_INDEX, WIDE_INDEX, NO_BALANCE = 1, 2, 4      # build flags (ls_b200_dist_build ``flags``)
 
 
+# ---- pure planning (host) ----------------------------------------------------------------------------
 def shard_bounds(total: int, world: int, rank: int, align: int = ALIGN) -> Tuple[int, int]:
-    """Contiguous candidate-index range of ``rank``: boundaries are multiples of
+    """Contiguous candidate-index range of ``rank`` for ``ls_b200_build_shard``: boundaries are multiples of
     ``align``, sizes differ by at most ``align``, the union is [0, total)."""
     words = (total + align - 1) // align
     lo = (words * rank) // world * align
@@ -43,111 +49,77 @@ def shard_bounds(total: int, world: int, rank: int, align: int = ALIGN) -> Tuple
     return min(lo, total), min(hi, total)
 
 
-def block_plan(total: int, world: int, blocks_per_rank: int = 16, min_block: int = 1 << 22,
-               align: int = ALIGN) -> List[Tuple[int, int]]:
-    """Block-cyclic split of the candidate-index range [0, total): block b = [lo, hi) belongs to rank
-    b % world.  Representatives -- and the work of finding them -- are NOT uniform in the candidate
-    index: a representative is the smallest member of its orbit, so they crowd into the low indices
-    (kagome-36 on two ranks: the lower half holds all 3.15e7 of them and 3/4 of the work).  Dealing
-    out ~16 blocks per rank evens that out while every block still yields a sorted range."""
-    if total <= 0:
-        return []
-    size = max(min_block, -(-total // (world * blocks_per_rank)))
-    size = -(-size // align) * align
-    return [(lo, min(lo + size, total)) for lo in range(0, total, size)]
-
-
 def row_bounds(dim: int, world: int, rank: int) -> Tuple[int, int, int]:
-    """Even row split with a fixed chunk = ceil(dim / world): returns
-    (row_begin, row_end, chunk).  Trailing ranks may own fewer (or zero) rows;
-    the replicated vector is padded to world * chunk."""
+    """Even row split with a fixed chunk = ceil(dim / world): (row_begin, row_end, chunk)."""
     chunk = (dim + world - 1) // world if dim > 0 else 0
     lo = min(rank * chunk, dim)
     hi = min((rank + 1) * chunk, dim)
     return lo, hi, chunk
 
 
-def exchange_shards(local, group=None):
-    """All ranks contribute a 1-D tensor (their shard, possibly empty); every rank
-    receives (full, offsets) where ``full`` is the concatenation in rank order and
-    ``offsets[r]`` the start of rank r's shard.  Works on CPU (gloo) and CUDA (NCCL)."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    count = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
-    counts = torch.zeros(world, dtype=torch.int64, device=local.device)
-    dist.all_gather_into_tensor(counts, count, group=group)
-    counts = counts.cpu().tolist()
-    offsets = [0]
-    for c in counts:
-        offsets.append(offsets[-1] + int(c))
-    full = torch.empty(offsets[-1], dtype=local.dtype, device=local.device)
-    rank = dist.get_rank(group)
-    full[offsets[rank]:offsets[rank + 1]].copy_(local)
-    for r in range(world):
-        if counts[r] > 0:
-            src = dist.get_global_rank(group, r) if group is not None else r
-            dist.broadcast(full[offsets[r]:offsets[r + 1]], src=src, group=group)
-    return full, offsets
+def even_bounds(dim: int, world: int) -> List[int]:
+    """Row boundaries of the sharded basis before balancing: rank r owns [b[r], b[r+1])."""
+    return [(dim * r) // world for r in range(world + 1)]
 
 
-def exchange_blocks(pieces, number_blocks: int, group=None, dtype=None, device=None):
-    """Block-cyclic counterpart of ``exchange_shards``: ``pieces`` are this rank's blocks (block
-    b = rank + k * world for k = 0, 1, ...) as 1-D tensors, each sorted; every rank receives the
-    concatenation of ALL blocks in block order plus the block offsets."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    if pieces:
-        local = torch.cat(pieces) if len(pieces) > 1 else pieces[0]
-    else:
-        local = torch.empty(0, dtype=dtype, device=device)
-    per_rank = (number_blocks + world - 1) // world
-    mine = torch.zeros(max(per_rank, 1), dtype=torch.int64, device=local.device)
-    for k, piece in enumerate(pieces):
-        mine[k] = piece.numel()
-    counts = torch.zeros(world * max(per_rank, 1), dtype=torch.int64, device=local.device)
-    dist.all_gather_into_tensor(counts, mine, group=group)
-    counts = counts.cpu().view(world, max(per_rank, 1))
-    full, rank_offsets = exchange_shards(local, group)
-    out = torch.empty_like(full)
-    block_offsets = [0]
-    within = [0] * world
-    for b in range(number_blocks):
-        r, k = b % world, b // world
-        n = int(counts[r, k])
-        src = rank_offsets[r] + within[r]
-        out[block_offsets[-1]:block_offsets[-1] + n].copy_(full[src:src + n])
-        within[r] += n
-        block_offsets.append(block_offsets[-1] + n)
-    return out, block_offsets
+def plan_blocks(total: int, world: int) -> List[Tuple[int, int]]:
+    """Blocks of the candidate-index range, block b scanned by rank b % world (csrc/dist.cu ``dist_block_plan``:
+    small blocks first -- representatives crowd into the low indices -- doubling every 8 * world blocks)."""
+    from ._lib import lib
+    n = int(lib.ls_b200_plan_blocks(int(total), int(world), None, None, 0))
+    begins = (C.c_uint64 * max(n, 1))()
+    ends = (C.c_uint64 * max(n, 1))()
+    lib.ls_b200_plan_blocks(int(total), int(world), begins, ends, n)
+    return [(int(begins[i]), int(ends[i])) for i in range(n)]
 
 
-# ---- CUDA side ---------------------------------------------------------------------------
-class _RawDevice:
-    """Zero-copy view of a raw device pointer for ``torch.as_tensor``."""
-
-    def __init__(self, ptr: int, count: int, typestr: str):
-        self.__cuda_array_interface__ = {
-            "shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None}
-
-
-def tensor_from_pointer(ptr: int, count: int, dtype: str):
-    """dtype: 'u8' (uint64 viewed as int64, NCCL has no uint64 arithmetic but moves bytes) or 'f8'."""
-    import torch
-    if count == 0:
-        return torch.empty(0, dtype=torch.int64 if dtype == "u8" else torch.float64, device="cuda")
-    typestr = "<i8" if dtype == "u8" else "<f8"
-    return torch.as_tensor(_RawDevice(ptr, count, typestr), device="cuda")
+@dataclass
+class RedistributionPlan:
+    scount: np.ndarray
+    sdispl: np.ndarray
+    rcount: np.ndarray
+    rdispl: np.ndarray
+    places: np.ndarray  # [k, 3]: (offset in the receive buffer, local row, length)
 
 
+def plan_redistribution(world: int, me: int, lengths: Sequence[int], owners: Sequence[int],
+                        bounds: Sequence[int]) -> RedistributionPlan:
+    """All-to-all-v plan of rank ``me`` that turns sorted pieces (``lengths[i]`` rows held by ``owners[i]``, in
+    ascending order) into contiguous row ranges ``bounds`` (csrc/dist.cu ``plan_redistribution``)."""
+    from ._lib import lib, i64_p
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    owners = np.ascontiguousarray(owners, dtype=np.int32)
+    bounds = np.ascontiguousarray(bounds, dtype=np.int64)
+    out = [np.zeros(world, dtype=np.int64) for _ in range(4)]
+    capacity = len(lengths) + world + 1
+    places = np.zeros((capacity, 3), dtype=np.int64)
+    n = int(lib.ls_b200_plan_redistribution(
+        world, me, len(lengths), lengths.ctypes.data_as(i64_p), owners.ctypes.data_as(C.POINTER(C.c_int32)),
+        bounds.ctypes.data_as(i64_p), *[o.ctypes.data_as(i64_p) for o in out], places.ctypes.data_as(i64_p), capacity))
+    if n < 0:
+        raise RuntimeError("ls_b200_plan_redistribution: place table too small")
+    return RedistributionPlan(*out, places[:n].copy())
+
+
+def balanced_bounds(edges: Sequence[int], costs: Sequence[float], world: int) -> List[int]:
+    """Contiguous row ranges of (nearly) equal cost; ``costs[b]`` is the cost of rows [edges[b], edges[b+1])."""
+    from ._lib import lib, i64_p, f64_p
+    edges = np.ascontiguousarray(edges, dtype=np.int64)
+    costs = np.ascontiguousarray(costs, dtype=np.float64)
+    assert len(edges) == len(costs) + 1
+    out = np.zeros(world + 1, dtype=np.int64)
+    lib.ls_b200_plan_balanced_bounds(len(costs), edges.ctypes.data_as(i64_p), costs.ctypes.data_as(f64_p), world,
+                                     out.ctypes.data_as(i64_p))
+    return [int(b) for b in out]
+
+
+# ---- process set-up ------------------------------------------------------------------------------------
 _stream = None
 
 
 def init_process(local_rank: Optional[int] = None):
-    """Select this rank's GPU and order all library work on a dedicated torch
-    stream, so that NCCL collectives and our kernels interleave without host syncs."""
+    """Select this rank's GPU and order all library work on a dedicated torch stream, so that torch's vector
+    algebra and the library's kernels / collectives interleave without host syncs."""
     import os
     import torch
     from . import _lib
@@ -164,209 +136,203 @@ def init_process(local_rank: Optional[int] = None):
     return _stream
 
 
-def build_sharded(basis, group=None) -> List[int]:
-    """Build ``basis`` across the ranks of ``group``: every rank scans its blocks of the candidate
-    range (``block_plan``: block-cyclic, because the work is concentrated at low indices) on its own
-    GPU, the pieces are exchanged over NCCL and the full sorted representative list (+ norms) is
-    installed on every rank.  Returns the block offsets into the representative list."""
-    import torch
+def init_communicator(group=None) -> Tuple[int, int]:
+    """Create the library's own NCCL communicator over the ranks of the (already initialised)
+    ``torch.distributed`` group: rank 0 draws the id, ``torch.distributed`` carries its 128 bytes -- nothing
+    else.  Returns (world, rank).  A single process needs no communicator."""
     import torch.distributed as dist
     from . import _lib
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    total = basis.number_candidates
-    plan = block_plan(total, world)
-    reps, norms = [], []
-    with_norms = basis.has_permutation_symmetries
-    mine = plan[rank::world]
-    d_reps = d_norms = 0
-    if mine:
-        size = plan[0][1] - plan[0][0]
-        d_reps, d_norms, counts = basis.build_blocks(mine[0][0], size, size * world, len(mine))
-        all_reps = tensor_from_pointer(d_reps, sum(counts), "u8")
-        all_norms = tensor_from_pointer(d_norms, sum(counts), "f8") if with_norms else None
-        start = 0
-        for c in counts:
-            reps.append(all_reps[start:start + c])
-            if with_norms:
-                norms.append(all_norms[start:start + c])
-            start += c
-    raw = [(d_reps, d_norms)]
-    full_reps, offsets = exchange_blocks(reps, len(plan), group, dtype=torch.int64, device="cuda")
-    dim = offsets[-1]
-    # the library takes ownership of buffers it allocated itself
-    own_reps = _lib.lib.ls_b200_device_malloc(max(8 * dim, 8))
-    tensor_from_pointer(own_reps, dim, "u8").copy_(full_reps)
-    own_norms = None
-    if with_norms:
-        full_norms, _ = exchange_blocks(norms, len(plan), group, dtype=torch.float64, device="cuda")
-        own_norms = _lib.lib.ls_b200_device_malloc(max(8 * dim, 8))
-        tensor_from_pointer(own_norms, dim, "f8").copy_(full_norms)
-    torch.cuda.current_stream().synchronize()
-    for d_reps, d_norms in raw:
-        if d_reps:
-            _lib.lib.ls_b200_device_free(d_reps)
-        if d_norms:
-            _lib.lib.ls_b200_device_free(d_norms)
-    basis.set_representatives_device(own_reps, own_norms, dim)
-    return offsets
+    if not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return 1, 0
+    if _lib.lib.ls_b200_comm_size() == world:
+        return world, rank
+    blob = [None]
+    if rank == 0:
+        buf = (C.c_ubyte * 128)()
+        if _lib.lib.ls_b200_comm_unique_id(buf, 128) != 0:
+            _lib.check_error()
+            raise RuntimeError("ls_b200_comm_unique_id failed")
+        blob[0] = bytes(buf)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast_object_list(blob, src=src, group=group)
+    raw = (C.c_ubyte * 128).from_buffer_copy(blob[0])
+    status = _lib.lib.ls_b200_comm_init(world, rank, raw)
+    _lib.check_error()
+    if status != 0:
+        raise RuntimeError("ls_b200_comm_init failed")
+    return world, rank
 
 
+# ---- the sharded basis ------------------------------------------------------------------------------------
 @dataclass
-class _Layout:
-    dim: int
+class Layout:
     world: int
     rank: int
-    row_begin: int
+    dim: int            # representatives over all ranks
+    row_begin: int      # this rank owns rows [row_begin, row_end) of the globally sorted list
     row_end: int
-    chunk: int                      # rows of the largest shard: the all-gather slot size
-    bounds: Optional[list] = None   # (row_begin, row_end) of every rank; None: the even split of row_bounds
+    global_index: int   # replicated index of the all-gather form: 0 none, 1 two-level, 2 wide (compact keys only)
+    search_steps: int
+    prefix_bits: int
+    bounds: List[int]
+
+    @property
+    def rows(self) -> int:
+        return self.row_end - self.row_begin
 
 
-def balanced_row_bounds(block_costs, block_rows: int, dim: int, world: int):
-    """Contiguous row ranges of (nearly) equal cost from per-block costs (block b = rows
-    [b block_rows, (b + 1) block_rows)): rank r ends at the first block boundary where the running
-    cost reaches (r + 1) / world of the total.  Rows of the sorted basis do not cost the same -- on
-    kagome-36 the first eighth of the rows holds 0.87x, the last 1.12x the mean number of matrix
-    elements -- and a step is as slow as its slowest rank."""
-    total = float(sum(block_costs))
-    bounds, lo, acc, b = [], 0, 0.0, 0
-    for r in range(world):
-        target = total * (r + 1) / world
-        while b < len(block_costs) and (acc + block_costs[b] <= target or r == world - 1):
-            acc += block_costs[b]
-            b += 1
-        # take the block that straddles the target if that lands closer to it
-        if r < world - 1 and b < len(block_costs) and target - acc > acc + block_costs[b] - target:
-            acc += block_costs[b]
-            b += 1
-        hi = dim if r == world - 1 else min(dim, b * block_rows)
-        bounds.append((lo, max(lo, hi)))
-        lo = max(lo, hi)
-    return bounds
+def layout_of(basis) -> Layout:
+    from ._lib import lib
+    out = (C.c_int64 * 8)()
+    if lib.ls_b200_dist_info(C.byref(basis._payload), out) != 0:
+        raise ValueError("the basis is not sharded (build it with build_distributed, or under init_communicator)")
+    world = int(out[0])
+    b = (C.c_int64 * (world + 1))()
+    lib.ls_b200_dist_bounds(C.byref(basis._payload), b, world + 1)
+    return Layout(world, int(out[1]), int(out[2]), int(out[3]), int(out[4]), int(out[5]), int(out[6]), int(out[7]),
+                  [int(v) for v in b])
 
 
-class ShardedOperator:
-    """y = H x with rows sharded over the ranks and x replicated by all-gather.
+def build_distributed(basis, balance_for=None, flags: int = 0) -> Layout:
+    """``ls_b200_dist_build``: the sharded build with its options spelled out (``basis.build()`` under an active
+    communicator is the same with the defaults).  ``balance_for``: an Operator on this basis; rows are then
+    split by its matrix-element count instead of evenly."""
+    from . import _lib
+    op = C.byref(balance_for._payload) if balance_for is not None else None
+    status = _lib.lib.ls_b200_dist_build(C.byref(basis._payload), op, int(flags))
+    _lib.check_error()
+    if status != 0:
+        raise RuntimeError("ls_b200_dist_build failed")
+    return layout_of(basis)
 
-    ``x_full`` is a padded replicated vector of length world * chunk; ``matvec``
-    computes this rank's rows into its slot of ``y_full`` and all-gathers in
-    place, so the output can be fed straight back in (Lanczos)."""
+
+def _as_int64(v: int) -> int:
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def hashed_vector(row_begin: int, row_end: int, seed: int = 42, device="cuda"):
+    """Deterministic pseudo-random vector entries in (-1, 1) that depend only on (seed, GLOBAL row): every rank
+    fills its own rows, and the vector is the same for any number of ranks.  (A start vector for Lanczos on a
+    basis whose full length -- 9.6e9 for kagome-42 -- no single host could draw.)"""
+    import torch
+    out = torch.empty(row_end - row_begin, dtype=torch.float64, device=device)
+    chunk = 1 << 25
+    for lo in range(row_begin, row_end, chunk):
+        hi = min(row_end, lo + chunk)
+        z = torch.arange(lo, hi, dtype=torch.int64, device=device)
+        z = z + _as_int64((seed + 1) * 0x9E3779B97F4A7C15)      # splitmix64: golden-ratio increment, then the finaliser
+        z = (z ^ ((z >> 30) & 0x3FFFFFFFF)) * -4658895280553007687      # 0xBF58476D1CE4E5B9
+        z = (z ^ ((z >> 27) & 0x1FFFFFFFFF)) * -7723592293110705685     # 0x94D049BB133111EB
+        z = z ^ ((z >> 31) & 0x1FFFFFFFF)
+        out[lo - row_begin:hi - row_begin] = (z >> 11).to(torch.float64) * (1.0 / (1 << 52))
+    return out
+
+
+class DistributedOperator:
+    """y_local = (H x)_local on a sharded basis, vectors device-resident (torch tensors of local length)."""
 
     device = "cuda"
 
-    def __init__(self, operator, group=None, dim: Optional[int] = None, bounds=None, balance: bool = True):
-        """``bounds``: explicit (row_begin, row_end) per rank; otherwise, with an operator and ``balance``, the
-        rows are split by matrix-element count (every rank computes the same split from the replicated basis),
-        else evenly."""
-        import torch.distributed as dist
+    def __init__(self, operator, mode: int = AUTO):
         self.op = operator
-        self.group = group
-        if dim is None:
-            dim = operator.basis.number_states
-        world = dist.get_world_size(group) if dist.is_initialized() else 1
-        rank = dist.get_rank(group) if dist.is_initialized() else 0
-        if bounds is None and balance and operator is not None and world > 1 and dim >= 4096 * world:
-            blocks = 64 * world
-            block_rows = -(-dim // blocks)
-            costs = []
-            for b in range(blocks):
-                lo_b, hi_b = min(b * block_rows, dim), min((b + 1) * block_rows, dim)
-                # 4 row-proportional units (alpha, norm, x, y traffic and the term scan) per row on top of its elements
-                costs.append(operator.count_matrix_elements(lo_b, hi_b) + 4 * (hi_b - lo_b) if hi_b > lo_b else 0)
-            bounds = balanced_row_bounds(costs, block_rows, dim, world)
-        if bounds is not None:
-            bounds = [(int(a), int(b)) for a, b in bounds]
-            assert len(bounds) == world and bounds[0][0] == 0 and bounds[-1][1] == dim
-            assert all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
-            chunk = max(hi - lo for lo, hi in bounds)
-            even = [row_bounds(dim, world, r)[:2] for r in range(world)]
-            if [tuple(b) for b in bounds] == [tuple(e) for e in even]:
-                bounds = None
-        if bounds is None:
-            lo, hi, chunk = row_bounds(dim, world, rank)
-        else:
-            lo, hi = bounds[rank]
-        self.layout = _Layout(dim, world, rank, lo, hi, chunk, bounds)
-        self._gather_buffers = {}
+        self.mode = mode
+        self.layout = layout_of(operator.basis)
 
     def empty_vector(self, dtype=None):
         import torch
-        L = self.layout
-        return torch.zeros(L.world * L.chunk, dtype=dtype or torch.float64, device=self.device)
+        return torch.zeros(self.layout.rows, dtype=dtype or torch.float64, device=self.device)
 
-    def local_rows(self, v):
-        L = self.layout
-        return v[L.row_begin:L.row_end]
-
-    def matvec(self, x_full, y_full, gather: bool = True) -> None:
+    def matvec(self, x_local, y_local, mode: Optional[int] = None) -> None:
+        """Asynchronous on the library stream (= torch's current stream after ``init_process``)."""
         import torch
-        import torch.distributed as dist
-        L = self.layout
-        cplx = x_full.dtype == torch.complex128
-        if L.row_end > L.row_begin:
-            self._local_rows(x_full, y_full, L.row_begin, L.row_end, cplx)
-        if gather and L.world > 1:
-            # While NCCL replicates y: canonicalise the matrix elements for the NEXT product (they do not depend
-            # on the vector).  Every product still runs both phases exactly once.
-            self.gather_rows(y_full, overlap=(lambda: self._prepare_rows(L.row_begin, L.row_end, cplx))
-                             if L.row_end > L.row_begin else None)
-
-    def gather_rows(self, v_full, overlap=None) -> None:
-        """Replicate every rank's rows of ``v_full`` on all ranks (one all-gather); ``overlap`` is called while
-        the collective is in flight."""
-        import torch
-        import torch.distributed as dist
-        L = self.layout
-        if L.world == 1:
-            return
-        real = (lambda t: torch.view_as_real(t)) if v_full.dtype == torch.complex128 else (lambda t: t)
-        if L.bounds is None:
-            # even split: rank r's rows already sit in slot r of the padded vector -- gather in place
-            mine = v_full[L.rank * L.chunk:(L.rank + 1) * L.chunk]
-            work = dist.all_gather_into_tensor(real(v_full), real(mine), group=self.group, async_op=True)
-            if overlap is not None:
-                overlap()
-            work.wait()
-            return
-        # balanced (uneven) split: gather fixed-size slots into a side buffer, then copy the other ranks' rows home
-        key = (v_full.dtype, v_full.device)
-        buf = self._gather_buffers.get(key)
-        if buf is None:
-            buf = torch.zeros(L.world * L.chunk, dtype=v_full.dtype, device=v_full.device)
-            self._gather_buffers[key] = buf
-        mine = buf[L.rank * L.chunk:(L.rank + 1) * L.chunk]
-        mine[:L.row_end - L.row_begin].copy_(v_full[L.row_begin:L.row_end])
-        work = dist.all_gather_into_tensor(real(buf), real(mine), group=self.group, async_op=True)
-        if overlap is not None:
-            overlap()
-        work.wait()
-        for r, (lo, hi) in enumerate(L.bounds):
-            if r != L.rank and hi > lo:
-                v_full[lo:hi].copy_(buf[r * L.chunk:r * L.chunk + (hi - lo)])
-
-    def _local_rows(self, x_full, y_full, row_begin: int, row_end: int, cplx: bool) -> None:
-        """y_full[row_begin:row_end] = (H x)[row_begin:row_end] on this rank's GPU."""
-        y_ptr = y_full.data_ptr() + row_begin * y_full.element_size()
-        if self.layout.world > 1:
-            # phase 2 (phase 1 ran during the previous all-gather, or runs now on the first call)
-            self.op.matvec_device_phase(2, x_full.data_ptr(), y_ptr, row_begin, row_end, complex_vectors=cplx)
+        from . import _lib
+        assert x_local.numel() == self.layout.rows and y_local.numel() == self.layout.rows
+        m = self.mode if mode is None else mode
+        if x_local.dtype == torch.complex128:
+            status = _lib.lib.ls_b200_dist_matvec_c128(C.byref(self.op._payload), x_local.data_ptr(), y_local.data_ptr(), m)
         else:
-            self.op.matvec_device(x_full.data_ptr(), y_ptr, row_begin, row_end, complex_vectors=cplx)
+            status = _lib.lib.ls_b200_dist_matvec(C.byref(self.op._payload), x_local.data_ptr(), y_local.data_ptr(), m)
+        _lib.check_error()
+        if status != 0:
+            raise RuntimeError("ls_b200_dist_matvec failed")
 
-    def _prepare_rows(self, row_begin: int, row_end: int, cplx: bool) -> None:
-        """Work of the next product that does not depend on the vector (overridable; no-op without an operator)."""
-        if self.op is not None:
-            self.op.matvec_device_phase(1, 0, 0, row_begin, row_end, complex_vectors=cplx)
+    def sync(self) -> None:
+        from . import _lib
+        _lib.lib.ls_b200_matvec_sync()
+        _lib.check_error()
 
-    def dot(self, a_full, b_full):
-        """Global <a, b> from the local rows (one all-reduce of a scalar)."""
+    def dot(self, a_local, b_local):
+        """Global <a, b> as a 1-element DEVICE tensor: local dot + one in-place all-reduce on the library's
+        communicator and stream -- no host round trip."""
         import torch
-        import torch.distributed as dist
-        s = torch.vdot(self.local_rows(a_full), self.local_rows(b_full)).reshape(1)
+        from . import _lib
+        s = torch.vdot(a_local, b_local).reshape(1)
         if self.layout.world > 1:
-            if s.dtype == torch.complex128:
-                dist.all_reduce(torch.view_as_real(s), group=self.group)
-            else:
-                dist.all_reduce(s, group=self.group)
+            words = 2 if s.dtype == torch.complex128 else 1
+            view = torch.view_as_real(s) if words == 2 else s
+            _lib.lib.ls_b200_comm_allreduce_f64(view.data_ptr(), words)
+            _lib.check_error()
         return s
+
+
+# ---- virtual ranks on one GPU -----------------------------------------------------------------------------------
+class EmulatedRanks:
+    """``world`` virtual ranks of a sharded basis on the current GPU (``ls_b200_emu_build`` /
+    ``ls_b200_emu_matvec``): the sharded build, the row balancing, both product forms and the wide index run
+    exactly as across processes, with device-to-device copies in place of the NCCL collectives."""
+
+    def __init__(self, make_basis, make_operator, world: int, flags: int = 0, balance: bool = False):
+        """``make_basis()`` -> a fresh (unbuilt) Basis, ``make_operator(basis)`` -> an Operator on it; called once per
+        virtual rank."""
+        from . import _lib
+        self.world = world
+        self.bases = [make_basis() for _ in range(world)]
+        self.ops = [make_operator(b) for b in self.bases]
+        bases = (C.c_void_p * world)(*[C.addressof(b._payload) for b in self.bases])
+        ops = (C.c_void_p * world)(*[C.addressof(o._payload) for o in self.ops])
+        status = _lib.lib.ls_b200_emu_build(bases, ops if balance else None, world, int(flags))
+        _lib.check_error()
+        if status != 0:
+            raise RuntimeError("ls_b200_emu_build failed")
+        self.layouts = [layout_of(b) for b in self.bases]
+        self._ops_array = ops
+
+    @classmethod
+    def from_model(cls, model, world: int, flags: int = 0, balance: bool = False) -> "EmulatedRanks":
+        return cls(model.basis, model.operator, world, flags, balance)
+
+    @property
+    def dim(self) -> int:
+        return self.layouts[0].dim
+
+    def states(self) -> np.ndarray:
+        """The concatenation of the local blocks (== the sorted representatives of the whole basis)."""
+        return np.concatenate([np.asarray(b.states) for b in self.bases]) if self.dim else np.zeros(0, np.uint64)
+
+    def matvec(self, x: np.ndarray, mode: int = AUTO) -> np.ndarray:
+        """y = H x for a full-length host vector: cut into the ranks' blocks, one product, reassembled."""
+        from . import _lib
+        cplx = np.iscomplexobj(x)
+        dt = np.complex128 if cplx else np.float64
+        x = np.ascontiguousarray(x, dtype=dt)
+        xs, ys = [], []
+        for L in self.layouts:
+            xs.append(_lib.DeviceArray.from_numpy(x[L.row_begin:L.row_end]) if L.rows else _lib.DeviceArray(1, dt))
+            ys.append(_lib.DeviceArray(max(L.rows, 1), dt))
+        xp = (C.c_void_p * self.world)(*[a.ptr for a in xs])
+        yp = (C.c_void_p * self.world)(*[a.ptr for a in ys])
+        status = _lib.lib.ls_b200_emu_matvec(self._ops_array, self.world, xp, yp, int(mode), 1 if cplx else 0)
+        _lib.check_error()
+        if status != 0:
+            raise RuntimeError("ls_b200_emu_matvec failed")
+        _lib.lib.ls_b200_matvec_sync()
+        _lib.check_error()
+        out = np.zeros(self.dim, dtype=dt)
+        for L, a in zip(self.layouts, ys):
+            if L.rows:
+                out[L.row_begin:L.row_end] = a.numpy()[:L.rows]
+        return out

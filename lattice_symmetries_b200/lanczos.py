@@ -1,17 +1,19 @@
-"""Ground state by Lanczos iteration with all vectors resident in HBM.
+"""Eigensolvers with all vectors resident in HBM.
 
-The reference delegates the eigensolve to scipy's ``eigsh``
-(python/example/getting_started.py:49) or PRIMME (chapel/src/Diagonalize.chpl:
-134-162, 298-325); both bounce every Lanczos vector through the host.  Here the
-three-term recurrence keeps its vectors on the GPU(s): the matvec is the
-library's device entry point (``ls_b200_matvec_device``), the vector algebra is
-torch on the same stream (plumbing), the global dots are one all-reduce of a
-scalar, and only the tridiagonal coefficients reach the host.
+The reference delegates the eigensolve to scipy's ``eigsh`` (python/example/getting_started.py:49) or PRIMME
+(chapel/src/Diagonalize.chpl:134-162, 166-177 ``numEvals``, 293-325); both bounce every Lanczos vector through
+the host.  Here the vectors never leave the GPU(s):
 
-No re-orthogonalisation: ghost copies do not disturb the extremal eigenvalue.
-The eigenvector, when requested, is accumulated in a second pass that replays
-the recurrence from the same start vector (two-pass Lanczos: 3 vectors of HBM
-instead of one per iteration).
+* :func:`lanczos_ground_state` -- three-term recurrence on three local vectors (the only option for kagome-42,
+  whose vectors are 9.6 GB per rank).  The recurrence coefficients stay ON THE DEVICE: alpha and beta are
+  1-element tensors produced by a local dot + one in-place all-reduce on the library's communicator, consumed
+  by ``addcmul_`` / ``div_`` without ever being read -- the host only looks at the tridiagonal matrix every
+  ``check_every`` iterations, so the launch queue never drains.
+* :func:`lanczos_thick_restart` -- k lowest eigenpairs with a bounded Krylov basis (m vectors in HBM), full
+  re-orthogonalisation inside the basis and Wu-Simon thick restarts; real or complex128 vectors.
+
+Both run on one GPU (an ``Operator``) or on a rank's row block of a sharded basis
+(:class:`distributed.DistributedOperator`); the matvec is the library's device entry point either way.
 """
 from __future__ import annotations
 
@@ -20,7 +22,7 @@ from typing import Optional
 
 import numpy as np
 
-__all__ = ["LanczosResult", "lanczos_ground_state"]
+__all__ = ["LanczosResult", "lanczos_ground_state", "lanczos_thick_restart"]
 
 
 @dataclass
@@ -29,9 +31,53 @@ class LanczosResult:
     iterations: int
     residual: float
     converged: bool
-    eigenvector: Optional[object] = None   # padded replicated torch tensor (ShardedOperator layout)
+    eigenvector: Optional[object] = None   # torch tensor: this rank's rows
     alphas: Optional[np.ndarray] = None
     betas: Optional[np.ndarray] = None
+    energies: Optional[np.ndarray] = None  # thick restart: the k lowest eigenvalues
+    residuals: Optional[np.ndarray] = None
+    eigenvectors: Optional[object] = None  # thick restart: [k, local rows]
+    matvecs: int = 0
+
+
+class _SingleDevice:
+    """The DistributedOperator interface over a plain Operator on one GPU."""
+
+    def __init__(self, operator):
+        from .distributed import Layout
+        self.op = operator
+        dim = operator.basis.number_states
+        self.layout = Layout(1, 0, dim, 0, dim, 0, 0, 0, [0, dim])
+
+    def empty_vector(self, dtype=None):
+        import torch
+        return torch.zeros(self.layout.dim, dtype=dtype or torch.float64, device="cuda")
+
+    def matvec(self, x, y, mode=None):
+        import torch
+        self.op.matvec_device(x.data_ptr(), y.data_ptr(), complex_vectors=x.dtype == torch.complex128)
+
+    def sync(self):
+        from . import _lib
+        _lib.lib.ls_b200_matvec_sync()
+        _lib.check_error()
+
+    def dot(self, a, b):
+        import torch
+        return torch.vdot(a, b).reshape(1)
+
+
+def _wrap(operator):
+    from .distributed import DistributedOperator, init_process, layout_of
+    import torch
+    init_process(torch.cuda.current_device() if torch.cuda.is_available() else None)
+    if hasattr(operator, "layout") and hasattr(operator, "matvec"):
+        return operator
+    try:
+        layout_of(operator.basis)
+    except ValueError:
+        return _SingleDevice(operator)
+    return DistributedOperator(operator)
 
 
 def _lowest(alphas, betas):
@@ -42,77 +88,168 @@ def _lowest(alphas, betas):
     return float(w[0]), v[:, 0]
 
 
-def _start_vector(sharded, seed: int):
-    """Deterministic start vector that does not depend on the number of ranks:
-    every rank draws the full vector from the same seed (host), keeps it all
-    (x is replicated anyway)."""
+def _start_vector(sh, seed: int, dtype=None):
+    """Deterministic, independent of the number of ranks: entry i depends on (seed, global row i) only."""
     import torch
-    L = sharded.layout
-    g = torch.Generator(device="cpu")
-    g.manual_seed(seed)
-    v = sharded.empty_vector()
-    chunk = 1 << 24
-    for lo in range(0, L.dim, chunk):
-        hi = min(L.dim, lo + chunk)
-        v[lo:hi].copy_(torch.randn(hi - lo, dtype=torch.float64, generator=g))
+    from .distributed import hashed_vector
+    L = sh.layout
+    v = hashed_vector(L.row_begin, L.row_end, seed)
+    if dtype == torch.complex128:
+        v = torch.complex(v, hashed_vector(L.row_begin, L.row_end, seed + 1000003))
     return v
 
 
 def lanczos_ground_state(operator, max_iters: int = 300, tol: float = 1e-12, seed: int = 42,
-                         compute_eigenvector: bool = False, group=None, check_every: int = 5) -> LanczosResult:
+                         compute_eigenvector: bool = False, check_every: int = 10,
+                         time_limit_s: Optional[float] = None, progress=None) -> LanczosResult:
     """Lowest eigenvalue (and optionally eigenvector) of a real symmetric ``Operator``.
 
-    ``tol`` bounds the Ritz residual |beta_k s_k| relative to |E0|.
-    Works on one GPU or, under ``torch.distributed``, on the rank's row shard
-    (see :class:`distributed.ShardedOperator`)."""
+    ``tol`` bounds the Ritz residual |beta_k s_k| relative to |E0|.  No re-orthogonalisation: ghost copies do not
+    disturb the extremal eigenvalue.  The eigenvector, when requested, is accumulated in a second pass that
+    replays the recurrence (two-pass Lanczos: 3 vectors of HBM instead of one per iteration).
+    ``time_limit_s``: stop at the next check once this much wall time has passed (the result says whether it
+    had converged).  ``progress(k, energy, residual)`` is called at every check."""
+    import time
     import torch
-    from . import _lib
-    from .distributed import ShardedOperator, init_process
-
-    init_process(torch.cuda.current_device() if torch.cuda.is_available() else None)
-    sh = operator if isinstance(operator, ShardedOperator) else ShardedOperator(operator, group)
+    sh = _wrap(operator)
+    t_start = time.perf_counter()
 
     def run(accumulate_with=None):
         v = _start_vector(sh, seed)
-        nrm = torch.sqrt(sh.dot(v, v))
-        v /= nrm
+        v /= torch.sqrt(sh.dot(v, v))
         v_prev = sh.empty_vector()
         w = sh.empty_vector()
         out = sh.empty_vector() if accumulate_with is not None else None
-        alphas, betas = [], []
-        beta = 0.0
-        energy, resid, converged = float("nan"), float("inf"), False
         n_steps = len(accumulate_with) if accumulate_with is not None else max_iters
+        coeffs = torch.zeros(2, max(n_steps, 1), dtype=torch.float64, device=v.device)  # alphas; betas -- on the device
+        weights = None if accumulate_with is None else torch.as_tensor(np.asarray(accumulate_with), device=v.device)
+        energy, resid, converged, done = float("nan"), float("inf"), False, 0
+        beta = None
         for k in range(n_steps):
             if out is not None:
-                out.add_(v, alpha=float(accumulate_with[k]))
+                out.addcmul_(v, weights[k:k + 1])
             sh.matvec(v, w)
-            alpha = float(sh.dot(v, w).item())
-            alphas.append(alpha)
-            w.add_(v, alpha=-alpha)
+            alpha = sh.dot(v, w)
+            coeffs[0, k:k + 1] = alpha
+            w.addcmul_(v, alpha, value=-1.0)
             if k > 0:
-                w.add_(v_prev, alpha=-beta)
-            beta = float(torch.sqrt(sh.dot(w, w)).item())
-            betas.append(beta)
-            if accumulate_with is None and ((k + 1) % check_every == 0 or k + 1 == n_steps or beta < 1e-14):
-                energy, s = _lowest(alphas, betas)
-                resid = abs(beta * s[-1])
-                if resid <= tol * max(1.0, abs(energy)) or beta < 1e-14:
+                w.addcmul_(v_prev, beta, value=-1.0)
+            beta = torch.sqrt(sh.dot(w, w))
+            coeffs[1, k:k + 1] = beta
+            done = k + 1
+            if accumulate_with is None and (done % check_every == 0 or done == n_steps):
+                host = coeffs[:, :done].cpu().numpy()  # the only host read: every check_every iterations
+                energy, s = _lowest(host[0], host[1])
+                resid = abs(host[1, -1] * s[-1])
+                if progress is not None:
+                    progress(done, energy, resid)
+                if resid <= tol * max(1.0, abs(energy)) or host[1, -1] < 1e-14:
                     converged = True
                     break
-            if beta < 1e-14:
-                break
+                if time_limit_s is not None and time.perf_counter() - t_start > time_limit_s:
+                    break
             v_prev, v, w = v, w, v_prev
-            v /= beta
-        _lib.lib.ls_b200_matvec_sync()
-        _lib.check_error()
-        return alphas, betas, energy, resid, converged, out
+            v /= beta   # (a vanishing beta -- invariant subspace found -- is caught at the next check)
+        sh.sync()
+        host = coeffs[:, :done].cpu().numpy()
+        return host[0].copy(), host[1].copy(), energy, resid, converged, out
 
     alphas, betas, energy, resid, converged, _ = run()
-    result = LanczosResult(energy, len(alphas), resid, converged, None, np.array(alphas), np.array(betas))
+    result = LanczosResult(energy, len(alphas), resid, converged, None, alphas, betas, matvecs=len(alphas))
     if compute_eigenvector:
         _, s = _lowest(alphas, betas)
         *_, vec = run(accumulate_with=s)
         vec /= torch.sqrt(sh.dot(vec, vec))
         result.eigenvector = vec
+        result.matvecs += len(alphas)
     return result
+
+
+def lanczos_thick_restart(operator, k: int = 1, basis_size: Optional[int] = None, tol: float = 1e-10,
+                          max_restarts: int = 200, seed: int = 42, dtype=None) -> LanczosResult:
+    """The ``k`` lowest eigenpairs (chapel/src/Diagonalize.chpl:166-177 ``numEvals``) by thick-restart Lanczos.
+
+    A Krylov basis of at most ``basis_size`` vectors lives in HBM ([m, local rows]); every new vector is
+    orthogonalised against the whole basis (classical Gram-Schmidt, twice: two fused ``V w`` products and one
+    all-reduce of m numbers each); when the basis is full the k lowest Ritz vectors are kept (one GEMM) and the
+    iteration continues from the residual direction.  Works for real symmetric and complex Hermitian operators
+    (``dtype=torch.complex128``).  ``tol`` bounds every residual |beta s_i[m]| relative to max(1, |theta_i|)."""
+    import torch
+    from . import _lib
+    sh = _wrap(operator)
+    dtype = dtype or torch.float64
+    m = basis_size or max(2 * k + 16, 24)
+    n = sh.layout.rows
+    V = torch.zeros(m, n, dtype=dtype, device="cuda")
+    T = np.zeros((m, m), dtype=np.complex128 if dtype == torch.complex128 else np.float64)
+    w = sh.empty_vector(dtype)
+
+    def reduce_(t):
+        if sh.layout.world > 1:
+            view = torch.view_as_real(t) if t.dtype == torch.complex128 else t
+            view = view.contiguous()
+            _lib.lib.ls_b200_comm_allreduce_f64(view.data_ptr(), view.numel())
+            _lib.check_error()
+            if t.dtype == torch.complex128:
+                t.copy_(torch.view_as_complex(view))
+            else:
+                t.copy_(view)
+        return t
+
+    v0 = _start_vector(sh, seed, dtype)
+    V[0] = v0 / torch.sqrt(sh.dot(v0, v0).real)
+    have = 1          # basis vectors present
+    locked = 0        # Ritz vectors carried over from the last restart (rows 0 .. locked-1 of T are diagonal + border)
+    matvecs = 0
+    theta = np.zeros(k)
+    resid = np.full(k, np.inf)
+    converged = False
+    for restart in range(max_restarts + 1):
+        j = have - 1
+        beta_last = 0.0
+        while True:
+            sh.matvec(V[j], w)
+            matvecs += 1
+            # coefficients against the whole basis, twice (CGS2); the first pass also yields column j of T
+            h = reduce_(torch.mv(V[:have].conj(), w))
+            w -= torch.mv(V[:have].t(), h)
+            h2 = reduce_(torch.mv(V[:have].conj(), w))
+            w -= torch.mv(V[:have].t(), h2)
+            col = (h + h2).cpu().numpy()
+            T[:have, j] = col
+            T[j, :have] = np.conj(col)
+            T[j, j] = col[j].real
+            beta = float(torch.sqrt(sh.dot(w, w).real).item())
+            beta_last = beta
+            if have == m or beta < 1e-13:
+                break
+            V[have] = w / beta
+            T[have, j] = T[j, have] = beta
+            have += 1
+            j += 1
+        evals, S = np.linalg.eigh(T[:have, :have])
+        kk = min(k, have)
+        theta = evals[:kk]
+        resid = np.abs(beta_last * S[have - 1, :kk])
+        if np.all(resid <= tol * np.maximum(1.0, np.abs(theta))) or beta_last < 1e-13:
+            converged = True
+        if converged or restart == max_restarts:
+            St = torch.as_tensor(S[:, :kk].T.copy(), device="cuda").to(dtype)
+            vecs = St @ V[:have]
+            sh.sync()
+            return LanczosResult(float(theta[0]), matvecs, float(resid.max()), converged, vecs[0], None, None,
+                                 energies=np.array(theta), residuals=np.array(resid), eigenvectors=vecs, matvecs=matvecs)
+        # thick restart: keep `keep` Ritz vectors, continue from the residual direction w / beta
+        keep = min(have - 1, max(kk + 4, (kk + have) // 2 if have > 2 * kk else kk))
+        keep = max(1, min(keep, m - 2))
+        St = torch.as_tensor(S[:, :keep].T.copy(), device="cuda").to(dtype)
+        V[:keep] = St @ V[:have]
+        V[keep] = w / beta_last
+        T[:] = 0
+        for i in range(keep):
+            T[i, i] = evals[i]
+            T[keep, i] = beta_last * S[have - 1, i]
+            T[i, keep] = np.conj(T[keep, i])
+        locked = keep
+        have = keep + 1
+    raise AssertionError("unreachable")
