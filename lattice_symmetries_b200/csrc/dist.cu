@@ -110,7 +110,9 @@ constexpr uint64_t kAlign = 32;  // candidate blocks start on a multiple of 32 (
 std::vector<std::pair<uint64_t, uint64_t>> dist_block_plan(uint64_t total, int world) {
   std::vector<std::pair<uint64_t, uint64_t>> plan;
   if (total == 0) return plan;
-  uint64_t const min_block = uint64_t(1) << 20;
+  uint64_t min_block = uint64_t(1) << 20;
+  if (char const *env = getenv("LS_B200_DIST_MIN_BLOCK"))  // tests: small problems cut into many pieces
+    min_block = std::max<uint64_t>(kAlign, strtoull(env, nullptr, 10) / kAlign * kAlign);
   uint64_t max_block = std::max<uint64_t>(min_block, total / ((uint64_t)world * 32));
   max_block = (max_block + kAlign - 1) / kAlign * kAlign;
   uint64_t size = min_block;
@@ -424,7 +426,7 @@ static void build_global_index(Team const &team, std::vector<ls_hs_basis *> cons
   DistShard &first = *shard_of(bases[0]);
   int64_t const dim = first.dim;
   int const number_bits = index_of(bases[0])->number_bits;
-  if (dim == 0 || number_bits == 0 || index_of(bases[0])->identity) return;
+  if (dim == 0 || number_bits == 0) return;
   bool wide = (flags & kDistWideIndex) != 0 || dim >= (int64_t(1) << 32) || (size_t)dim * 8 > (size_t(8) << 30);
   if (char const *env = getenv("LS_B200_DIST_INDEX")) wide = strcmp(env, "wide") == 0 ? true : (dim < (int64_t(1) << 32) ? false : wide);
   std::vector<size_t> row_displs((size_t)team.world + 1);
@@ -572,6 +574,7 @@ static void dist_build(Team const &team, std::vector<ls_hs_basis *> const &bases
     install_representatives(bases[m], static_cast<uint64_t *>(reps[m]), with_norms ? static_cast<double *>(norms[m]) : nullptr,
                             (uint64_t)n, 22);
     IndexData *local = index_of(bases[m]);
+    local->identity = false;  // a shard's rows start at bounds[r]: index == state only holds for the unsharded list
     auto *sh = new DistShard();
     sh->world = P;
     sh->rank = r;
@@ -611,7 +614,6 @@ static void dist_matvec(Team const &team, std::vector<ls_hs_operator const *> co
   }
   DistShard const &first = *local[0]->dist;
   if (first.dim == 0) return;
-  bool const identity = local[0]->identity;
   bool const have_global = first.global_index != nullptr;
   if (mode == kProductAuto) {
     mode = have_global ? kProductAllGather : kProductAllToAll;
@@ -620,7 +622,6 @@ static void dist_matvec(Team const &team, std::vector<ls_hs_operator const *> co
       if (strcmp(env, "allgather") == 0 && have_global) mode = kProductAllGather;
     }
   }
-  LSB_CHECK(!identity, "bases whose index is the identity are not distributed");
   if (mode == kProductAllGather) {
     LSB_CHECK(have_global, "all-gather products need the replicated index (built without it)");
     size_t const scalar = complex_vectors ? 2 : 1;

@@ -31,7 +31,7 @@ import numpy as np
 __all__ = [
     "shard_bounds", "row_bounds", "plan_blocks", "plan_redistribution", "even_bounds", "balanced_bounds",
     "init_process", "init_communicator", "Layout", "build_distributed", "DistributedOperator", "EmulatedRanks",
-    "hashed_vector", "ALLGATHER", "ALLTOALL", "AUTO", "NO_GLOBAL_INDEX", "WIDE_INDEX", "NO_BALANCE",
+    "hashed_vector", "hashed_values", "layout_of", "ALLGATHER", "ALLTOALL", "AUTO", "NO_GLOBAL_INDEX", "WIDE_INDEX", "NO_BALANCE",
 ]
 
 ALIGN = 32  # candidate shards start on a multiple of 32 (one bit-sliced word)
@@ -214,8 +214,24 @@ def _as_int64(v: int) -> int:
     return v - (1 << 64) if v >= (1 << 63) else v
 
 
+def _splitmix_unit(z):
+    """splitmix64 finaliser of int64 tensor ``z`` (wrapping arithmetic) -> float64 in [0, 1)."""
+    import torch
+    z = (z ^ ((z >> 30) & 0x3FFFFFFFF)) * -4658895280553007687      # 0xBF58476D1CE4E5B9
+    z = (z ^ ((z >> 27) & 0x1FFFFFFFFF)) * -7723592293110705685     # 0x94D049BB133111EB
+    z = z ^ ((z >> 31) & 0x1FFFFFFFF)
+    return ((z >> 11) & 0x1FFFFFFFFFFFFF).to(torch.float64) * (1.0 / (1 << 53))
+
+
+def hashed_values(rows, seed: int = 42):
+    """Entries of the hashed vector at arbitrary GLOBAL rows (an int64 tensor, any device)."""
+    import torch
+    z = rows.to(torch.int64) + _as_int64((seed + 1) * 0x9E3779B97F4A7C15)   # golden-ratio increment
+    return 2.0 * _splitmix_unit(z) - 1.0
+
+
 def hashed_vector(row_begin: int, row_end: int, seed: int = 42, device="cuda"):
-    """Deterministic pseudo-random vector entries in (-1, 1) that depend only on (seed, GLOBAL row): every rank
+    """Deterministic pseudo-random vector entries in [-1, 1) that depend only on (seed, GLOBAL row): every rank
     fills its own rows, and the vector is the same for any number of ranks.  (A start vector for Lanczos on a
     basis whose full length -- 9.6e9 for kagome-42 -- no single host could draw.)"""
     import torch
@@ -223,12 +239,7 @@ def hashed_vector(row_begin: int, row_end: int, seed: int = 42, device="cuda"):
     chunk = 1 << 25
     for lo in range(row_begin, row_end, chunk):
         hi = min(row_end, lo + chunk)
-        z = torch.arange(lo, hi, dtype=torch.int64, device=device)
-        z = z + _as_int64((seed + 1) * 0x9E3779B97F4A7C15)      # splitmix64: golden-ratio increment, then the finaliser
-        z = (z ^ ((z >> 30) & 0x3FFFFFFFF)) * -4658895280553007687      # 0xBF58476D1CE4E5B9
-        z = (z ^ ((z >> 27) & 0x1FFFFFFFFF)) * -7723592293110705685     # 0x94D049BB133111EB
-        z = z ^ ((z >> 31) & 0x1FFFFFFFF)
-        out[lo - row_begin:hi - row_begin] = (z >> 11).to(torch.float64) * (1.0 / (1 << 52))
+        out[lo - row_begin:hi - row_begin] = hashed_values(torch.arange(lo, hi, dtype=torch.int64, device=device), seed)
     return out
 
 

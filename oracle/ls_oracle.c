@@ -563,12 +563,34 @@ LS_ORACLE_API void oracle_apply_off_diag(oracle_terms const *t,
  * Rows [row_begin, row_end) are processed; returns the number of off-diagonal
  * matrix elements emitted, or -1 on an invalid index.  Threads use atomic adds
  * like ConcurrentAccessor.chpl:31-33. */
-LS_ORACLE_API int64_t oracle_matvec(oracle_basis const *b,
+/* Optional hooks: the reference's OWN compiled kernels (oracle/_ref/libref.so = kernels/reference.c,
+ * kernels/indexing.c) stand in for the two steps of the loop below that could be compiled from the reference tree:
+ *   apply_off_diag : ls_internal_operator_apply_off_diag_x1(op, batch, alphas, betas, coeffs, offsets, xs)
+ *   state_index    : ls_hs_state_index_binary_search_kernel(batch, spins, 1, indices, 1, data)
+ * state_info stays the restatement (the reference's is Halide-generated).  Used by the CPU-baseline timing. */
+typedef void (*ref_apply_off_diag_fn)(void const *op, ptrdiff_t batch, uint64_t const *alphas, uint64_t *betas,
+                                      void *coeffs, ptrdiff_t *offsets, double const *xs);
+typedef void (*ref_state_index_fn)(ptrdiff_t batch, uint64_t const *spins, ptrdiff_t spins_stride, ptrdiff_t *indices,
+                                   ptrdiff_t indices_stride, void const *data);
+static ref_apply_off_diag_fn g_ref_apply = NULL;
+static ref_state_index_fn g_ref_index = NULL;
+static void const *g_ref_operator = NULL;
+static void const *g_ref_index_data = NULL;
+LS_ORACLE_API void oracle_set_reference_hooks(void *apply_fn, void const *op, void *index_fn, void const *index_data) {
+  g_ref_apply = (ref_apply_off_diag_fn)apply_fn;
+  g_ref_operator = op;
+  g_ref_index = (ref_state_index_fn)index_fn;
+  g_ref_index_data = index_data;
+}
+
+/* block_stride: one block of 64 columns is processed every `block_stride` columns of [row_begin, row_end)
+ * (64 = every column; larger = a uniform sample of the columns, for the CPU-baseline timing). */
+LS_ORACLE_API int64_t oracle_matvec_strided(oracle_basis const *b,
                                     oracle_terms const *off,
                                     oracle_terms const *diag,
                                     oracle_index const *index,
                                     uint64_t const *reps, ptrdiff_t dim,
-                                    ptrdiff_t row_begin, ptrdiff_t row_end,
+                                    ptrdiff_t row_begin, ptrdiff_t row_end, ptrdiff_t block_stride,
                                     double const *x, double *y,
                                     int zero_and_diag) {
   /* flags: bit 0 = zero y and apply the diagonal first (localDiagonal);
@@ -600,11 +622,17 @@ LS_ORACLE_API int64_t oracle_matvec(oracle_basis const *b,
     double *norms = (double *)malloc(cap * sizeof(double));
     ptrdiff_t *idx = (ptrdiff_t *)malloc(cap * sizeof(ptrdiff_t));
     ptrdiff_t offsets[ROWS + 1];
+    ptrdiff_t const stride = block_stride < ROWS ? ROWS : block_stride;
+    ptrdiff_t const nblocks = row_end > row_begin ? (row_end - row_begin + stride - 1) / stride : 0;
 #pragma omp for schedule(dynamic, 16)
-    for (ptrdiff_t r0 = row_begin; r0 < row_end; r0 += ROWS) {
+    for (ptrdiff_t blk = 0; blk < nblocks; ++blk) {
+      ptrdiff_t const r0 = row_begin + blk * stride;
       ptrdiff_t const count = (row_end - r0 < ROWS) ? row_end - r0 : ROWS;
-      oracle_apply_off_diag(off, count, reps + r0, tmp_spins, tmp_coeffs,
-                            offsets, x + r0);
+      if (g_ref_apply != NULL)
+        g_ref_apply(g_ref_operator, count, reps + r0, tmp_spins, tmp_coeffs, offsets, x + r0);
+      else
+        oracle_apply_off_diag(off, count, reps + r0, tmp_spins, tmp_coeffs,
+                              offsets, x + r0);
       ptrdiff_t const n = offsets[count];
       total += n;
       double *cs;
@@ -640,7 +668,8 @@ LS_ORACLE_API int64_t oracle_matvec(oracle_basis const *b,
         cs = tmp_coeffs;
         bs = tmp_spins;
       }
-      oracle_state_index(index, n, bs, idx);
+      if (g_ref_index != NULL) g_ref_index(n, bs, 1, idx, 1, g_ref_index_data);
+      else oracle_state_index(index, n, bs, idx);
       for (ptrdiff_t k = 0; k < n; ++k) {
         double const c = cs[2 * k]; /* coeffs[k]:real(64) */
         if (c != 0) {
@@ -656,6 +685,13 @@ LS_ORACLE_API int64_t oracle_matvec(oracle_basis const *b,
     free(tmp_spins); free(tmp_coeffs); free(betas); free(chars); free(norms); free(idx);
   }
   return bad ? -1 : total;
+}
+
+LS_ORACLE_API int64_t oracle_matvec(oracle_basis const *b, oracle_terms const *off, oracle_terms const *diag,
+                                    oracle_index const *index, uint64_t const *reps, ptrdiff_t dim,
+                                    ptrdiff_t row_begin, ptrdiff_t row_end, double const *x, double *y,
+                                    int zero_and_diag) {
+  return oracle_matvec_strided(b, off, diag, index, reps, dim, row_begin, row_end, 64, x, y, zero_and_diag);
 }
 
 LS_ORACLE_API int oracle_num_threads(void) {

@@ -92,6 +92,11 @@ def lib():
             C.POINTER(oracle_basis), C.POINTER(oracle_terms), C.POINTER(oracle_terms), C.c_void_p, u64_p,
             C.c_ssize_t, C.c_ssize_t, C.c_ssize_t, f64_p, f64_p, C.c_int]
         L.oracle_matvec.restype = C.c_int64
+        L.oracle_matvec_strided.argtypes = [
+            C.POINTER(oracle_basis), C.POINTER(oracle_terms), C.POINTER(oracle_terms), C.c_void_p, u64_p,
+            C.c_ssize_t, C.c_ssize_t, C.c_ssize_t, C.c_ssize_t, f64_p, f64_p, C.c_int]
+        L.oracle_matvec_strided.restype = C.c_int64
+        L.oracle_set_reference_hooks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -205,6 +210,7 @@ class Basis:
 class Index:
     def __init__(self, reps: np.ndarray, number_bits: int, prefix_bits: int = 22):
         self.reps = np.ascontiguousarray(reps, dtype=np.uint64)
+        self.prefix_bits = min(int(prefix_bits), int(number_bits))
         self.handle = lib().oracle_index_create(_p(self.reps, u64_p), self.reps.shape[0], number_bits, prefix_bits)
 
     def __call__(self, spins) -> np.ndarray:
@@ -260,17 +266,38 @@ def apply_off_diag(terms: Terms, alphas, xs=None):
 
 
 def matvec(basis: Basis, off: Terms, diag: Terms, index: Index, x: np.ndarray, row_begin: int = 0,
-           row_end: Optional[int] = None, sampling_prefix: bool = False) -> Tuple[np.ndarray, int]:
+           row_end: Optional[int] = None, sampling_prefix: bool = False, block_stride: int = 64,
+           reference_kernels: bool = False) -> Tuple[np.ndarray, int]:
     """Push-form y = H x as the reference assembles it; returns (y, number of
-    off-diagonal matrix elements emitted from the columns [row_begin, row_end))."""
+    off-diagonal matrix elements emitted from the columns [row_begin, row_end)).
+
+    ``block_stride`` > 64 (timing only): one block of 64 columns every ``block_stride`` columns -- a uniform sample.
+    ``reference_kernels`` (timing only): apply_off_diag and state_index are the reference's own compiled
+    kernels/reference.c and kernels/indexing.c (oracle/_ref/libref.so) instead of the restatement."""
     reps = index.reps
     dim = reps.shape[0]
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.zeros(dim, dtype=np.float64)
     if row_end is None:
         row_end = dim
-    n = lib().oracle_matvec(C.byref(basis.c), off.ptr(), diag.ptr(), index.handle, _p(reps, u64_p), dim,
-                            row_begin, row_end, _p(x, f64_p), _p(y, f64_p), 3 if sampling_prefix else 1)
+    hooks = None
+    if reference_kernels:
+        R = ref()
+        op, keep = _ref_op(off, diag, basis.number_bits)
+        arr = _ext_array(reps.ctypes.data, dim, None)
+        data = R.ls_hs_create_state_index_binary_search_kernel_data(C.byref(arr), basis.number_bits, index.prefix_bits)
+        hooks = (op, keep, arr, data)
+        lib().oracle_set_reference_hooks(
+            C.cast(R.ls_internal_operator_apply_off_diag_x1, C.c_void_p), C.cast(C.pointer(op), C.c_void_p),
+            C.cast(R.ls_hs_state_index_binary_search_kernel, C.c_void_p), data)
+    try:
+        n = lib().oracle_matvec_strided(C.byref(basis.c), off.ptr(), diag.ptr(), index.handle, _p(reps, u64_p), dim,
+                                        row_begin, row_end, int(block_stride), _p(x, f64_p), _p(y, f64_p),
+                                        3 if sampling_prefix else 1)
+    finally:
+        if hooks is not None:
+            lib().oracle_set_reference_hooks(None, None, None, None)
+            ref().ls_hs_destroy_state_index_binary_search_kernel_data(hooks[3])
     if n < 0:
         raise RuntimeError("oracle_matvec: invalid index (operator does not respect the basis symmetries)")
     return y, int(n)

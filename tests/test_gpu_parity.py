@@ -155,12 +155,11 @@ def test_block_cyclic_build_interleaves(oracle, built, name, world):
     """A rank's block-cyclic share in one call (ls_b200_build_blocks); the ranks' pieces interleave
     block by block to the full sorted list, with norms."""
     from lattice_symmetries_b200 import _lib
-    from lattice_symmetries_b200.distributed import block_plan
     p, (ob, reps, *_), basis, op = built(name, oracle)
     fresh = p.product_basis()
     total = fresh.number_candidates
-    plan = block_plan(total, world, blocks_per_rank=3, min_block=64)
-    size = plan[0][1] - plan[0][0]
+    size = max(64, (total // (3 * world) + 31) // 32 * 32)   # equal blocks (multiples of 32), ~3 per rank
+    plan = [(a, min(total, a + size)) for a in range(0, total, size)]
     pieces = {}
     for rank in range(world):
         mine = plan[rank::world]
