@@ -326,6 +326,8 @@ def parse_args():
     ap.add_argument("--workload", default=os.environ.get("LS_BENCH_WORKLOAD", "kagome36"))
     ap.add_argument("--mode", default="auto", choices=["auto", "allgather", "alltoall"],
                     help="distributed product form (N > 1)")
+    ap.add_argument("--dist-flags", type=int, default=0,
+                    help="ls_b200_dist_build flags (N > 1): 1 no replicated index, 2 wide replicated index, 4 even row split")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-checks", action="store_true")
@@ -463,7 +465,7 @@ def main():
         t0 = time.perf_counter()
         ev0.record()
         if world > 1:
-            build_distributed(basis, balance_for=op)   # rows split so that every rank holds the same number of elements
+            build_distributed(basis, balance_for=op, flags=args.dist_flags)   # rows split so that every rank holds the same number of elements
         else:
             basis.build()
         ev1.record()

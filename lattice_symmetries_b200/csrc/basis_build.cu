@@ -129,7 +129,18 @@ struct EnumView {
   uint64_t count_a;  // mode 2
   uint64_t total;
   uint64_t const *binom;  // device [65][65]
+  // Block-cyclic share of a rank (dist.cu): the kernels walk VIRTUAL words 0, 1, 2, ...; virtual block v >> cyc_shift
+  // is block (v >> cyc_shift) * cyc_world + cyc_rank of the candidate range.  cyc_world == 0: virtual == actual.
+  int cyc_shift;
+  uint32_t cyc_world, cyc_rank;
 };
+
+// word of 32 candidates addressed by the kernels -> word of the candidate range
+__host__ __device__ __forceinline__ uint64_t actual_word(EnumView const &e, uint64_t v) {
+  if (e.cyc_world == 0) return v;
+  uint64_t const block = v >> e.cyc_shift;
+  return ((block * e.cyc_world + e.cyc_rank) << e.cyc_shift) + (v & ((uint64_t(1) << e.cyc_shift) - 1));
+}
 
 struct EnumPlan {
   EnumView view;
@@ -247,9 +258,11 @@ generate_states_kernel(EnumView e, uint64_t k_begin, uint64_t count, uint64_t *_
   for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks;
        c += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t const first = c * chunk;
-    uint64_t const last = min(first + chunk, count);
+    uint64_t last = min(first + chunk, count);
+    uint64_t const k_actual = e.cyc_world == 0 ? k_begin + first : actual_word(e, c) * 32;  // (cyclic shares start at 0)
+    if (e.cyc_world != 0) last = min(last, first + (e.total - k_actual));
     CandidateIter it;
-    it.init(e, k_begin + first);
+    it.init(e, k_actual);
     for (uint64_t k = first; k < last; ++k) {
       out[k] = it.value(e);
       if (k + 1 < last) it.next(e);
@@ -300,7 +313,7 @@ build_flags_bitsliced_kernel(GroupView g, EnumView e, uint64_t word_begin, uint6
   for (int i = 0; i < NP; ++i) xr[i] = 0;
 
   if (w < number_words) {
-    uint64_t const k0 = (word_begin + w) * 32;
+    uint64_t const k0 = (list != nullptr ? word_begin + w : actual_word(e, word_begin + w)) * 32;
     uint64_t const remaining = (list != nullptr ? list_count : e.total) - k0;
     int const valid = remaining >= 32 ? 32 : (int)remaining;
     alive = valid == 32 ? 0xffffffffu : ((1u << valid) - 1u);
@@ -427,7 +440,7 @@ build_flags_scalar_kernel(GroupView g, EnumView e, uint64_t word_begin, uint64_t
   uint64_t const w = (uint64_t)blockIdx.x * kBuildThreads + tid;
   uint32_t alive = 0, events = 0;
   if (w < number_words) {
-    uint64_t const k0 = (word_begin + w) * 32;
+    uint64_t const k0 = actual_word(e, word_begin + w) * 32;
     uint64_t const remaining = e.total - k0;
     int const valid = remaining >= 32 ? 32 : (int)remaining;
     CandidateIter it;
@@ -497,7 +510,7 @@ build_scatter_kernel(GroupView g, EnumView e, uint64_t word_begin, uint64_t numb
   if (alive == 0) return;
   uint64_t pos = out_base + (uint64_t)block_offsets[blockIdx.x] + warp_base + (incl - mine);
   double const trivial_norm = norm_from_sum(g, 1.0);
-  uint64_t const k0 = (word_begin + w) * 32;
+  uint64_t const k0 = (list != nullptr ? word_begin + w : actual_word(e, word_begin + w)) * 32;
   int const last = 31 - __clz((int)alive);
   CandidateIter it;
   if (list == nullptr) it.init(e, k0);
@@ -554,20 +567,71 @@ static FlagsKernel pick_flags_kernel(int np, bool inv, bool filter) {
 // ranges; the output is their concatenation, counts[i] the number found in range i.  One call
 // serves a rank's whole block-cyclic share: scratch and output are allocated once.
 static bool want_managed_view();
-BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<uint64_t> *counts, bool host_visible) {
+// first[i] = position in the (sorted) output of the first representative that is >= the first candidate of the
+// rank's i-th block; first[number_blocks] = count
+__global__ void __launch_bounds__(256)
+cyclic_block_starts_kernel(EnumView e, uint64_t number_blocks, uint64_t const *__restrict__ reps, uint64_t count,
+                           uint64_t *__restrict__ first) {
+  uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > number_blocks) return;
+  if (i == number_blocks) {
+    first[i] = count;
+    return;
+  }
+  uint64_t const k = actual_word(e, i << e.cyc_shift) * 32;
+  CandidateIter it;
+  it.init(e, k);
+  uint64_t const state = it.value(e);
+  uint64_t lo = 0, hi = count;
+  while (lo < hi) {
+    uint64_t const mid = lo + (hi - lo) / 2;
+    if (__ldg(reps + mid) < state) lo = mid + 1;
+    else hi = mid;
+  }
+  first[i] = lo;
+}
+
+CyclicShare cyclic_share(uint64_t total, int block_shift, int world, int rank) {
+  CyclicShare c;
+  c.shift = block_shift;
+  c.world = world;
+  c.rank = rank;
+  uint64_t const block = uint64_t(32) << block_shift;  // candidates per block
+  uint64_t const blocks_total = (total + block - 1) / block;
+  c.blocks_total = blocks_total;
+  c.number_blocks = (uint64_t)rank < blocks_total ? (blocks_total - (uint64_t)rank + (uint64_t)world - 1) / (uint64_t)world : 0;
+  c.virtual_candidates = 0;
+  if (c.number_blocks > 0) {
+    uint64_t const last_block = (c.number_blocks - 1) * (uint64_t)world + (uint64_t)rank;
+    uint64_t const last_begin = last_block * block;
+    c.virtual_candidates = (c.number_blocks - 1) * block + (std::min(total, last_begin + block) - last_begin);
+  }
+  return c;
+}
+
+BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<uint64_t> *counts, bool host_visible,
+                         CyclicShare const *cyc) {
   Runtime &rt = runtime();
   BasisInfo const info = basis_info(basis);
   LSB_CHECK(info.number_bits <= 64, "bases with more than 64 bits are not supported");
-  EnumPlan const plan = make_plan(basis, info);
-  EnumView const &e = plan.view;
+  EnumPlan plan = make_plan(basis, info);
+  EnumView &e = plan.view;
+  if (cyc != nullptr) {
+    // a rank's block-cyclic share (dist.cu) scanned as ONE virtual range: the kernels translate word numbers, so the
+    // launches are as large as those of a single-GPU build; counts = representatives per block (from the output)
+    e.cyc_shift = cyc->shift;
+    e.cyc_world = (uint32_t)cyc->world;
+    e.cyc_rank = (uint32_t)cyc->rank;
+    ranges = Ranges{{0, cyc->virtual_candidates}};
+  }
   uint64_t candidates = 0, longest = 0;
   for (auto &r : ranges) {
-    r.second = std::min(r.second, e.total);
+    if (cyc == nullptr) r.second = std::min(r.second, e.total);
     r.first = std::min(r.first, r.second);
     candidates += r.second - r.first;
     longest = std::max(longest, r.second - r.first);
   }
-  if (counts != nullptr) counts->assign(ranges.size(), 0);
+  if (counts != nullptr) counts->assign(cyc != nullptr ? (size_t)cyc->number_blocks : ranges.size(), 0);
   BuildResult res;
   if (candidates == 0) return res;
   static bool const profile = getenv("LS_B200_PROFILE") != nullptr;
@@ -599,7 +663,7 @@ BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<ui
       count_launch();
       CUDA_CHECK(cudaGetLastError());
       res.count += count;
-      if (counts != nullptr) (*counts)[i] = count;
+      if (counts != nullptr && cyc == nullptr) (*counts)[i] = count;
     }
   } else {
     GroupData const &g = *info.group;
@@ -672,7 +736,7 @@ BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<ui
         unsigned const blocks = (unsigned)((nwords + kBuildThreads - 1) / kBuildThreads);
         // Clip the enumeration so that the tail word of this range is masked.
         EnumView ev = e;
-        ev.total = k_end;
+        if (cyc == nullptr) ev.total = k_end;
         // `source` / `source_words` / `source_blocks`: what the final scatter reads -- candidates by index, or
         // (two-phase) the compacted survivors of the filter
         uint64_t const *source = nullptr;
@@ -763,9 +827,22 @@ BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<ui
         }
         emitted += chunk_total;
       }
-      if (counts != nullptr) (*counts)[i] = emitted - emitted_before;
+      if (counts != nullptr && cyc == nullptr) (*counts)[i] = emitted - emitted_before;
     }
     res.count = emitted;
+  }
+  if (cyc != nullptr && counts != nullptr && cyc->number_blocks > 0) {
+    static DeviceBuffer<uint64_t> starts;
+    uint64_t const nb = cyc->number_blocks;
+    uint64_t *d = starts.reserve((size_t)nb + 1);
+    cyclic_block_starts_kernel<<<(unsigned)((nb + 256) / 256), 256, 0, rt.stream>>>(e, nb, res.d_reps, res.count, d);
+    count_launch();
+    CUDA_CHECK(cudaGetLastError());
+    std::vector<uint64_t> h((size_t)nb + 1);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), d, sizeof(uint64_t) * (nb + 1), cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    for (uint64_t b = 0; b < nb; ++b) (*counts)[(size_t)b] = h[(size_t)b + 1] - h[(size_t)b];
+    res.d_block_starts = d;
   }
   CUDA_CHECK(cudaEventRecord(rt.ev1, rt.stream));
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
@@ -870,6 +947,20 @@ void ensure_norms(IndexData &ix, GroupData const &g) {
     launch_state_info(g, n, ix.d_reps + b, betas.ptr, chars.ptr, ix.d_norms + b);
   }
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+}
+
+uint64_t *alloc_representatives(uint64_t count) {
+  Runtime &rt = runtime();
+  uint64_t *p = nullptr;
+  size_t const bytes = sizeof(uint64_t) * std::max<uint64_t>(count, 1);
+  if (getenv("LS_B200_NO_HOST_MIRROR") == nullptr && want_managed_view() && cudaMallocManaged(&p, bytes) == cudaSuccess) {
+    CUDA_CHECK(cudaMemAdvise(p, bytes, cudaMemAdviseSetPreferredLocation, rt.device));
+    CUDA_CHECK(cudaMemPrefetchAsync(p, bytes, rt.device, rt.stream));
+    return p;
+  }
+  (void)cudaGetLastError();
+  CUDA_CHECK(cudaMalloc(&p, bytes));
+  return p;
 }
 
 uint64_t number_candidates(ls_hs_basis const *basis) { return make_plan(basis, basis_info(basis)).view.total; }

@@ -24,7 +24,10 @@
 #include <nccl.h>  // types and prototypes only: libnccl is loaded at run time, the library does not link it
 
 #include <algorithm>
+#include <chrono>
+#include <memory>
 #include <numeric>
+#include <string>
 
 #include "state.hpp"
 
@@ -103,30 +106,25 @@ DistShard::~DistShard() {
 // ---- host-side planning (pure functions; exported for the CPU tests) ---------------------------------------------
 constexpr uint64_t kAlign = 32;  // candidate blocks start on a multiple of 32 (one bit-sliced word)
 
-// Blocks of the candidate-index range [0, total), block b scanned by rank b % world.  A representative is the
-// smallest member of its orbit, so representatives -- and the work of finding them -- crowd into the low indices
-// (kagome-36: the first 3 % of the range hold 90 % of them): the plan starts with small blocks and doubles the size
-// every 8 * world blocks, so that every rank gets an equal share of every density regime.
-std::vector<std::pair<uint64_t, uint64_t>> dist_block_plan(uint64_t total, int world) {
-  std::vector<std::pair<uint64_t, uint64_t>> plan;
-  if (total == 0) return plan;
+// Blocks of the candidate-index range [0, total): EQUAL blocks of 32 << shift candidates, block b scanned by rank
+// b % world.  A representative is the smallest member of its orbit, so representatives -- and the work of finding
+// them -- crowd into the low indices (kagome-36: the first 3 % of the range hold 90 % of them); dealing many small
+// blocks round-robin gives every rank the same share of every density regime.  A rank scans its whole share as one
+// virtual range (build_ranges, CyclicShare), so small blocks cost nothing in launch size.
+int dist_block_shift(uint64_t total, int world) {
   uint64_t min_block = uint64_t(1) << 20;
   if (char const *env = getenv("LS_B200_DIST_MIN_BLOCK"))  // tests: small problems cut into many pieces
-    min_block = std::max<uint64_t>(kAlign, strtoull(env, nullptr, 10) / kAlign * kAlign);
-  uint64_t max_block = std::max<uint64_t>(min_block, total / ((uint64_t)world * 32));
-  max_block = (max_block + kAlign - 1) / kAlign * kAlign;
-  uint64_t size = min_block;
-  uint64_t lo = 0;
-  int in_generation = 0;
-  while (lo < total) {
-    uint64_t const hi = std::min(total, lo + size);
-    plan.emplace_back(lo, hi);
-    lo = hi;
-    if (++in_generation == 8 * world && size < max_block) {
-      size = std::min(max_block, size * 2);
-      in_generation = 0;
-    }
-  }
+    min_block = std::max<uint64_t>(kAlign, strtoull(env, nullptr, 10));
+  uint64_t const want = std::max<uint64_t>(min_block, total / ((uint64_t)world * 4096));  // <= ~4096 blocks per rank
+  int shift = 0;
+  while ((uint64_t(32) << (shift + 1)) <= want) ++shift;
+  return shift;
+}
+
+std::vector<std::pair<uint64_t, uint64_t>> dist_block_plan(uint64_t total, int world) {
+  std::vector<std::pair<uint64_t, uint64_t>> plan;
+  uint64_t const block = uint64_t(32) << dist_block_shift(total, world);
+  for (uint64_t lo = 0; lo < total; lo += block) plan.emplace_back(lo, std::min(total, lo + block));
   return plan;
 }
 
@@ -191,7 +189,8 @@ RedistPlan plan_redistribution(int world, int me, std::vector<Piece> const &piec
 // Contiguous row ranges of (nearly) equal cost: `edges` are ascending row numbers (edges[0] = 0, edges.back() = dim),
 // costs[b] the cost of rows [edges[b], edges[b+1]).  Rank r ends at the block boundary closest to (r+1)/world of the
 // total (rows of the sorted basis do not cost the same: kagome-36, eight ranks, even split: 0.87x .. 1.12x the mean).
-std::vector<int64_t> dist_balanced_bounds(std::vector<int64_t> const &edges, std::vector<double> const &costs, int world) {
+std::vector<int64_t> dist_balanced_bounds(std::vector<int64_t> const &edges, std::vector<double> const &costs, int world,
+                                          bool interpolate = false) {
   int64_t const dim = edges.back();
   std::vector<int64_t> bounds((size_t)world + 1, dim);
   bounds[0] = 0;
@@ -202,8 +201,16 @@ std::vector<int64_t> dist_balanced_bounds(std::vector<int64_t> const &edges, std
   for (int r = 0; r + 1 < world; ++r) {
     double const target = total * (double)(r + 1) / (double)world;
     while (b < costs.size() && acc + costs[b] <= target) acc += costs[b++];
-    if (b < costs.size() && target - acc > acc + costs[b] - target) acc += costs[b++];
-    bounds[(size_t)r + 1] = std::max(bounds[(size_t)r], edges[b]);
+    int64_t cut = edges[std::min(b, edges.size() - 1)];
+    if (interpolate) {
+      // inside block b rows cost about the same (they are neighbours in the sorted list): cut it proportionally
+      if (b < costs.size() && costs[b] > 0)
+        cut = edges[b] + (int64_t)((double)(edges[b + 1] - edges[b]) * ((target - acc) / costs[b]));
+    } else if (b < costs.size() && target - acc > acc + costs[b] - target) {
+      acc += costs[b++];
+      cut = edges[b];
+    }
+    bounds[(size_t)r + 1] = std::min(dim, std::max(bounds[(size_t)r], cut));
   }
   return bounds;
 }
@@ -295,8 +302,10 @@ struct Team {
   }
 
   // In place: segment r = bytes [displs[r], displs[r+1]) of every buffer is valid on rank r; afterwards everywhere.
-  void all_gather_v(std::vector<unsigned char *> const &buf, std::vector<size_t> const &displs) const {
+  void all_gather_v(std::vector<unsigned char *> const &buf, std::vector<size_t> const &displs,
+                    cudaStream_t stream = nullptr) const {
     Runtime &rt = runtime();
+    if (stream == nullptr) stream = rt.stream;
     if (emulated) {
       for (size_t dst = 0; dst < members.size(); ++dst)
         for (size_t src = 0; src < members.size(); ++src) {
@@ -312,7 +321,7 @@ struct Team {
       size_t const n = displs[(size_t)root + 1] - displs[(size_t)root];
       if (n > 0)
         NCCL_CHECK(nccl().Broadcast(buf[0] + displs[(size_t)root], buf[0] + displs[(size_t)root], n, ncclChar, root,
-                                    g_comm.comm, rt.stream));
+                                    g_comm.comm, stream));
     }
     NCCL_CHECK(nccl().GroupEnd());
   }
@@ -367,15 +376,32 @@ static Team emulated_team(int world) {
 }
 
 // ---- redistribution of sorted pieces into contiguous row ranges --------------------------------------------------
-// data[m]: the pieces owned by member m, concatenated (device); replaced by its new rows (a fresh allocation).
+struct PlaceDev {
+  int64_t src, dst, length;
+};
+// place p: fresh[dst .. dst + length) = recv[src .. src + length)   (8-byte elements; one CTA per place, round-robin)
+__global__ void __launch_bounds__(256)
+place_kernel(PlaceDev const *__restrict__ places, int64_t n, uint64_t const *__restrict__ recv, uint64_t *__restrict__ fresh) {
+  for (int64_t p = blockIdx.x; p < n; p += gridDim.x) {
+    PlaceDev const pl = places[p];
+    for (int64_t i = threadIdx.x; i < pl.length; i += blockDim.x) fresh[pl.dst + i] = recv[pl.src + i];
+  }
+}
+
+// data[m]: the pieces owned by member m, concatenated (device); replaced by its new rows, in a buffer obtained from
+// `allocate(elements)` -- the old buffer is freed.  The receive buffers live for the process (grow-only): with peer
+// access enabled every cudaMalloc / cudaFree maps or unmaps on all GPUs and costs milliseconds.
 static void redistribute(Team const &team, std::vector<Piece> const &pieces, std::vector<int64_t> const &bounds,
-                         std::vector<void *> &data, size_t elem) {
+                         std::vector<void *> &data, void *(*allocate)(uint64_t elements)) {
   Runtime &rt = runtime();
   size_t const M = team.size();
+  size_t const elem = 8;
   std::vector<RedistPlan> plans;
   std::vector<unsigned char const *> send(M);
   std::vector<unsigned char *> recv(M), fresh(M);
   std::vector<std::vector<size_t>> sd(M), sc(M), rd(M), rc(M);
+  static std::vector<std::unique_ptr<DeviceBuffer<uint64_t>>> receive;
+  while (receive.size() < M) receive.push_back(std::make_unique<DeviceBuffer<uint64_t>>());
   for (size_t m = 0; m < M; ++m) {
     plans.push_back(plan_redistribution(team.world, team.members[m], pieces, bounds));
     RedistPlan const &p = plans.back();
@@ -389,23 +415,42 @@ static void redistribute(Team const &team, std::vector<Piece> const &pieces, std
     rd[m] = bytes(p.rdispl);
     rc[m] = bytes(p.rcount);
     send[m] = static_cast<unsigned char const *>(data[m]);
-    void *r = nullptr, *f = nullptr;
-    CUDA_CHECK(cudaMalloc(&r, std::max<size_t>((size_t)p.total_recv * elem, 8)));
-    CUDA_CHECK(cudaMalloc(&f, std::max<size_t>((size_t)p.total_recv * elem, 8)));
-    recv[m] = static_cast<unsigned char *>(r);
-    fresh[m] = static_cast<unsigned char *>(f);
+    recv[m] = reinterpret_cast<unsigned char *>(receive[m]->reserve((size_t)p.total_recv + 1));
+    fresh[m] = static_cast<unsigned char *>(allocate((uint64_t)p.total_recv));
   }
   team.all_to_all_v(send, sd, sc, recv, rd, rc);
-  for (size_t m = 0; m < M; ++m)
-    for (auto const &pl : plans[m].places)
-      CUDA_CHECK(cudaMemcpyAsync(fresh[m] + (size_t)pl.dst * elem, recv[m] + (size_t)pl.src * elem, (size_t)pl.length * elem,
-                                 cudaMemcpyDeviceToDevice, rt.stream));
+  static DeviceBuffer<PlaceDev> table;
+  for (size_t m = 0; m < M; ++m) {
+    size_t const n = plans[m].places.size();
+    if (n == 0) continue;
+    if (n <= 8) {
+      for (auto const &pl : plans[m].places)
+        CUDA_CHECK(cudaMemcpyAsync(fresh[m] + (size_t)pl.dst * elem, recv[m] + (size_t)pl.src * elem,
+                                   (size_t)pl.length * elem, cudaMemcpyDeviceToDevice, rt.stream));
+      continue;
+    }
+    static_assert(sizeof(PlaceDev) == sizeof(RedistPlan::Place), "place layout");
+    PlaceDev *d = table.reserve(n);
+    CUDA_CHECK(cudaMemcpyAsync(d, plans[m].places.data(), sizeof(PlaceDev) * n, cudaMemcpyHostToDevice, rt.stream));
+    unsigned const blocks = (unsigned)std::min<size_t>(n, (size_t)rt.sm_count * 8);
+    place_kernel<<<blocks, 256, 0, rt.stream>>>(d, (int64_t)n, reinterpret_cast<uint64_t const *>(recv[m]),
+                                                reinterpret_cast<uint64_t *>(fresh[m]));
+    count_launch();
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));  // (the table buffer is reused by the next member)
+  }
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
   for (size_t m = 0; m < M; ++m) {
-    cudaFree(recv[m]);
     cudaFree(data[m]);
     data[m] = fresh[m];
   }
+}
+
+static void *allocate_representatives(uint64_t elements) { return alloc_representatives(elements); }
+static void *allocate_plain(uint64_t elements) {
+  void *p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, 8 * std::max<uint64_t>(elements, 1)));
+  return p;
 }
 
 // ---- distributed build ----------------------------------------------------------------------------------------------
@@ -491,78 +536,97 @@ static void dist_build(Team const &team, std::vector<ls_hs_basis *> const &bases
   size_t const M = team.size();
   int const P = team.world;
   for (ls_hs_basis *b : bases) LSB_CHECK(b->representatives.num_elts == 0 && index_of(b) == nullptr, "basis is already built");
+  static bool const profile = getenv("LS_B200_PROFILE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  std::string phases;
+  auto lap = [&](char const *what) {
+    if (!profile) return;
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    auto const now = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof buf, " %s %.2f ms,", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    phases += buf;
+    t_last = now;
+  };
   bool const with_norms = basis_info(bases[0]).has_permutation_symmetries;
 
   // 1. every rank scans its blocks of the candidate range
   uint64_t const total = number_candidates(bases[0]);
-  auto const plan = dist_block_plan(total, P);
-  size_t const nb = plan.size();
+  int const block_shift = dist_block_shift(total, P);
+  size_t const nb = (size_t)cyclic_share(total, block_shift, P, 0).blocks_total;
   size_t const per_rank = std::max<size_t>(1, (nb + (size_t)P - 1) / (size_t)P);
   std::vector<std::vector<uint64_t>> counts(M);
   std::vector<void *> reps(M, nullptr), norms(M, nullptr);
+  std::vector<uint64_t const *> starts(M, nullptr);
+  std::vector<uint64_t *> kept_starts;
   double kernel_ms = 0;
   for (size_t m = 0; m < M; ++m) {
-    Ranges mine;
-    for (size_t b = (size_t)team.members[m]; b < nb; b += (size_t)P) mine.push_back(plan[b]);
-    BuildResult r = build_ranges(bases[m], mine, &counts[m]);
+    CyclicShare const share = cyclic_share(total, block_shift, P, team.members[m]);
+    BuildResult r = build_ranges(bases[m], Ranges{}, &counts[m], false, &share);
     kernel_ms = std::max(kernel_ms, rt.last_build_ms);
-    counts[m].resize(per_rank, 0);
     reps[m] = r.d_reps;
     norms[m] = r.d_norms;
+    starts[m] = r.d_block_starts;
+    if (M > 1 && r.d_block_starts != nullptr && !counts[m].empty()) {
+      // emulated ranks share the library's scratch: keep this member's block starts
+      size_t const n = counts[m].size() + 1;
+      uint64_t *keep = nullptr;
+      CUDA_CHECK(cudaMalloc(&keep, sizeof(uint64_t) * n));
+      CUDA_CHECK(cudaMemcpyAsync(keep, r.d_block_starts, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, rt.stream));
+      CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+      starts[m] = keep;
+      kept_starts.push_back(keep);
+    }
   }
-  // 2. everybody learns every block's size; the pieces in block order are the sorted list
+  lap("scan");
+  // 2. everybody learns every block's size -- the pieces in block order are the sorted list -- and, when the rows
+  //    are to be balanced for an operator, every block's cost (its matrix elements + 4 row-proportional units per
+  //    row: alpha, norm, x, y traffic and the term scan)
+  bool const balance = !balance_for.empty() && balance_for[0] != nullptr && (flags & kDistNoBalance) == 0 && P > 1;
+  std::vector<std::vector<uint64_t>> costs(M);
+  if (balance) {
+    static std::vector<std::unique_ptr<DeviceBuffer<uint64_t>>> scratch;
+    while (scratch.size() < M) scratch.push_back(std::make_unique<DeviceBuffer<uint64_t>>());
+    for (size_t m = 0; m < M; ++m) {
+      size_t const mine = counts[m].size();  // blocks of this member (before padding)
+      costs[m].assign(per_rank, 0);
+      if (mine == 0 || starts[m] == nullptr) continue;
+      uint64_t *d = scratch[m]->reserve(mine);
+      uint64_t rows_m = 0;
+      for (uint64_t c : counts[m]) rows_m += c;
+      count_elements_segments(operator_dev(balance_for[m]), static_cast<uint64_t const *>(reps[m]), (int64_t)rows_m, starts[m],
+                              (int64_t)mine, d);
+      CUDA_CHECK(cudaMemcpyAsync(costs[m].data(), d, sizeof(uint64_t) * mine, cudaMemcpyDeviceToHost, rt.stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    for (size_t m = 0; m < M; ++m)
+      for (size_t k = 0; k < counts[m].size(); ++k) costs[m][k] += 4 * counts[m][k];
+  }
+  for (size_t m = 0; m < M; ++m) counts[m].resize(per_rank, 0);
   std::vector<uint64_t> const table = team.gather_host(counts, per_rank);
+  std::vector<uint64_t> cost_table;
+  if (balance) cost_table = team.gather_host(costs, per_rank);
   std::vector<Piece> pieces;
+  std::vector<int64_t> edges{0};
+  std::vector<double> piece_costs;
   int64_t dim = 0;
   for (size_t b = 0; b < nb; ++b) {
-    int64_t const n = (int64_t)table[(b % (size_t)P) * per_rank + b / (size_t)P];
+    size_t const at = (b % (size_t)P) * per_rank + b / (size_t)P;
+    int64_t const n = (int64_t)table[at];
     pieces.push_back({dim, n, (int)(b % (size_t)P)});
     dim += n;
+    edges.push_back(dim);
+    if (balance) piece_costs.push_back((double)cost_table[at]);
   }
-  // 3. one all-to-all-v per array: every piece travels to the rank that owns its rows
+  // 3. row ranges: even, or of equal cost (boundaries interpolated inside a block: neighbouring rows cost the same)
   std::vector<int64_t> bounds = dist_even_bounds(dim, P);
-  redistribute(team, pieces, bounds, reps, 8);
-  if (with_norms) redistribute(team, pieces, bounds, norms, 8);
-  // 4. optional: move the boundaries so that every rank holds the same number of matrix elements of `balance_for`
-  bool const balance = !balance_for.empty() && balance_for[0] != nullptr && (flags & kDistNoBalance) == 0 && P > 1 &&
-                       dim >= 4096 * (int64_t)P;
-  if (balance) {
-    size_t const fine = 64;
-    std::vector<std::vector<uint64_t>> mine(M, std::vector<uint64_t>(fine, 0));
-    for (size_t m = 0; m < M; ++m) {
-      int const r = team.members[m];
-      int64_t const n = bounds[(size_t)r + 1] - bounds[(size_t)r];
-      OperatorDev &od = operator_dev(balance_for[m]);
-      for (size_t k = 0; k < fine; ++k) {
-        int64_t const a = (int64_t)(((__int128)n * (int64_t)k) / (int64_t)fine), b = (int64_t)(((__int128)n * (int64_t)(k + 1)) / (int64_t)fine);
-        // 4 row-proportional units (alpha, norm, x, y traffic and the term scan) per row on top of its elements
-        mine[m][k] = b > a ? (uint64_t)(count_elements(od, static_cast<uint64_t const *>(reps[m]), a, b) + 4 * (b - a)) : 0;
-      }
-    }
-    std::vector<uint64_t> const all = team.gather_host(mine, fine);
-    std::vector<int64_t> edges{0};
-    std::vector<double> costs;
-    for (int r = 0; r < P; ++r) {
-      int64_t const n = bounds[(size_t)r + 1] - bounds[(size_t)r];
-      for (size_t k = 0; k < fine; ++k) {
-        int64_t const b = bounds[(size_t)r] + (int64_t)(((__int128)n * (int64_t)(k + 1)) / (int64_t)fine);
-        if (b > edges.back()) {
-          edges.push_back(b);
-          costs.push_back((double)all[(size_t)r * fine + k]);
-        } else if (!costs.empty()) {
-          costs.back() += (double)all[(size_t)r * fine + k];
-        }
-      }
-    }
-    std::vector<int64_t> const balanced = dist_balanced_bounds(edges, costs, P);
-    if (balanced != bounds) {
-      std::vector<Piece> held;
-      for (int r = 0; r < P; ++r) held.push_back({bounds[(size_t)r], bounds[(size_t)r + 1] - bounds[(size_t)r], r});
-      redistribute(team, held, balanced, reps, 8);
-      if (with_norms) redistribute(team, held, balanced, norms, 8);
-      bounds = balanced;
-    }
-  }
+  if (balance && dim >= 4096 * (int64_t)P) bounds = dist_balanced_bounds(edges, piece_costs, P, true);
+  for (uint64_t *k : kept_starts) cudaFree(k);
+  lap("counts");
+  // 4. one all-to-all-v per array: every piece travels to the rank that owns its rows, straight into the final arrays
+  redistribute(team, pieces, bounds, reps, allocate_representatives);
+  if (with_norms) redistribute(team, pieces, bounds, norms, allocate_plain);
+  lap("redistribute");
   // 5. the local rows become the basis' representatives (host view, local index), tagged with the shard layout
   std::vector<std::vector<uint64_t>> firsts(M, std::vector<uint64_t>(1, ~uint64_t(0)));
   for (size_t m = 0; m < M; ++m) {
@@ -593,9 +657,14 @@ static void dist_build(Team const &team, std::vector<ls_hs_basis *> const &bases
     CUDA_CHECK(cudaMemcpy(sh.d_splitters, sh.splitters.data(), sizeof(uint64_t) * (size_t)P, cudaMemcpyHostToDevice));
     sh.push = new PushBuffers();
   }
+  lap("install + local index");
   // 6. replicated lookup structure of the all-gather products
   if ((flags & kDistNoGlobalIndex) == 0) build_global_index(team, bases, flags);
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+  lap("replicated index");
+  if (profile)
+    fprintf(stderr, "[ls_b200] dist_build rank %d/%d: %lld states, %zu blocks of %llu candidates;%s\n", team.members[0], P,
+            (long long)dim, nb, (unsigned long long)(uint64_t(32) << block_shift), phases.c_str());
   rt.last_build_ms = kernel_ms;
 }
 
@@ -604,7 +673,7 @@ enum : int { kProductAuto = 0, kProductAllGather = 1, kProductAllToAll = 2 };
 
 static void dist_matvec(Team const &team, std::vector<ls_hs_operator const *> const &ops,
                         std::vector<double const *> const &x, std::vector<double *> const &y, int mode,
-                        bool complex_vectors) {
+                        bool complex_vectors, cudaEvent_t x_ready = nullptr, double *host_y = nullptr) {
   Runtime &rt = runtime();
   size_t const M = team.size();
   std::vector<IndexData *> local(M);
@@ -638,25 +707,53 @@ static void dist_matvec(Team const &team, std::vector<ls_hs_operator const *> co
         sh.xs_full_words = words;
       }
       full[m] = reinterpret_cast<unsigned char *>(sh.d_xs_full);
-      // n_j x_j of the local rows, straight into their slot of the replicated vector
-      launch_prescale(local[m]->number_states, complex_vectors, local[m]->d_norms, x[m],
-                      sh.d_xs_full + (size_t)sh.bounds[(size_t)sh.rank] * scalar);
     }
-    team.all_gather_v(full, displs);
+    // Real ranks: pre-scaling (n_j x_j of the local rows, straight into their slot of the replicated vector) and the
+    // all-gather run on their own stream, under the canonicalisation of the first chunk of rows (which reads only the
+    // representatives); the first kernel that reads the replicated vector waits for the collective.
+    cudaEvent_t gathered = nullptr;
+    cudaStream_t side = rt.stream;
+    bool const overlap = !team.emulated && team.world > 1 && getenv("LS_B200_DIST_NO_OVERLAP") == nullptr;
+    if (overlap) {
+      static cudaStream_t comm_stream = nullptr;
+      static cudaEvent_t inputs_ready = nullptr, done = nullptr;
+      if (comm_stream == nullptr) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&inputs_ready, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+      }
+      CUDA_CHECK(cudaEventRecord(inputs_ready, rt.stream));  // x written by earlier work on the library stream; the
+      CUDA_CHECK(cudaStreamWaitEvent(comm_stream, inputs_ready, 0));  // previous product is through with the replica
+      side = comm_stream;
+      gathered = done;
+    }
+    if (x_ready != nullptr) CUDA_CHECK(cudaStreamWaitEvent(side, x_ready, 0));
+    for (size_t m = 0; m < M; ++m) {
+      DistShard &sh = *local[m]->dist;
+      launch_prescale(local[m]->number_states, complex_vectors, local[m]->d_norms, x[m],
+                      sh.d_xs_full + (size_t)sh.bounds[(size_t)sh.rank] * scalar, side);
+    }
+    team.all_gather_v(full, displs, side);
+    if (overlap) CUDA_CHECK(cudaEventRecord(gathered, side));
     for (size_t m = 0; m < M; ++m) {
       DistShard &sh = *local[m]->dist;
       MvTarget t{};
+      t.xs_ready = gathered;
       t.index = sh.global_index->view();
       t.rows = local[m]->d_reps;
       t.norms = local[m]->d_norms;
       t.number_rows = local[m]->number_states;
       t.xs = sh.d_xs_full;
       if (t.number_rows > 0)
-        matvec_device(ops[m], 0, t.number_rows, x[m], y[m], complex_vectors, 1, 0, 0, nullptr, 0, &t);
+        matvec_device(ops[m], 0, t.number_rows, x[m], y[m], complex_vectors, 1, 0, 0, host_y, 0, &t);
     }
+    // (a rank without rows launched nothing that waits: later work on the library stream must still not touch the
+    // replicated vector before the collective is through)
+    if (gathered != nullptr) CUDA_CHECK(cudaStreamWaitEvent(rt.stream, gathered, 0));
     return;
   }
   LSB_CHECK(!complex_vectors, "all-to-all products take real vectors (as the reference's matvec)");
+  if (x_ready != nullptr) CUDA_CHECK(cudaStreamWaitEvent(rt.stream, x_ready, 0));
   LSB_CHECK(team.world <= 64, "at most 64 ranks");
   int64_t const chunk_rows = push_chunk_rows(ops[0], 0);
   int64_t rounds = 0;
@@ -697,18 +794,20 @@ static void dist_matvec(Team const &team, std::vector<ls_hs_operator const *> co
     for (size_t m = 0; m < M; ++m)
       push_consume(ops[m], *local[m], local[m]->dist->push->recv.ptr, (int64_t)received[m], y[m]);
   }
-  (void)rt;
+  if (host_y != nullptr && local[0]->number_states > 0)
+    CUDA_CHECK(cudaMemcpyAsync(host_y, y[0], sizeof(double) * (size_t)local[0]->number_states, cudaMemcpyDeviceToHost, rt.stream));
 }
 
 // Entry points for the rest of the library: the product of a basis that carries a shard layout.
 bool dist_is_sharded(ls_hs_basis const *basis) { return shard_of(basis) != nullptr; }
 
-void dist_matvec_local(ls_hs_operator const *op, double const *d_x, double *d_y, int mode, bool complex_vectors) {
+void dist_matvec_local(ls_hs_operator const *op, double const *d_x, double *d_y, int mode, bool complex_vectors,
+                       cudaEvent_t x_ready, double *host_y) {
   DistShard *sh = shard_of(op->basis);
   LSB_CHECK(sh != nullptr, "not a distributed basis");
   LSB_CHECK(sh->world == comm_world(), "the basis was sharded over a different communicator");
   Team const team = real_team();
-  dist_matvec(team, {op}, {d_x}, {d_y}, mode, complex_vectors);
+  dist_matvec(team, {op}, {d_x}, {d_y}, mode, complex_vectors, x_ready, host_y);
 }
 
 void dist_build_local(ls_hs_basis *basis, ls_hs_operator const *balance_for, int flags) {

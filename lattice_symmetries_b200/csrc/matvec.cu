@@ -586,13 +586,64 @@ count_elements_kernel(TermsView off, uint64_t const *__restrict__ reps, int64_t 
   if ((threadIdx.x & 31) == 0 && local != 0) atomicAdd(out, local);
 }
 
+// per_row[i] = matrix elements of row i (T < 32768, so 16 bits suffice)
+__global__ void __launch_bounds__(256)
+count_elements_rows_kernel(TermsView off, uint64_t const *__restrict__ reps, int64_t n, uint16_t *__restrict__ per_row) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t const alpha = reps[i];
+    unsigned c = 0;
+    for (int t = 0; t < off.number_terms; ++t) c += ((alpha & __ldg(off.m + t)) == __ldg(off.l + t)) ? 1u : 0u;
+    per_row[i] = (uint16_t)c;
+  }
+}
+// out[b] = sum of per_row over [starts[b], starts[b + 1]) (one CTA per segment, round-robin: the work per row is a
+// 2-byte read, so even a million-row segment takes microseconds)
+__global__ void __launch_bounds__(256)
+sum_segments_kernel(uint16_t const *__restrict__ per_row, uint64_t const *__restrict__ starts, int64_t number_segments,
+                    uint64_t *__restrict__ out) {
+  __shared__ unsigned long long warp_sums[8];
+  for (int64_t b = blockIdx.x; b < number_segments; b += gridDim.x) {
+    unsigned long long local = 0;
+    for (uint64_t i = starts[b] + threadIdx.x; i < starts[b + 1]; i += blockDim.x) local += per_row[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long total = 0;
+      for (int w = 0; w < 8; ++w) total += warp_sums[w];
+      out[b] = total;
+    }
+    __syncthreads();
+  }
+}
+
+// d_out[b] = matrix elements of rows [d_starts[b], d_starts[b + 1]); number_rows = d_starts[number_segments]
+void count_elements_segments(OperatorDev &od, uint64_t const *d_rows, int64_t number_rows, uint64_t const *d_starts,
+                             int64_t number_segments, uint64_t *d_out) {
+  if (number_segments <= 0) return;
+  Runtime &rt = runtime();
+  static DeviceBuffer<uint16_t> per_row;
+  uint16_t *d = per_row.reserve((size_t)number_rows + 1);
+  if (number_rows > 0) {
+    unsigned const blocks = (unsigned)std::min<int64_t>((number_rows + 255) / 256, (int64_t)rt.sm_count * 16);
+    count_elements_rows_kernel<<<blocks, 256, 0, rt.stream>>>(od.off.view(), d_rows, number_rows, d);
+  }
+  unsigned const blocks = (unsigned)std::min<int64_t>(number_segments, (int64_t)rt.sm_count * 8);
+  sum_segments_kernel<<<blocks, 256, 0, rt.stream>>>(d, d_starts, number_segments, d_out);
+  count_launch(2);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 void ensure_norms(IndexData &ix, GroupData const &g);
 
-void launch_prescale(int64_t n, bool complex_vectors, double const *norms, double const *x, double *xs) {
+void launch_prescale(int64_t n, bool complex_vectors, double const *norms, double const *x, double *xs,
+                     cudaStream_t stream) {
   if (n <= 0) return;
   Runtime &rt = runtime();
+  if (stream == nullptr) stream = rt.stream;
   unsigned const blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 16);
-  prescale_kernel<<<blocks, 256, 0, rt.stream>>>(n, complex_vectors ? 1 : 0, norms, x, xs);
+  prescale_kernel<<<blocks, 256, 0, stream>>>(n, complex_vectors ? 1 : 0, norms, x, xs);
   count_launch();
   CUDA_CHECK(cudaGetLastError());
 }
@@ -785,8 +836,7 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
     a.number_chars = 2;
   }
   if (target != nullptr) {
-    LSB_CHECK(phase == 0 && number_vectors == 1 && host_y == nullptr,
-              "distributed products take one device-resident vector at a time");
+    LSB_CHECK(phase == 0 && number_vectors == 1, "distributed products take one vector at a time");
     a.xs = target->xs;  // the replicated vector (already multiplied by the norms where the basis has them)
   }
   LSB_CHECK(a.off.number_terms < 0x8000, "too many off-diagonal terms");
@@ -1084,6 +1134,8 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
         CUDA_CHECK(cudaStreamWaitEvent(stream_b, slot.orbit_done, 0));
       }
     }
+    if (chunk_index == 0 && target != nullptr && target->xs_ready != nullptr)
+      CUDA_CHECK(cudaStreamWaitEvent(stream_b, target->xs_ready, 0));  // the replicated vector is read from here on
     if (profile) {
       sc.spans.emplace_back(sc.events_used, 1);
       CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
@@ -1532,9 +1584,28 @@ void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors, double c
       LSB_CHECK(num_vectors == 1, "distributed products take one vector at a time");
       double *d_x = sc.x.reserve(n + 1);
       double *d_y = sc.y.reserve(n + 1);
-      if (n > 0) CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
-      dist_matvec_local(op, d_x, d_y, 0, false);
-      if (n > 0) CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+      cudaPointerAttributes attr_x{}, attr_y{};
+      bool const pinned_x = cudaPointerGetAttributes(&attr_x, x) == cudaSuccess && attr_x.type == cudaMemoryTypeHost;
+      bool const pinned_y = cudaPointerGetAttributes(&attr_y, y) == cudaSuccess && attr_y.type == cudaMemoryTypeHost;
+      (void)cudaGetLastError();
+      if (pinned_x && pinned_y && n > 0) {
+        // x uploads on the copy stream under the canonicalisation of the first chunk; finished row chunks of y drain
+        // on the copy stream behind the next chunks' kernels
+        if (sc.copy_stream == nullptr) {
+          CUDA_CHECK(cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
+          CUDA_CHECK(cudaEventCreateWithFlags(&sc.copies_done, cudaEventDisableTiming));
+        }
+        if (sc.x_uploaded == nullptr) CUDA_CHECK(cudaEventCreateWithFlags(&sc.x_uploaded, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(sc.copies_done, s));  // (the previous product is through with d_x)
+        CUDA_CHECK(cudaStreamWaitEvent(sc.copy_stream, sc.copies_done, 0));
+        CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, sc.copy_stream));
+        CUDA_CHECK(cudaEventRecord(sc.x_uploaded, sc.copy_stream));
+        dist_matvec_local(op, d_x, d_y, 0, false, sc.x_uploaded, y);
+      } else {
+        if (n > 0) CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        dist_matvec_local(op, d_x, d_y, 0, false, nullptr, nullptr);
+        if (n > 0) CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+      }
       ok = matvec_finish();
       return;
     }

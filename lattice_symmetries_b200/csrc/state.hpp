@@ -93,6 +93,8 @@ struct MvTarget {
   double const *norms;    // [number_rows], or nullptr when all 1
   int64_t number_rows;
   double const *xs;       // replicated n_j x_j (x_j when norms == nullptr), indexed by `index`
+  cudaEvent_t xs_ready;   // nullptr, or: xs is complete once this event fires (the all-gather runs on another stream
+                          // under the canonicalisation of the first chunk, which does not read it)
 };
 
 // Device copies adopted from a basis build, keyed by the host pointer handed
@@ -138,8 +140,11 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
                    double *host_y = nullptr, int phase = 0, MvTarget const *target = nullptr);
 bool matvec_finish();
 extern char const *kInvalidIndexMessage;
-void launch_prescale(int64_t n, bool complex_vectors, double const *norms, double const *x, double *xs);
+void launch_prescale(int64_t n, bool complex_vectors, double const *norms, double const *x, double *xs,
+                     cudaStream_t stream = nullptr);
 int64_t count_elements(OperatorDev &od, uint64_t const *d_rows, int64_t row_begin, int64_t row_end);
+void count_elements_segments(OperatorDev &od, uint64_t const *d_rows, int64_t number_rows, uint64_t const *d_starts,
+                             int64_t number_segments, uint64_t *d_out);
 
 // Push form (all-to-all products, mirrors chapel/src/DistributedMatrixVector.chpl:545-579, 775-807): records
 // (representative, coefficient) grouped by the rank that owns the representative.
@@ -165,10 +170,24 @@ struct BuildResult {
   uint64_t *d_reps = nullptr;
   double *d_norms = nullptr;  // nullptr for unprojected bases
   uint64_t count = 0;
+  uint64_t const *d_block_starts = nullptr;  // cyclic shares: [number_blocks + 1] first row of every block (library scratch,
+                                             // valid until the next build)
 };
+// Allocation of the array that becomes basis->representatives: managed (device-resident, host-readable) when the
+// host view is wanted and supported, plain device memory otherwise.
+uint64_t *alloc_representatives(uint64_t count);
 using Ranges = std::vector<std::pair<uint64_t, uint64_t>>;
+// A rank's block-cyclic share of the candidate range: blocks of 32 << shift candidates, block b scanned by rank
+// b % world (the last block may be partial).
+struct CyclicShare {
+  int shift = 15, world = 1, rank = 0;
+  uint64_t blocks_total = 0;       // over all ranks
+  uint64_t number_blocks = 0;      // of this rank
+  uint64_t virtual_candidates = 0; // candidates in this rank's blocks
+};
+CyclicShare cyclic_share(uint64_t total, int block_shift, int world, int rank);
 BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<uint64_t> *counts = nullptr,
-                         bool host_visible = false);
+                         bool host_visible = false, CyclicShare const *cyc = nullptr);
 uint64_t number_candidates(ls_hs_basis const *basis);
 // Installs device-resident representatives (+ norms) as the basis' list: host view, index, kernels.
 void install_representatives(ls_hs_basis *basis, uint64_t *d_reps, double *d_norms, uint64_t count, int cache_bits);
@@ -182,7 +201,10 @@ IndexData *create_index_from_device(uint64_t *d_reps, int64_t count, int number_
 int comm_world();  // ranks of the active communicator (1 without one)
 bool dist_is_sharded(ls_hs_basis const *basis);
 // y_local = (H x)_local on this rank's rows; x, y device-resident, local length.  mode: 0 auto, 1 all-gather, 2 all-to-all.
-void dist_matvec_local(ls_hs_operator const *op, double const *d_x, double *d_y, int mode, bool complex_vectors);
+// x_ready (optional): d_x is complete once this event fires (an upload in flight on another stream); host_y (optional,
+// pinned): finished row chunks of d_y are also copied there on the copy stream.
+void dist_matvec_local(ls_hs_operator const *op, double const *d_x, double *d_y, int mode, bool complex_vectors,
+                       cudaEvent_t x_ready = nullptr, double *host_y = nullptr);
 void dist_build_local(ls_hs_basis *basis, ls_hs_operator const *balance_for, int flags);
 
 // Basis predicates the Chapel side asks the Haskell host for

@@ -46,7 +46,8 @@ def test_shard_bounds_partition(total, world):
 @pytest.mark.parametrize("total", [0, 1, 31, 4096, 2704156, 4537567650, 269128937220])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_block_plan_partition(total, world):
-    """Blocks tile [0, total), start on multiples of 32, begin small and never shrink (except the tail)."""
+    """Blocks tile [0, total), are equal (a power of two >= 2^20 candidates; the tail may be short) and numerous
+    enough to deal every density regime out evenly, yet at most ~8192 per rank."""
     plan = plan_blocks(total, world)
     assert sum(hi - lo for lo, hi in plan) == total
     prev = 0
@@ -55,9 +56,12 @@ def test_block_plan_partition(total, world):
         prev = hi
     assert prev == total
     sizes = [hi - lo for lo, hi in plan]
-    if len(sizes) > 1:
-        assert sizes[0] == min(1 << 20, sizes[0])
-        assert all(b >= a for a, b in zip(sizes[:-2], sizes[1:-1]))
+    if sizes:
+        block = sizes[0] if len(sizes) > 1 else None
+        if block is not None:
+            assert block >= 1 << 20 and block & (block - 1) == 0
+            assert all(s == block for s in sizes[:-1]) and sizes[-1] <= block
+        assert len(plan) <= 8192 * world + 1
     # fine enough to deal out: a long range gives every rank many blocks
     if total > (1 << 20) * 64 * world:
         assert len(plan) >= 32 * world
