@@ -270,6 +270,21 @@ struct Team {
     return table;
   }
 
+  // Minimum over all ranks of a host value (emulated: over the members).
+  int64_t min_host(std::vector<int64_t> const &mine) const {
+    int64_t local = mine[0];
+    for (int64_t v : mine) local = std::min(local, v);
+    if (emulated) return local;
+    Runtime &rt = runtime();
+    static DeviceBuffer<int64_t> stage;
+    int64_t *d = stage.reserve(1);
+    CUDA_CHECK(cudaMemcpyAsync(d, &local, sizeof local, cudaMemcpyHostToDevice, rt.stream));
+    NCCL_CHECK(nccl().AllReduce(d, d, 1, ncclInt64, ncclMin, g_comm.comm, rt.stream));
+    CUDA_CHECK(cudaMemcpyAsync(&local, d, sizeof local, cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    return local;
+  }
+
   // Personalised exchange; counts and displacements in bytes, [member][peer].
   void all_to_all_v(std::vector<unsigned char const *> const &send, std::vector<std::vector<size_t>> const &sdispl,
                     std::vector<std::vector<size_t>> const &scount, std::vector<unsigned char *> const &recv,
@@ -388,6 +403,16 @@ place_kernel(PlaceDev const *__restrict__ places, int64_t n, uint64_t const *__r
   }
 }
 
+static std::vector<std::unique_ptr<DeviceBuffer<uint64_t>>> &receive_buffers() {
+  static std::vector<std::unique_ptr<DeviceBuffer<uint64_t>>> buffers;
+  return buffers;
+}
+// Scratch that grew with the basis is kept for the next build only while it is small.
+static void release_redistribute_scratch(size_t above_bytes) {
+  for (auto &b : receive_buffers())
+    if (b->capacity * sizeof(uint64_t) > above_bytes) b->release();
+}
+
 // data[m]: the pieces owned by member m, concatenated (device); replaced by its new rows, in a buffer obtained from
 // `allocate(elements)` -- the old buffer is freed.  The receive buffers live for the process (grow-only): with peer
 // access enabled every cudaMalloc / cudaFree maps or unmaps on all GPUs and costs milliseconds.
@@ -400,7 +425,7 @@ static void redistribute(Team const &team, std::vector<Piece> const &pieces, std
   std::vector<unsigned char const *> send(M);
   std::vector<unsigned char *> recv(M), fresh(M);
   std::vector<std::vector<size_t>> sd(M), sc(M), rd(M), rc(M);
-  static std::vector<std::unique_ptr<DeviceBuffer<uint64_t>>> receive;
+  auto &receive = receive_buffers();
   while (receive.size() < M) receive.push_back(std::make_unique<DeviceBuffer<uint64_t>>());
   for (size_t m = 0; m < M; ++m) {
     plans.push_back(plan_redistribution(team.world, team.members[m], pieces, bounds));
@@ -446,6 +471,7 @@ static void redistribute(Team const &team, std::vector<Piece> const &pieces, std
   }
 }
 
+static void release_redistribute_scratch(size_t above_bytes);
 static void *allocate_representatives(uint64_t elements) { return alloc_representatives(elements); }
 static void *allocate_plain(uint64_t elements) {
   void *p = nullptr;
@@ -475,6 +501,31 @@ static void build_global_index(Team const &team, std::vector<ls_hs_basis *> cons
   bool wide = (flags & kDistWideIndex) != 0 || dim >= (int64_t(1) << 32) || (size_t)dim * 8 > (size_t(8) << 30);
   if (char const *env = getenv("LS_B200_DIST_INDEX")) wide = strcmp(env, "wide") == 0 ? true : (dim < (int64_t(1) << 32) ? false : wide);
   std::vector<size_t> row_displs((size_t)team.world + 1);
+  {
+    // Does the all-gather form fit?  It needs the replicated lookup structure and the replicated vector on EVERY rank,
+    // next to what the caller still wants for itself (its Krylov vectors: LS_B200_DIST_RESERVE_GB, default four local
+    // vectors + 4 GB).  All ranks must come to the same answer: the minimum of the free memory decides.
+    int const pb = index_choose_prefix_bits(dim, number_bits);
+    size_t const key_bytes_est = number_bits - pb <= 16 ? 2 : 4;
+    size_t need = (size_t)dim * 8;  // replicated pre-scaled vector
+    need += wide ? (size_t)dim * key_bytes_est + ((size_t(1) << pb) + 1) * 8
+                 : (size_t)dim * (8 + key_bytes_est) + ((size_t(1) << pb) + 1) * 20;
+    int64_t most_rows = 0;
+    for (int r = 0; r < team.world; ++r) most_rows = std::max(most_rows, first.bounds[(size_t)r + 1] - first.bounds[(size_t)r]);
+    size_t reserve = (size_t)most_rows * 8 * 4 + (size_t(4) << 30);
+    if (char const *env = getenv("LS_B200_DIST_RESERVE_GB")) reserve = (size_t)(atof(env) * (double)(size_t(1) << 30));
+    size_t free_bytes = 0, total_bytes = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_bytes, &total_bytes));
+    if (team.emulated) free_bytes /= std::max<size_t>(1, M);  // virtual ranks share one device
+    int64_t const headroom = team.min_host({(int64_t)free_bytes - (int64_t)(need + need / 16) - (int64_t)reserve});
+    if (headroom < 0) {
+      if (getenv("LS_B200_PROFILE") != nullptr)
+        fprintf(stderr, "[ls_b200] dist_build: the all-gather form needs %.1f GB per rank (+ %.1f GB reserve), %.1f GB are "
+                        "free: products take the all-to-all form\n",
+                (double)need / 1e9, (double)reserve / 1e9, (double)free_bytes / 1e9);
+      return;
+    }
+  }
   if (!wide) {
     std::vector<unsigned char *> full(M);
     for (size_t r = 0; r <= (size_t)team.world; ++r) row_displs[r] = (size_t)first.bounds[r] * 8;
@@ -482,7 +533,7 @@ static void build_global_index(Team const &team, std::vector<ls_hs_basis *> cons
       IndexData *local = index_of(bases[m]);
       DistShard &sh = *local->dist;
       void *p = nullptr;
-      CUDA_CHECK(cudaMalloc(&p, (size_t)dim * 8));
+      p = alloc_local((size_t)dim * 8);
       full[m] = static_cast<unsigned char *>(p);
       if (local->number_states > 0)
         CUDA_CHECK(cudaMemcpyAsync(full[m] + row_displs[(size_t)sh.rank], local->d_reps, (size_t)local->number_states * 8,
@@ -494,7 +545,8 @@ static void build_global_index(Team const &team, std::vector<ls_hs_basis *> cons
           create_index_from_device(reinterpret_cast<uint64_t *>(full[m]), dim, number_bits, 22);
     return;
   }
-  int const prefix_bits = index_choose_prefix_bits(dim, number_bits);
+  int prefix_bits = index_choose_prefix_bits(dim, number_bits);
+  if (char const *env = getenv("LS_B200_DIST_PREFIX")) prefix_bits = std::max(1, std::min(atoi(env), number_bits));  // A/B knob
   int const shift = number_bits - prefix_bits;
   if (shift > 32) return;  // no compact keys: only the all-to-all form is available
   int const key_bytes = shift <= 16 ? 2 : 4;
@@ -506,9 +558,9 @@ static void build_global_index(Team const &team, std::vector<ls_hs_basis *> cons
     IndexData *local = index_of(bases[m]);
     DistShard &sh = *local->dist;
     void *k = nullptr;
-    CUDA_CHECK(cudaMalloc(&k, (size_t)dim * (size_t)key_bytes));
+    k = alloc_local((size_t)dim * (size_t)key_bytes);
     keys[m] = static_cast<unsigned char *>(k);
-    CUDA_CHECK(cudaMalloc(&offsets[m], sizeof(int64_t) * (size_t)number_offsets));
+    alloc_local(&offsets[m], sizeof(int64_t) * (size_t)number_offsets);
     index_local_keys(local->d_reps, local->number_states, shift, keys[m] + row_displs[(size_t)sh.rank], key_bytes);
     index_local_offsets64(local->d_reps, local->number_states, shift, number_offsets, offsets[m]);
   }
@@ -658,6 +710,8 @@ static void dist_build(Team const &team, std::vector<ls_hs_basis *> const &bases
     sh.push = new PushBuffers();
   }
   lap("install + local index");
+  release_redistribute_scratch(size_t(1) << 30);
+  release_count_scratch(size_t(1) << 30);
   // 6. replicated lookup structure of the all-gather products
   if ((flags & kDistNoGlobalIndex) == 0) build_global_index(team, bases, flags);
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
@@ -703,7 +757,7 @@ static void dist_matvec(Team const &team, std::vector<ls_hs_operator const *> co
       if (sh.xs_full_words < words) {
         cudaFree(sh.d_xs_full);
         sh.d_xs_full = nullptr;
-        CUDA_CHECK(cudaMalloc(&sh.d_xs_full, sizeof(double) * words));
+        alloc_local(&sh.d_xs_full, sizeof(double) * words);
         sh.xs_full_words = words;
       }
       full[m] = reinterpret_cast<unsigned char *>(sh.d_xs_full);
@@ -728,12 +782,30 @@ static void dist_matvec(Team const &team, std::vector<ls_hs_operator const *> co
       gathered = done;
     }
     if (x_ready != nullptr) CUDA_CHECK(cudaStreamWaitEvent(side, x_ready, 0));
+    // LS_B200_PROFILE: device time of pre-scaling + all-gather, reported by the NEXT product (no extra sync)
+    static bool const profile = getenv("LS_B200_PROFILE") != nullptr;
+    static cudaEvent_t t_begin = nullptr, t_end = nullptr;
+    static bool timed = false;
+    if (profile && !team.emulated) {
+      if (t_begin == nullptr) {
+        CUDA_CHECK(cudaEventCreate(&t_begin));
+        CUDA_CHECK(cudaEventCreate(&t_end));
+      } else if (timed && cudaEventQuery(t_end) == cudaSuccess) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t_begin, t_end) == cudaSuccess) runtime().last_allgather_ms = ms;
+      }
+      CUDA_CHECK(cudaEventRecord(t_begin, side));
+    }
     for (size_t m = 0; m < M; ++m) {
       DistShard &sh = *local[m]->dist;
       launch_prescale(local[m]->number_states, complex_vectors, local[m]->d_norms, x[m],
                       sh.d_xs_full + (size_t)sh.bounds[(size_t)sh.rank] * scalar, side);
     }
     team.all_gather_v(full, displs, side);
+    if (profile && !team.emulated) {
+      CUDA_CHECK(cudaEventRecord(t_end, side));
+      timed = true;
+    }
     if (overlap) CUDA_CHECK(cudaEventRecord(gathered, side));
     for (size_t m = 0; m < M; ++m) {
       DistShard &sh = *local[m]->dist;

@@ -215,11 +215,11 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
   int64_t const number_offsets = (int64_t(1) << ix.prefix_bits) + 1;
   unsigned const blocks = (unsigned)std::min<int64_t>((number_offsets + 255) / 256, (int64_t)rt.sm_count * 16);
   if (ix.number_states < (int64_t(1) << 32)) {
-    CUDA_CHECK(cudaMalloc(&ix.d_offsets32, sizeof(uint32_t) * (size_t)number_offsets));
+    alloc_local(&ix.d_offsets32, sizeof(uint32_t) * (size_t)number_offsets);
     bucket_offsets_kernel<uint32_t><<<blocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, ix.shift,
                                                                  number_offsets, ix.d_offsets32);
   } else {
-    CUDA_CHECK(cudaMalloc(&ix.d_offsets64, sizeof(int64_t) * (size_t)number_offsets));
+    alloc_local(&ix.d_offsets64, sizeof(int64_t) * (size_t)number_offsets);
     bucket_offsets_kernel<int64_t><<<blocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, ix.shift,
                                                                 number_offsets, ix.d_offsets64);
   }
@@ -228,11 +228,11 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
   uint64_t const mask = ix.shift >= 64 ? ~uint64_t(0) : ((uint64_t(1) << ix.shift) - 1);
   unsigned const lblocks = (unsigned)std::min<int64_t>((ix.number_states + 255) / 256, (int64_t)rt.sm_count * 16);
   if (ix.shift <= 16) {
-    CUDA_CHECK(cudaMalloc(&ix.d_lows16, sizeof(uint16_t) * (size_t)ix.number_states));
+    alloc_local(&ix.d_lows16, sizeof(uint16_t) * (size_t)ix.number_states);
     low_bits_kernel<uint16_t><<<lblocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, mask, ix.d_lows16);
     count_launch();
   } else if (ix.shift <= 32) {
-    CUDA_CHECK(cudaMalloc(&ix.d_lows32, sizeof(uint32_t) * (size_t)ix.number_states));
+    alloc_local(&ix.d_lows32, sizeof(uint32_t) * (size_t)ix.number_states);
     low_bits_kernel<uint32_t><<<lblocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, mask, ix.d_lows32);
     count_launch();
   }
@@ -249,7 +249,7 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
     // second level: sizes -> exclusive scan -> fill; dropped when nothing is crowded
     int64_t const nb = number_offsets - 1;
     uint32_t *d_units = nullptr;
-    CUDA_CHECK(cudaMalloc(&d_units, sizeof(uint32_t) * (size_t)(nb + 1)));  // becomes sub_info
+    alloc_local(&d_units, sizeof(uint32_t) * (size_t)(nb + 1));  // becomes sub_info
     uint32_t *d_first = first_buffer.reserve((size_t)(nb + 1));
     CUDA_CHECK(cudaMemsetAsync(d_units + nb, 0, sizeof(uint32_t), rt.stream));
     sub_sizes_kernel<<<blocks, 256, 0, rt.stream>>>(ix.d_offsets32, nb, ix.shift, d_units);
@@ -263,8 +263,8 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
     CUDA_CHECK(cudaStreamSynchronize(rt.stream));
     // (no 32-bit wrap: a crowded bucket of n states adds at most n / 64 + 1 units and n sums to < 2^32)
     if (total_units > 0 && total_units < (1u << 27)) {
-      CUDA_CHECK(cudaMalloc(&ix.d_subtab, sizeof(uint32_t) * (size_t)total_units * 8));
-      CUDA_CHECK(cudaMalloc(&ix.d_entry8, sizeof(uint2) * (size_t)nb));
+      alloc_local(&ix.d_subtab, sizeof(uint32_t) * (size_t)total_units * 8);
+      alloc_local(&ix.d_entry8, sizeof(uint2) * (size_t)nb);
       IndexView v = ix.view();
       v.sub_info = nullptr;
       v.entry8 = nullptr;

@@ -40,6 +40,7 @@
 //                      gathers conj(chi) w sign xs[j], sums in term order and
 //                      writes y[i] once.
 // Unprojected bases (and spin-inversion-only ones) skip the first two kernels.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -251,7 +252,7 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
   for (int u = 0; u < kRankBatch; ++u) {
     uint64_t const q = warp_q0 + (uint64_t)u * 32 + lane;
     live[u] = q < total;
-    needle[u] = live[u] ? __ldcs(a.q_rep + q) : 0;
+    needle[u] = live[u] ? (a.perm != nullptr ? __ldcs(a.q_sorted + q) : __ldcs(a.q_rep + q)) : 0;
   }
   int64_t j[kRankBatch];
   if (a.debug_skip & 8) {  // profiling only: no index search
@@ -275,7 +276,8 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
 #pragma unroll
   for (int u = 0; u < kRankBatch; ++u) {
     if (!live[u]) continue;
-    uint64_t const q = warp_q0 + (uint64_t)u * 32 + lane;
+    uint64_t q = warp_q0 + (uint64_t)u * 32 + lane;
+    if (a.perm != nullptr) q = __ldcs(a.perm + q);  // sorted ranking: back to the element's CSR position
     bool const missing = j[u] < 0;
     double fr = 1.0, fi = 0.0;
     if (product) {
@@ -618,13 +620,20 @@ sum_segments_kernel(uint16_t const *__restrict__ per_row, uint64_t const *__rest
   }
 }
 
+static DeviceBuffer<uint16_t> &per_row_scratch() {
+  static DeviceBuffer<uint16_t> b;
+  return b;
+}
+void release_count_scratch(size_t above_bytes) {
+  if (per_row_scratch().capacity * sizeof(uint16_t) > above_bytes) per_row_scratch().release();
+}
+
 // d_out[b] = matrix elements of rows [d_starts[b], d_starts[b + 1]); number_rows = d_starts[number_segments]
 void count_elements_segments(OperatorDev &od, uint64_t const *d_rows, int64_t number_rows, uint64_t const *d_starts,
                              int64_t number_segments, uint64_t *d_out) {
   if (number_segments <= 0) return;
   Runtime &rt = runtime();
-  static DeviceBuffer<uint16_t> per_row;
-  uint16_t *d = per_row.reserve((size_t)number_rows + 1);
+  uint16_t *d = per_row_scratch().reserve((size_t)number_rows + 1);
   if (number_rows > 0) {
     unsigned const blocks = (unsigned)std::min<int64_t>((number_rows + 255) / 256, (int64_t)rt.sm_count * 16);
     count_elements_rows_kernel<<<blocks, 256, 0, rt.stream>>>(od.off.view(), d_rows, number_rows, d);
@@ -674,6 +683,8 @@ struct ChunkSlot {
   DeviceBuffer<uint8_t> q_cidx;
   DeviceBuffer<uint16_t> q_tsign;
   DeviceBuffer<double> vals;
+  DeviceBuffer<uint64_t> q_sorted;  // sorted ranking
+  DeviceBuffer<uint32_t> perm;
   cudaEvent_t orbit_done = nullptr, released = nullptr;
 };
 struct MatvecScratch {
@@ -695,6 +706,9 @@ struct MatvecScratch {
   cudaEvent_t copies_done = nullptr, x_uploaded = nullptr;
   DeviceBuffer<unsigned char> scan_tmp;
   size_t scan_tmp_bytes = 0;
+  DeviceBuffer<unsigned char> sort_tmp;  // sorted ranking: cub radix-sort scratch, positions 0, 1, 2, ...
+  DeviceBuffer<uint32_t> iota;
+  size_t iota_filled = 0;
   int *d_error = nullptr;
   double2 *d_plain_chars = nullptr;  // {1, +1, -1}: character table of the unprojected / inversion-only modes
   // per-kernel device time of the last matvec (LS_B200_PROFILE=1): events around every orbit / gather launch
@@ -726,6 +740,62 @@ static void release_phase_slots() {
   sc.phase_op = nullptr;
   sc.phase_index = nullptr;
   sc.phase_ready = false;
+}
+
+__global__ void iota_kernel(uint32_t *__restrict__ out, size_t begin, size_t end) {
+  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (uint32_t)i;
+}
+__global__ void segment_starts_kernel(uint64_t *__restrict__ starts, int64_t number_segments, int64_t row_begin,
+                                      int64_t row_end, int64_t segment_rows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= number_segments; i += (int64_t)gridDim.x * blockDim.x)
+    starts[i] = (uint64_t)min(row_end, row_begin + i * segment_rows);
+}
+
+// Chunks of rows holding at most `capacity` matrix elements each, cut at multiples of 16384 rows by exact counts
+// (one counting pass, cached): the sorted-ranking path sizes its sorts and buffers by them.
+static OperatorDev::ChunkPlan const &chunk_plan(OperatorDev &od, uint64_t const *d_rows, int64_t row_begin, int64_t row_end,
+                                                int64_t capacity) {
+  OperatorDev::ChunkPlan &p = od.plan;
+  if (p.rows == d_rows && p.row_begin == row_begin && p.row_end == row_end && p.capacity == capacity && p.version == od.version)
+    return p;
+  Runtime &rt = runtime();
+  int64_t const T = std::max(1, od.off.number_terms);
+  int64_t segment_rows = 16384;
+  while (segment_rows > 1 && segment_rows * T > capacity) segment_rows /= 2;  // a segment always fits
+  int64_t const ns = (row_end - row_begin + segment_rows - 1) / segment_rows;
+  static DeviceBuffer<uint64_t> starts, sums;
+  uint64_t *d_starts = starts.reserve((size_t)ns + 1);
+  uint64_t *d_sums = sums.reserve((size_t)ns + 1);
+  segment_starts_kernel<<<(unsigned)std::min<int64_t>((ns + 256) / 256, 1024), 256, 0, rt.stream>>>(d_starts, ns, row_begin,
+                                                                                                  row_end, segment_rows);
+  count_launch();
+  // (count_elements_segments indexes rows from 0: hand it the rows of this call)
+  count_elements_segments(od, d_rows, row_end, d_starts, ns, d_sums);
+  std::vector<uint64_t> h((size_t)ns);
+  CUDA_CHECK(cudaMemcpyAsync(h.data(), d_sums, sizeof(uint64_t) * (size_t)ns, cudaMemcpyDeviceToHost, rt.stream));
+  CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+  release_count_scratch(size_t(1) << 30);
+  p.begin.assign(1, row_begin);
+  p.elements.clear();
+  int64_t acc = 0;
+  for (int64_t i = 0; i < ns; ++i) {
+    int64_t const n = (int64_t)h[(size_t)i];
+    if (acc > 0 && acc + n > capacity) {
+      p.begin.push_back(row_begin + i * segment_rows);
+      p.elements.push_back(acc);
+      acc = 0;
+    }
+    acc += n;
+  }
+  p.begin.push_back(row_end);
+  p.elements.push_back(acc);
+  p.rows = d_rows;
+  p.row_begin = row_begin;
+  p.row_end = row_end;
+  p.capacity = capacity;
+  p.version = od.version;
+  return p;
 }
 
 template <class K>
@@ -902,13 +972,41 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
   bool const phased = phase != 0 && split && T > 0 && a.mode == kModeGroup && a.number_vectors == 1;
   if (phased) pipelined = false;
   int const number_slots = phased ? 0 : (pipelined ? 2 : 1);
+  // Sorted ranking (LS_B200_MV_SORT=1, off by default).  The chunk's representatives are radix-sorted by their
+  // leading bits before the index search, so that consecutive threads walk the level-1 table, the keys and the vector
+  // in ascending order, and the values are scattered back to CSR order; chunks are cut by exact element counts.
+  // Bit-identical results.  Measured on a 17 GB footprint (chain-40, translations only: 3.5e10 elements): the sort
+  // costs 2.0 s against a 0.76 s unsorted rank + gather, whose random accesses the memory system sustains as long as
+  // the tables are mapped with large pages (see alloc_local) -- so it stays an A/B knob.
+  bool sorted = false;
+  if (split && queued && want_tsign && a.number_vectors == 1 && phase == 0 && !pipelined && a.mode == kModeGroup) {
+    if (char const *env = getenv("LS_B200_MV_SORT")) sorted = atoi(env) != 0;
+  }
+  OperatorDev::ChunkPlan const *plan = nullptr;
+  int sort_begin_bit = 0, sort_end_bit = 64;
+  if (sorted) {
+    plan = &chunk_plan(od, a.rows, row_begin, row_end, capacity);
+    int sort_bits = 24;
+    if (char const *env = getenv("LS_B200_MV_SORT_BITS")) sort_bits = std::max(1, atoi(env));
+    sort_end_bit = std::max(1, info.number_bits);
+    sort_begin_bit = std::max(0, sort_end_bit - sort_bits);
+  }
   if (queued) {
-    chunk_rows = std::max<int64_t>(1, std::min<int64_t>(chunk_rows, capacity / T));
-    capacity = chunk_rows * T;
+    if (sorted) {
+      chunk_rows = 1;
+      for (size_t c = 0; c + 1 < plan->begin.size(); ++c) chunk_rows = std::max(chunk_rows, plan->begin[c + 1] - plan->begin[c]);
+    } else {
+      chunk_rows = std::max<int64_t>(1, std::min<int64_t>(chunk_rows, capacity / T));
+      capacity = chunk_rows * T;
+    }
     for (int k = 0; k < number_slots; ++k) {
       ChunkSlot &slot = sc.slot[k];
       slot.counts.reserve((size_t)chunk_rows + 1);
       slot.offsets.reserve((size_t)chunk_rows + 1);
+      if (sorted) {
+        slot.q_sorted.reserve((size_t)capacity + 32);
+        slot.perm.reserve((size_t)capacity + 32);
+      }
       if (split || fused)
         slot.vals.reserve(((size_t)capacity + 32) * (complex_vectors ? 2 : 1) * (size_t)a.number_vectors);
       if (!fused) {
@@ -926,6 +1024,18 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
     if (tmp > sc.scan_tmp_bytes) {
       sc.scan_tmp.reserve(tmp);
       sc.scan_tmp_bytes = sc.scan_tmp.capacity;
+    }
+    if (sorted) {
+      size_t bytes = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint64_t const *)nullptr, (uint64_t *)nullptr, (uint32_t const *)nullptr,
+                                      (uint32_t *)nullptr, (int)capacity, sort_begin_bit, sort_end_bit, rt.stream);
+      sc.sort_tmp.reserve(bytes);
+      uint32_t *iota = sc.iota.reserve((size_t)capacity + 32);
+      if (sc.iota_filled < (size_t)capacity || sc.iota.capacity != sc.iota_filled) {
+        iota_kernel<<<rt.sm_count * 8, 256, 0, rt.stream>>>(iota, 0, sc.iota.capacity);
+        count_launch();
+        sc.iota_filled = sc.iota.capacity;
+      }
     }
     if (a.mode == kModeGroup) {
       LSB_CHECK(np >= 4 && np <= 64 && (np & 3) == 0, "unsupported number of bits");
@@ -1098,8 +1208,8 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
   }
 
   int64_t chunk_index = 0;
-  for (int64_t begin = row_begin; begin < row_end; begin += chunk_rows, ++chunk_index) {
-    int64_t const nrows = std::min(chunk_rows, row_end - begin);
+  for (int64_t begin = row_begin; begin < row_end; ++chunk_index) {
+    int64_t const nrows = sorted ? plan->begin[(size_t)chunk_index + 1] - begin : std::min(chunk_rows, row_end - begin);
     ChunkSlot &slot = sc.slot[pipelined ? (chunk_index & 1) : 0];
     a.chunk_begin = begin;
     a.chunk_rows = (int)nrows;
@@ -1143,7 +1253,23 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
     if (fused && queued) {
       row_sum<<<ceil_div((size_t)nrows, 256), 256, sum_smem, stream_b>>>(a);
     } else if (split && queued) {
-      size_t const max_tiles = ceil_div((size_t)nrows * (size_t)T, 32 * kRankBatch);
+      size_t max_tiles = ceil_div((size_t)nrows * (size_t)T, 32 * kRankBatch);
+      a.perm = nullptr;
+      a.q_sorted = nullptr;
+      if (sorted) {
+        int64_t const n = plan->elements[(size_t)chunk_index];
+        LSB_CHECK(n <= capacity, "chunk plan exceeds the buffer capacity");
+        max_tiles = ceil_div((size_t)std::max<int64_t>(n, 1), 32 * kRankBatch);
+        if (n > 0) {
+          size_t bytes = sc.sort_tmp.capacity;
+          cub::DeviceRadixSort::SortPairs(sc.sort_tmp.ptr, bytes, (uint64_t const *)a.q_rep, slot.q_sorted.ptr,
+                                          (uint32_t const *)sc.iota.ptr, slot.perm.ptr, (int)n, sort_begin_bit, sort_end_bit,
+                                          stream_b);
+          count_launch(4);
+          a.perm = slot.perm.ptr;
+          a.q_sorted = slot.q_sorted.ptr;
+        }
+      }
       size_t const rank_smem = a.q_tsign != nullptr ? ((size_t)T + (size_t)a.number_chars) * 16 : 0;
       unsigned const blocks = std::min<unsigned>(ceil_div(max_tiles, kRankThreads / 32), rank_resident);
       rank_gather<<<blocks, kRankThreads, rank_smem, stream_b>>>(a);
@@ -1164,6 +1290,7 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
     if (pipelined) CUDA_CHECK(cudaEventRecord(slot.released, stream_b));
     CUDA_CHECK(cudaGetLastError());
     drain(chunk_index, begin, nrows, stream_b);
+    begin += nrows;
   }
   drain_finish();
   CUDA_CHECK(cudaEventRecord(rt.ev1, rt.stream));

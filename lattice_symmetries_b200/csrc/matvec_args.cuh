@@ -50,6 +50,10 @@ struct MatvecArgs {
   uint8_t *q_cidx;       // [capacity] index of the minimising character
   uint16_t *q_tsign;     // [capacity] split path: term | sign << 15 of every matrix element (nullptr: not recorded)
   double *vals;          // [capacity] (x2 when complex) fused path: conj(chi) w sign n_j x_j of every matrix element
+  // sorted ranking (large bases, see matvec_device): q_sorted[k] = the k-th smallest representative of the chunk (by its
+  // leading bits), perm[k] = its position in CSR order; nullptr: rank in CSR order
+  uint64_t const *q_sorted;
+  uint32_t const *perm;
   // block matvec (split path): vector v reads x + v x_stride / xs + v x_stride, writes y + v y_stride and
   // vals + v vals_stride (strides in scalars of the vector type)
   int number_vectors;

@@ -53,6 +53,23 @@ void Runtime::ensure() {
   CUDA_CHECK(cudaEventCreate(&ev1));
 }
 
+// Allocation of the large randomly-accessed tables (index levels, keys, the replicated vector).  Default: cudaMalloc.
+// LS_B200_POOL_MALLOC=1: stream-ordered allocations from the device's default memory pool, which -- unlike cudaMalloc
+// once peer access is enabled -- is mapped by this device only.  A/B on 2 x B200 (chain-40, 17 GB of tables, random
+// 8-byte gathers): no difference in kernel time (397 ms either way), so the plain allocator stays the default.
+void *alloc_local(size_t bytes) {
+  Runtime &rt = runtime();
+  void *p = nullptr;
+  static bool const plain = getenv("LS_B200_POOL_MALLOC") == nullptr;  // A/B knob
+  if (plain) {
+    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 8)));
+    return p;
+  }
+  CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(bytes, 8), rt.stream));
+  CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+  return p;
+}
+
 std::unordered_map<void const *, BuiltReps> &built_registry() {
   static std::unordered_map<void const *, BuiltReps> m;
   return m;
@@ -148,6 +165,7 @@ double ls_b200_last_kernel_ms(char const *name) {
   if (name != nullptr && strcmp(name, "orbit") == 0) return rt.last_orbit_ms;
   if (name != nullptr && strcmp(name, "gather") == 0) return rt.last_gather_ms;
   if (name != nullptr && strcmp(name, "combine") == 0) return rt.last_combine_ms;
+  if (name != nullptr && strcmp(name, "allgather") == 0) return rt.last_allgather_ms;  // of the product BEFORE the last one
   if (name != nullptr && strcmp(name, "orbit_launches") == 0) return (double)rt.last_orbit_launches;
   if (name != nullptr && strcmp(name, "gather_launches") == 0) return (double)rt.last_gather_launches;
   return rt.last_matvec_ms;

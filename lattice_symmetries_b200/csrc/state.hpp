@@ -131,6 +131,14 @@ struct OperatorDev {
   void const *stats_index = nullptr;
   int64_t stats_rows = -1;
   int64_t stats_elements = 0;
+  // sorted ranking: chunks of rows cut by exact matrix-element counts (matvec_device), cached per row set
+  struct ChunkPlan {
+    void const *rows = nullptr;
+    int64_t row_begin = -1, row_end = -1, capacity = 0;
+    uint64_t version = 0;
+    std::vector<int64_t> begin;     // [chunks + 1] first row of every chunk
+    std::vector<int64_t> elements;  // [chunks] off-diagonal matrix elements of every chunk
+  } plan;
 };
 OperatorDev &operator_dev(ls_hs_operator const *op);
 
@@ -143,6 +151,7 @@ extern char const *kInvalidIndexMessage;
 void launch_prescale(int64_t n, bool complex_vectors, double const *norms, double const *x, double *xs,
                      cudaStream_t stream = nullptr);
 int64_t count_elements(OperatorDev &od, uint64_t const *d_rows, int64_t row_begin, int64_t row_end);
+void release_count_scratch(size_t above_bytes);
 void count_elements_segments(OperatorDev &od, uint64_t const *d_rows, int64_t number_rows, uint64_t const *d_starts,
                              int64_t number_segments, uint64_t *d_out);
 

@@ -98,6 +98,23 @@ def test_emulated_products_match_oracle(oracle, name, world, flags, balance, mon
         assert team.layouts[0].global_index == 2   # the wide index was asked for and built
 
 
+@pytest.mark.parametrize("name", ["chain24_symm", "kagome24_c2v_inv", "chain40_hw3"])
+@pytest.mark.parametrize("world,flags", [(2, 0), (3, 2)])
+def test_emulated_allgather_sorted_ranking(oracle, name, world, flags, monkeypatch):
+    """The all-gather form with the sorted ranking (what a kagome-42 rank runs), two-level and wide replicated index."""
+    from lattice_symmetries_b200.distributed import ALLGATHER
+    monkeypatch.setenv("LS_B200_MV_SORT", "1")
+    monkeypatch.setenv("LS_B200_MV_CHUNK", "20000")
+    p = _problems()[name]()
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    team = _emulated(p, world, flags, True)
+    if team.layouts[0].global_index == 0:
+        pytest.skip("no compact keys for this shape: only the all-to-all form exists")
+    x = np.random.default_rng(15).standard_normal(reps.shape[0])
+    want = oracle.matvec(ob, off, diag, index, x)[0]
+    assert _rel_err(team.matvec(x, ALLGATHER), want) <= MATVEC_RTOL
+
+
 @pytest.mark.parametrize("name", ["ladder_2x8_dm", "kagome12_complex", "chain20_k3"])
 @pytest.mark.parametrize("world,flags", [(2, 0), (3, 2)])
 def test_emulated_complex_allgather_equals_single_gpu(oracle, name, world, flags):
@@ -117,6 +134,20 @@ def test_emulated_complex_allgather_equals_single_gpu(oracle, name, world, flags
     team = _emulated(p, world, flags)
     got = team.matvec(x, ALLGATHER)
     assert _rel_err(got, want) <= MATVEC_RTOL
+
+
+def test_allgather_form_is_dropped_when_it_does_not_fit(oracle, monkeypatch):
+    """The replicated index + vector must fit next to the caller's reserve on every rank; otherwise the build leaves
+    them out and the automatic product form is all-to-all."""
+    from lattice_symmetries_b200.distributed import AUTO
+    monkeypatch.setenv("LS_B200_DIST_RESERVE_GB", "100000")
+    p = _problems()["kagome18_c2"]()
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    team = _emulated(p, 3)
+    assert all(L.global_index == 0 for L in team.layouts)
+    x = np.random.default_rng(2).standard_normal(reps.shape[0])
+    want = oracle.matvec(ob, off, diag, index, x)[0]
+    assert _rel_err(team.matvec(x, AUTO), want) <= MATVEC_RTOL
 
 
 def test_emulated_alltoall_invalid_sector_raises(oracle):

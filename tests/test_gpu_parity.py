@@ -370,6 +370,50 @@ def test_matvec_pipeline_variants_agree(oracle, built, name, chunk, monkeypatch)
         assert _rel_err(y2, y0) < MATVEC_RTOL, variant
 
 
+@pytest.mark.parametrize("name", ["chain16_symm", "chain24_symm", "kagome24_c2v_inv", "kagome18_c2", "chain40_hw3"])
+@pytest.mark.parametrize("chunk,bits", [(None, None), ("8192", "6"), ("300000", "64")])
+def test_matvec_sorted_ranking_is_bit_identical(oracle, built, name, chunk, bits, monkeypatch):
+    """Sorted ranking (the large-footprint path: representatives radix-sorted by their leading bits before the index
+    search, values scattered back to CSR order) changes the ORDER of the lookups only: y is bit-identical, with
+    chunks cut by element count (tiny, uneven, single) and any number of sort bits."""
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    x = np.random.default_rng(16).standard_normal(reps.shape[0])
+    monkeypatch.setenv("LS_B200_MV_SORT", "0")
+    y0 = op.apply_to_state_vector(x)
+    monkeypatch.setenv("LS_B200_MV_SORT", "1")
+    if chunk is not None:
+        monkeypatch.setenv("LS_B200_MV_CHUNK", chunk)
+        monkeypatch.setenv("LS_B200_MV_SORT_BITS", bits)
+    y1 = op.apply_to_state_vector(x)
+    assert np.array_equal(y1, y0)
+    want = oracle.matvec(ob, off, diag, index, x)[0]
+    assert _rel_err(y1, want) < MATVEC_RTOL
+    # device-resident entry point on a row range
+    from lattice_symmetries_b200 import _lib
+    dim = reps.shape[0]
+    d_x = _lib.DeviceArray.from_numpy(x)
+    d_y = _lib.DeviceArray(dim, np.float64)
+    lo, hi = dim // 3, dim - dim // 5
+    op.matvec_device(d_x.ptr, d_y.ptr, lo, hi, sync=True)
+    assert np.array_equal(d_y.numpy()[:hi - lo], y0[lo:hi])
+
+
+@pytest.mark.parametrize("name", ["ladder_2x8_dm", "kagome12_complex"])
+def test_matvec_sorted_ranking_complex(oracle, built, name, monkeypatch):
+    from lattice_symmetries_b200 import _lib
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    dim = reps.shape[0]
+    d_x = _lib.DeviceArray.from_numpy(np.random.default_rng(8).standard_normal(dim) + 1j * np.random.default_rng(9).standard_normal(dim))
+    d_y = _lib.DeviceArray(dim, np.complex128)
+    monkeypatch.setenv("LS_B200_MV_SORT", "0")
+    op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
+    y0 = d_y.numpy().copy()
+    monkeypatch.setenv("LS_B200_MV_SORT", "1")
+    monkeypatch.setenv("LS_B200_MV_CHUNK", "4096")
+    op.matvec_device(d_x.ptr, d_y.ptr, complex_vectors=True, sync=True)
+    assert np.array_equal(d_y.numpy(), y0)
+
+
 @pytest.mark.parametrize("name", ["ladder_2x8_dm", "kagome12_complex"])
 def test_matvec_complex_pipeline_variants_agree(oracle, built, name, monkeypatch):
     from lattice_symmetries_b200 import _lib

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--time-limit", type=float, default=None, help="seconds of Lanczos wall time")
     ap.add_argument("--matvecs", type=int, default=3, help="timed products before the Lanczos run")
     ap.add_argument("--no-lanczos", action="store_true")
+    ap.add_argument("--also-mode", default=None, choices=["allgather", "alltoall"],
+                    help="time the products in a second form as well (same basis, same vector)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
 
@@ -62,7 +64,13 @@ def main():
         if world > 1:
             dist.barrier()
 
-    model, desc = bench.make_model(args.workload)
+    if args.workload.startswith("chaint"):   # translations x spin inversion only: the large-footprint probe
+        from lattice_symmetries_b200 import lattices
+        n = int(args.workload[6:])
+        model = lattices.heisenberg_chain(n, parity_sector=None, spin_inversion=1)
+        desc = f"Heisenberg chain N={n}, Sz=0, translations x spin inversion"
+    else:
+        model, desc = bench.make_model(args.workload)
     basis = model.basis()
     op = model.operator(basis)
     say(f"{world} GPU(s): {desc}; {basis.number_candidates} candidates")
@@ -88,6 +96,17 @@ def main():
 
     x = hashed_vector(L.row_begin, L.row_end, 42)
     y = sh.empty_vector()
+    if args.also_mode is not None:
+        other = {"allgather": ALLGATHER, "alltoall": ALLTOALL}[args.also_mode]
+        for k in range(max(1, args.matvecs - 1)):
+            barrier()
+            t0 = time.perf_counter()
+            sh.matvec(x, y, other)
+            sh.sync()
+            barrier()
+            dt = time.perf_counter() - t0
+            say(f"matvec {k} ({args.also_mode}): {dt * 1e3:.1f} ms = {elements / dt:.3e} matrix-elements/s; {mem()}")
+        result["also_mode"] = {"mode": args.also_mode, "ms": dt * 1e3, "x_H_x": float(sh.dot(x, y).item())}
     times = []
     for k in range(args.matvecs):
         barrier()
@@ -96,7 +115,9 @@ def main():
         sh.sync()
         barrier()
         times.append(time.perf_counter() - t0)
-        say(f"matvec {k}: {times[-1] * 1e3:.1f} ms = {elements / times[-1]:.3e} matrix-elements/s; {mem()}")
+        parts = {k2: round(lib.ls_b200_last_kernel_ms(k2.encode()), 1) for k2 in ("orbit", "gather", "combine", "allgather")}
+        say(f"matvec {k}: {times[-1] * 1e3:.1f} ms = {elements / times[-1]:.3e} matrix-elements/s; {mem()}; "
+            f"rank 0 kernels ms (LS_B200_PROFILE; allgather = of the previous product) {parts}")
     if times:
         result["matvec_ms"] = [v * 1e3 for v in times]
         result["matrix_elements_per_s"] = elements / min(times)
