@@ -393,6 +393,15 @@ int ls_b200_dist_build(ls_hs_basis *basis, ls_hs_operator const *balance_for, in
 int ls_b200_dist_matvec(ls_hs_operator const *op, double const *x_local_dev, double *y_local_dev, int mode);
 int ls_b200_dist_matvec_c128(ls_hs_operator const *op, ls_hs_scalar const *x_local_dev, ls_hs_scalar *y_local_dev,
                              int mode); /* all-gather form only */
+/* Moves the row boundaries so that every rank spends the same TIME on a product, using the kernel times measured
+ * during the LAST product on this basis (requires LS_B200_PROFILE=1 in the environment; rows at the high end of the
+ * sorted list cost up to 2.6x more per matrix element than those at the low end because their lookups scatter).
+ * Collective.  Afterwards the local block -- basis->representatives, ls_b200_dist_info -- has changed and the
+ * caller's vectors must be re-split.  Returns 0 when rows moved, 1 when nothing changed, -1 on error. */
+int ls_b200_dist_rebalance(ls_hs_basis *basis);
+/* The same for virtual ranks with explicit costs: costs[r * 1024 + k] = cost of the k-th of 1024 equal pieces of
+ * virtual rank r's rows. */
+int ls_b200_emu_rebalance(ls_hs_basis **bases, int world, double const *costs);
 /* out = {world, rank, dim over all ranks, first row, one past the last row of this rank,
  *        replicated index (0 none, 1 two-level, 2 wide), its search trip count, its prefix bits}; -1 when the basis
  * is not sharded. */

@@ -204,6 +204,8 @@ PROTOTYPES = {
     "ls_b200_dist_build": (C.c_int, [C.POINTER(ls_hs_basis), C.c_void_p, C.c_int]),
     "ls_b200_dist_matvec": (C.c_int, [C.POINTER(ls_hs_operator), C.c_void_p, C.c_void_p, C.c_int]),
     "ls_b200_dist_matvec_c128": (C.c_int, [C.POINTER(ls_hs_operator), C.c_void_p, C.c_void_p, C.c_int]),
+    "ls_b200_dist_rebalance": (C.c_int, [C.POINTER(ls_hs_basis)]),
+    "ls_b200_emu_rebalance": (C.c_int, [C.c_void_p, C.c_int, f64_p]),
     "ls_b200_dist_info": (C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_int64)]),
     "ls_b200_dist_bounds": (C.c_int, [C.POINTER(ls_hs_basis), C.POINTER(C.c_int64), C.c_int]),
     "ls_b200_emu_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),

@@ -55,7 +55,7 @@ struct Runtime {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_matvec_ms = 0, last_build_ms = 0;
   // LS_B200_PROFILE=1: summed device time / launch count of the two matvec kernels in the last matvec
-  double last_orbit_ms = 0, last_gather_ms = 0, last_combine_ms = 0, last_allgather_ms = 0;
+  double last_orbit_ms = 0, last_gather_ms = 0, last_combine_ms = 0, last_allgather_ms = 0, last_count_ms = 0;
   int last_orbit_launches = 0, last_gather_launches = 0;
 
   void ensure();  // throws CudaFailure when no usable device

@@ -722,6 +722,104 @@ static void dist_build(Team const &team, std::vector<ls_hs_basis *> const &bases
   rt.last_build_ms = kernel_ms;
 }
 
+// ---- re-balancing by MEASURED cost ------------------------------------------------------------------------------------
+// Matrix elements do not all cost the same: the rows at the low end of the sorted list (many leading zeros) couple to
+// representatives close to themselves, so their lookups and gathers hit warm cache lines, while the rows at the high
+// end scatter over the whole basis.  Kagome-42 on 8 GPUs, rows split by element count: rank + gather takes 2.1 s on
+// rank 0 and 5.5 s on rank 7.  Given the measured cost density of one product (costs[m][k] = kernel time of the k-th
+// of kCostSegments equal pieces of member m's rows), the row boundaries move so that every rank gets the same TIME.
+// Only the local rows move; the replicated index and the layout of the replicated vector refer to GLOBAL rows and
+// stay valid.  The caller's vectors must be re-split afterwards (ls_b200_dist_info has the new range).
+constexpr int kCostSegments = 1024;
+
+static bool dist_rebalance(Team const &team, std::vector<ls_hs_basis *> const &bases,
+                           std::vector<std::vector<double>> const &costs) {
+  Runtime &rt = runtime();
+  size_t const M = team.size();
+  int const P = team.world;
+  std::vector<IndexData *> local(M);
+  for (size_t m = 0; m < M; ++m) {
+    local[m] = index_of(bases[m]);
+    LSB_CHECK(local[m] != nullptr && local[m]->dist != nullptr, "the basis was not built by the distributed build");
+    LSB_CHECK(costs[m].size() == (size_t)kCostSegments, "dist_rebalance: one cost per segment");
+  }
+  std::vector<int64_t> const bounds = local[0]->dist->bounds;
+  int64_t const dim = local[0]->dist->dim;
+  bool const with_norms = local[0]->d_norms != nullptr || basis_info(bases[0]).has_permutation_symmetries;
+  // everybody learns everybody's cost density
+  std::vector<std::vector<uint64_t>> bits(M, std::vector<uint64_t>((size_t)kCostSegments));
+  for (size_t m = 0; m < M; ++m)
+    for (int k = 0; k < kCostSegments; ++k) memcpy(&bits[m][(size_t)k], &costs[m][(size_t)k], sizeof(double));
+  std::vector<uint64_t> const table = team.gather_host(bits, (size_t)kCostSegments);
+  std::vector<int64_t> edges{0};
+  std::vector<double> piece_costs;
+  for (int r = 0; r < P; ++r) {
+    int64_t const n = bounds[(size_t)r + 1] - bounds[(size_t)r];
+    for (int k = 0; k < kCostSegments; ++k) {
+      int64_t const e = bounds[(size_t)r] + (int64_t)(((__int128)n * (k + 1)) / kCostSegments);
+      double c;
+      memcpy(&c, &table[(size_t)r * kCostSegments + (size_t)k], sizeof c);
+      if (e > edges.back()) {
+        edges.push_back(e);
+        piece_costs.push_back(c);
+      } else if (!piece_costs.empty()) {
+        piece_costs.back() += c;
+      }
+    }
+  }
+  double total_cost = 0;
+  for (double c : piece_costs) total_cost += c;
+  if (edges.back() != dim || piece_costs.empty() || !(total_cost > 0)) return false;  // nothing measured: nothing moves
+  std::vector<int64_t> const fresh = dist_balanced_bounds(edges, piece_costs, P, true);
+  if (fresh == bounds) return false;
+  // detach the local arrays from the bases (the index and the host view go, the arrays travel)
+  std::vector<void *> reps(M, nullptr), norms(M, nullptr);
+  std::vector<DistShard *> shards(M, nullptr);
+  for (size_t m = 0; m < M; ++m) {
+    shards[m] = local[m]->dist;
+    local[m]->dist = nullptr;
+    reps[m] = local[m]->d_reps;
+    norms[m] = local[m]->d_norms;
+    local[m]->d_norms = nullptr;
+    local[m]->owns_d_reps = false;  // (a managed array was to be released by the host view's freer: not called either)
+    local[m]->d_reps = nullptr;
+    delete local[m];
+    bases[m]->kernels->state_index_data = nullptr;
+    bases[m]->kernels->state_index_kernel = nullptr;
+    bases[m]->representatives.elts = nullptr;
+    bases[m]->representatives.num_elts = 0;
+    bases[m]->representatives.freer = nullptr;
+  }
+  std::vector<Piece> held;
+  for (int r = 0; r < P; ++r) held.push_back({bounds[(size_t)r], bounds[(size_t)r + 1] - bounds[(size_t)r], r});
+  redistribute(team, held, fresh, reps, allocate_representatives);
+  if (with_norms) redistribute(team, held, fresh, norms, allocate_plain);
+  release_redistribute_scratch(size_t(1) << 30);
+  std::vector<std::vector<uint64_t>> firsts(M, std::vector<uint64_t>(1, ~uint64_t(0)));
+  for (size_t m = 0; m < M; ++m) {
+    int const r = team.members[m];
+    int64_t const n = fresh[(size_t)r + 1] - fresh[(size_t)r];
+    if (n > 0) CUDA_CHECK(cudaMemcpyAsync(firsts[m].data(), reps[m], 8, cudaMemcpyDeviceToHost, rt.stream));
+    CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    install_representatives(bases[m], static_cast<uint64_t *>(reps[m]), with_norms ? static_cast<double *>(norms[m]) : nullptr,
+                            (uint64_t)n, 22);
+    IndexData *ix = index_of(bases[m]);
+    ix->identity = false;
+    ix->dist = shards[m];
+    shards[m]->bounds = fresh;
+  }
+  std::vector<uint64_t> const splitters = team.gather_host(firsts, 1);
+  for (size_t m = 0; m < M; ++m) {
+    DistShard &sh = *shards[m];
+    sh.splitters = splitters;
+    for (int r = P - 2; r >= 0; --r)
+      if (fresh[(size_t)r + 1] == fresh[(size_t)r]) sh.splitters[(size_t)r] = sh.splitters[(size_t)r + 1];
+    CUDA_CHECK(cudaMemcpy(sh.d_splitters, sh.splitters.data(), sizeof(uint64_t) * (size_t)P, cudaMemcpyHostToDevice));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+  return true;
+}
+
 // ---- distributed products ---------------------------------------------------------------------------------------------
 enum : int { kProductAuto = 0, kProductAllGather = 1, kProductAllToAll = 2 };
 
@@ -976,6 +1074,32 @@ int ls_b200_dist_matvec_c128(ls_hs_operator const *op, ls_hs_scalar const *x_loc
   guarded(__func__, [&] {
     dist_matvec_local(op, reinterpret_cast<double const *>(x_local_dev), reinterpret_cast<double *>(y_local_dev), mode, true);
     status = 0;
+  });
+  return status;
+}
+
+int ls_b200_dist_rebalance(ls_hs_basis *basis) {
+  int status = -1;
+  guarded(__func__, [&] {
+    IndexData *ix = index_of(basis);
+    LSB_CHECK(ix != nullptr && ix->dist != nullptr, "ls_b200_dist_rebalance: not a distributed basis");
+    std::vector<std::vector<double>> costs(1, std::vector<double>((size_t)kCostSegments, 0.0));
+    // a rank whose last product recorded no costs (no rows, or LS_B200_PROFILE unset) reports zeros: harmless when
+    // every rank does so (nothing moves), but all ranks must make this call together either way
+    (void)matvec_last_row_costs(ix->number_states, kCostSegments, costs[0].data());
+    status = dist_rebalance(real_team(), {basis}, costs) ? 0 : 1;
+  });
+  return status;
+}
+
+int ls_b200_emu_rebalance(ls_hs_basis **bases, int world, double const *costs) {
+  int status = -1;
+  guarded(__func__, [&] {
+    LSB_CHECK(world >= 1 && bases != nullptr && costs != nullptr, "ls_b200_emu_rebalance: invalid arguments");
+    std::vector<ls_hs_basis *> b(bases, bases + world);
+    std::vector<std::vector<double>> c((size_t)world);
+    for (int r = 0; r < world; ++r) c[(size_t)r].assign(costs + (size_t)r * kCostSegments, costs + (size_t)(r + 1) * kCostSegments);
+    status = dist_rebalance(emulated_team(world), b, c) ? 0 : 1;
   });
   return status;
 }

@@ -714,7 +714,13 @@ struct MatvecScratch {
   // per-kernel device time of the last matvec (LS_B200_PROFILE=1): events around every orbit / gather launch
   std::vector<cudaEvent_t> events;
   size_t events_used = 0;
-  std::vector<std::pair<size_t, int>> spans;  // (index of start event, kind: 0 orbit, 1 gather)
+  std::vector<std::pair<size_t, int>> spans;  // (index of start event, kind: 0 orbit, 1 gather, 2 row sum, 3 row count)
+  // LS_B200_PROFILE, plain chunk loop: which chunk every span belongs to and the rows of every chunk -- the measured
+  // cost density over the rows that the distributed driver re-balances the ranks with (ls_b200_dist_rebalance)
+  std::vector<int> span_chunk;
+  std::vector<std::pair<int64_t, int64_t>> chunk_rows;  // (first row relative to the call, rows)
+  std::vector<double> chunk_ms;
+  int64_t cost_rows = 0;  // rows of the call the costs belong to
 };
 static MatvecScratch &mv_scratch() {
   static MatvecScratch s;
@@ -847,6 +853,9 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
   static bool const profile = getenv("LS_B200_PROFILE") != nullptr;
   sc.events_used = 0;
   sc.spans.clear();
+  sc.span_chunk.clear();
+  sc.chunk_rows.clear();
+  sc.cost_rows = row_end - row_begin;
   CUDA_CHECK(cudaEventRecord(rt.ev0, rt.stream));
 
   MatvecArgs a{};
@@ -1211,6 +1220,7 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
   for (int64_t begin = row_begin; begin < row_end; ++chunk_index) {
     int64_t const nrows = sorted ? plan->begin[(size_t)chunk_index + 1] - begin : std::min(chunk_rows, row_end - begin);
     ChunkSlot &slot = sc.slot[pipelined ? (chunk_index & 1) : 0];
+    if (profile) sc.chunk_rows.emplace_back(begin - row_begin, nrows);
     a.chunk_begin = begin;
     a.chunk_rows = (int)nrows;
     a.counts = slot.counts.ptr;
@@ -1222,12 +1232,19 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
     a.vals_stride = capacity + 32;
     if (queued) {
       if (pipelined && chunk_index >= 2) CUDA_CHECK(cudaStreamWaitEvent(stream_a, slot.released, 0));
+      if (profile) {
+        sc.spans.emplace_back(sc.events_used, 3);
+        sc.span_chunk.push_back((int)sc.chunk_rows.size() - 1);
+        CUDA_CHECK(cudaEventRecord(next_event(sc), stream_a));
+      }
       row_count_kernel<<<ceil_div((size_t)nrows + 1, 256), 256, count_smem, stream_a>>>(a);
       size_t tmp = sc.scan_tmp_bytes;
       cub::DeviceScan::ExclusiveSum(sc.scan_tmp.ptr, tmp, a.counts, a.offsets, (int)(nrows + 1), stream_a);
       count_launch(2);
       if (profile) {
+        CUDA_CHECK(cudaEventRecord(next_event(sc), stream_a));
         sc.spans.emplace_back(sc.events_used, 0);
+        sc.span_chunk.push_back((int)sc.chunk_rows.size() - 1);
         CUDA_CHECK(cudaEventRecord(next_event(sc), stream_a));
       }
       if (a.mode == kModeGroup) {
@@ -1248,6 +1265,7 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
       CUDA_CHECK(cudaStreamWaitEvent(stream_b, target->xs_ready, 0));  // the replicated vector is read from here on
     if (profile) {
       sc.spans.emplace_back(sc.events_used, 1);
+      sc.span_chunk.push_back((int)sc.chunk_rows.size() - 1);
       CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
     }
     if (fused && queued) {
@@ -1277,6 +1295,7 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
       if (profile) {
         CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
         sc.spans.emplace_back(sc.events_used, 2);
+        sc.span_chunk.push_back((int)sc.chunk_rows.size() - 1);
         CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));
       }
       if (a.q_tsign != nullptr)
@@ -1305,18 +1324,46 @@ bool matvec_finish() {
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
   float ms = 0;
   if (cudaEventElapsedTime(&ms, rt.ev0, rt.ev1) == cudaSuccess) rt.last_matvec_ms = ms;
-  rt.last_orbit_ms = rt.last_gather_ms = rt.last_combine_ms = 0;
+  rt.last_orbit_ms = rt.last_gather_ms = rt.last_combine_ms = rt.last_count_ms = 0;
   rt.last_orbit_launches = rt.last_gather_launches = 0;
+  bool const by_chunk = !sc.spans.empty() && sc.span_chunk.size() == sc.spans.size();
+  sc.chunk_ms.assign(by_chunk ? sc.chunk_rows.size() : 0, 0.0);
+  size_t span_no = 0;
   for (auto const &span : sc.spans) {
     float t = 0;
+    size_t const this_span = span_no++;
     if (cudaEventElapsedTime(&t, sc.events[span.first], sc.events[span.first + 1]) != cudaSuccess) continue;
+    if (by_chunk && sc.span_chunk[this_span] >= 0) sc.chunk_ms[(size_t)sc.span_chunk[this_span]] += t;
     if (span.second == 0) { rt.last_orbit_ms += t; ++rt.last_orbit_launches; }
     else if (span.second == 2) { rt.last_combine_ms += t; }
+    else if (span.second == 3) { rt.last_count_ms += t; }
     else { rt.last_gather_ms += t; ++rt.last_gather_launches; }
   }
   if (flag != 0) {
     CUDA_CHECK(cudaMemsetAsync(sc.d_error, 0, sizeof(int), rt.stream));
     return false;
+  }
+  return true;
+}
+
+// Measured cost (ms of kernel time, LS_B200_PROFILE) of the rows of the last product, resampled to `segments` equal
+// pieces of its row range; false when the last product recorded none.
+bool matvec_last_row_costs(int64_t number_rows, int segments, double *out) {
+  MatvecScratch &sc = mv_scratch();
+  for (int k = 0; k < segments; ++k) out[k] = 0.0;
+  if (sc.chunk_ms.empty() || sc.chunk_ms.size() != sc.chunk_rows.size() || sc.cost_rows != number_rows || number_rows <= 0)
+    return false;
+  for (size_t c = 0; c < sc.chunk_ms.size(); ++c) {
+    int64_t const b = sc.chunk_rows[c].first, n = sc.chunk_rows[c].second;
+    if (n <= 0) continue;
+    // spread the chunk's time over the segments it overlaps, in proportion to the rows
+    int64_t const k0 = (int64_t)(((__int128)b * segments) / number_rows);
+    int64_t const k1 = (int64_t)(((__int128)(b + n - 1) * segments) / number_rows);
+    for (int64_t k = k0; k <= k1 && k < segments; ++k) {
+      int64_t const lo = std::max<int64_t>(b, (int64_t)(((__int128)k * number_rows + segments - 1) / segments));
+      int64_t const hi = std::min<int64_t>(b + n, (int64_t)(((__int128)(k + 1) * number_rows + segments - 1) / segments));
+      if (hi > lo) out[k] += sc.chunk_ms[c] * (double)(hi - lo) / (double)n;
+    }
   }
   return true;
 }

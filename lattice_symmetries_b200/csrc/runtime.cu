@@ -165,6 +165,7 @@ double ls_b200_last_kernel_ms(char const *name) {
   if (name != nullptr && strcmp(name, "orbit") == 0) return rt.last_orbit_ms;
   if (name != nullptr && strcmp(name, "gather") == 0) return rt.last_gather_ms;
   if (name != nullptr && strcmp(name, "combine") == 0) return rt.last_combine_ms;
+  if (name != nullptr && strcmp(name, "count") == 0) return rt.last_count_ms;  // row_count + scan
   if (name != nullptr && strcmp(name, "allgather") == 0) return rt.last_allgather_ms;  // of the product BEFORE the last one
   if (name != nullptr && strcmp(name, "orbit_launches") == 0) return (double)rt.last_orbit_launches;
   if (name != nullptr && strcmp(name, "gather_launches") == 0) return (double)rt.last_gather_launches;

@@ -147,6 +147,7 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
                    bool complex_vectors, int number_vectors = 1, int64_t x_stride = 0, int64_t y_stride = 0,
                    double *host_y = nullptr, int phase = 0, MvTarget const *target = nullptr);
 bool matvec_finish();
+bool matvec_last_row_costs(int64_t number_rows, int segments, double *out);
 extern char const *kInvalidIndexMessage;
 void launch_prescale(int64_t n, bool complex_vectors, double const *norms, double const *x, double *xs,
                      cudaStream_t stream = nullptr);

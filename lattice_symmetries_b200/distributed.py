@@ -30,7 +30,7 @@ import numpy as np
 
 __all__ = [
     "shard_bounds", "row_bounds", "plan_blocks", "plan_redistribution", "even_bounds", "balanced_bounds",
-    "init_process", "init_communicator", "Layout", "build_distributed", "DistributedOperator", "EmulatedRanks",
+    "init_process", "init_communicator", "Layout", "build_distributed", "rebalance_distributed", "DistributedOperator", "EmulatedRanks",
     "hashed_vector", "hashed_values", "layout_of", "ALLGATHER", "ALLTOALL", "AUTO", "NO_GLOBAL_INDEX", "WIDE_INDEX", "NO_BALANCE",
 ]
 
@@ -209,6 +209,19 @@ def build_distributed(basis, balance_for=None, flags: int = 0) -> Layout:
     return layout_of(basis)
 
 
+def rebalance_distributed(basis) -> Layout:
+    """``ls_b200_dist_rebalance``: move the row boundaries so that every rank spends the same time on a product,
+    from the kernel times measured during the last product (``LS_B200_PROFILE=1`` must be set before the first
+    product).  Collective; vectors split by the old layout must be re-split.  Returns the new layout."""
+    from . import _lib
+    status = _lib.lib.ls_b200_dist_rebalance(C.byref(basis._payload))
+    _lib.check_error()
+    if status < 0:
+        raise RuntimeError("ls_b200_dist_rebalance failed")
+    basis._keep.pop("views", None)
+    return layout_of(basis)
+
+
 def _as_int64(v: int) -> int:
     v &= (1 << 64) - 1
     return v - (1 << 64) if v >= (1 << 63) else v
@@ -319,6 +332,21 @@ class EmulatedRanks:
     @property
     def dim(self) -> int:
         return self.layouts[0].dim
+
+    def rebalance(self, costs: np.ndarray) -> bool:
+        """``ls_b200_emu_rebalance``: ``costs[r, k]`` = cost of the k-th of 1024 equal pieces of virtual rank r's rows."""
+        from . import _lib
+        costs = np.ascontiguousarray(costs, dtype=np.float64)
+        assert costs.shape == (self.world, 1024)
+        bases = (C.c_void_p * self.world)(*[C.addressof(b._payload) for b in self.bases])
+        status = _lib.lib.ls_b200_emu_rebalance(bases, self.world, costs.ctypes.data_as(_lib.f64_p))
+        _lib.check_error()
+        if status < 0:
+            raise RuntimeError("ls_b200_emu_rebalance failed")
+        for b in self.bases:
+            b._keep.pop("views", None)
+        self.layouts = [layout_of(b) for b in self.bases]
+        return status == 0
 
     def states(self) -> np.ndarray:
         """The concatenation of the local blocks (== the sorted representatives of the whole basis)."""

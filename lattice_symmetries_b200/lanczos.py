@@ -101,14 +101,17 @@ def _start_vector(sh, seed: int, dtype=None):
 
 def lanczos_ground_state(operator, max_iters: int = 300, tol: float = 1e-12, seed: int = 42,
                          compute_eigenvector: bool = False, check_every: int = 10,
-                         time_limit_s: Optional[float] = None, progress=None) -> LanczosResult:
+                         time_limit_s: Optional[float] = None, progress=None,
+                         energy_tol: Optional[float] = None) -> LanczosResult:
     """Lowest eigenvalue (and optionally eigenvector) of a real symmetric ``Operator``.
 
     ``tol`` bounds the Ritz residual |beta_k s_k| relative to |E0|.  No re-orthogonalisation: ghost copies do not
     disturb the extremal eigenvalue.  The eigenvector, when requested, is accumulated in a second pass that
     replays the recurrence (two-pass Lanczos: 3 vectors of HBM instead of one per iteration).
     ``time_limit_s``: stop at the next check once this much wall time has passed (the result says whether it
-    had converged).  ``progress(k, energy, residual)`` is called at every check."""
+    had converged).  ``progress(k, energy, residual)`` is called at every check.  ``energy_tol``: also stop when the
+    Ritz value moved by less than ``energy_tol * |E0|`` over each of the last two checks (the eigenVALUE converges
+    with the square of the residual, long before the residual itself is small)."""
     import time
     import torch
     sh = _wrap(operator)
@@ -125,6 +128,7 @@ def lanczos_ground_state(operator, max_iters: int = 300, tol: float = 1e-12, see
         weights = None if accumulate_with is None else torch.as_tensor(np.asarray(accumulate_with), device=v.device)
         energy, resid, converged, done = float("nan"), float("inf"), False, 0
         beta = None
+        history = []
         for k in range(n_steps):
             if out is not None:
                 out.addcmul_(v, weights[k:k + 1])
@@ -143,7 +147,12 @@ def lanczos_ground_state(operator, max_iters: int = 300, tol: float = 1e-12, see
                 resid = abs(host[1, -1] * s[-1])
                 if progress is not None:
                     progress(done, energy, resid)
+                history.append(energy)
                 if resid <= tol * max(1.0, abs(energy)) or host[1, -1] < 1e-14:
+                    converged = True
+                    break
+                if energy_tol is not None and len(history) >= 3 and all(
+                        abs(history[-i] - history[-i - 1]) <= energy_tol * max(1.0, abs(energy)) for i in (1, 2)):
                     converged = True
                     break
                 if time_limit_s is not None and time.perf_counter() - t_start > time_limit_s:

@@ -32,6 +32,7 @@ def main() -> int:
     from oracle import ls_oracle as oracle
     import helpers as H
 
+    os.environ["LS_B200_PROFILE"] = "1"   # kernel times per chunk of rows: what ls_b200_dist_rebalance balances with
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     init_process(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -87,6 +88,23 @@ def main() -> int:
             e_ref, _ = H.oracle_ground_state_energy(oracle, p)
             check(f"{model.name}: Lanczos E0 {res.energy:.12f} vs oracle eigsh {e_ref:.12f}",
                   abs(res.energy - e_ref) <= 1e-9 * abs(e_ref))
+        # re-balance by the kernel times of the last product (collective), then everything again on the new blocks
+        from lattice_symmetries_b200.distributed import rebalance_distributed
+        dop.matvec(xl, yl, ALLGATHER if lay.global_index else ALLTOALL)
+        dop.sync()
+        lay2 = rebalance_distributed(basis)
+        lo, hi = lay2.row_begin, lay2.row_end
+        check(f"{model.name}: block after re-balancing", np.array_equal(np.asarray(basis.states), reps[lo:hi]))
+        dop = DistributedOperator(op)
+        xl = torch.from_numpy(x[lo:hi].copy()).cuda()
+        yl = dop.empty_vector()
+        for mode, label in ((ALLGATHER, "all-gather"), (ALLTOALL, "all-to-all")):
+            if mode == ALLGATHER and lay2.global_index == 0:
+                continue
+            dop.matvec(xl, yl, mode)
+            dop.sync()
+            err = float(np.linalg.norm(yl.cpu().numpy() - want[lo:hi])) / scale
+            check(f"{model.name}: {label} product after re-balancing rel err {err:.2e}", err <= 1e-12)
         del dop, op, basis
 
     flag = torch.tensor([len(failures)], dtype=torch.int64, device="cuda")

