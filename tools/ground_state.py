@@ -156,7 +156,7 @@ def main():
         result["rebalanced_bounds"] = L.bounds
         x = hashed_vector(L.row_begin, L.row_end, 42)
         y = sh.empty_vector()
-        for k in range(2):
+        for k in range(1):
             barrier()
             t0 = time.perf_counter()
             sh.matvec(x, y, mode)
