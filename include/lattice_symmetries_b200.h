@@ -360,6 +360,15 @@ int ls_b200_copy_to_host(void *dst_host, void const *src_dev, size_t bytes);
 void *ls_b200_host_malloc(size_t bytes);
 void ls_b200_host_free(void *p);
 
+/* Extension (rows of the symmetry-PROJECTED operator, batched; semantics of chapel/src/BatchedOperator.chpl:207-253):
+ * for every alphas[i], the entries offsets[i] .. offsets[i+1] hold the representative of each image, and the matrix
+ * element chi c n(beta) / n(alpha_i) (0 for images of vanishing norm).  Host pointers; reps / coeffs / indices need
+ * room for count * (number of off-diagonal terms) entries, offsets for count + 1.  indices (may be NULL): position of
+ * each representative in the built basis, -1 when absent.  Returns the number of entries, -1 on error. */
+int64_t ls_b200_operator_apply_off_diag_projected(ls_hs_operator const *op, int64_t count, uint64_t const *alphas,
+                                                  uint64_t *reps, ls_hs_scalar *coeffs, int64_t *offsets,
+                                                  int64_t *indices);
+
 /* Drops the device-side tables cached for an operator (term tables, phased-product buffers); call before the
  * ls_hs_operator struct is freed.  Harmless for operators the library has never seen. */
 void ls_b200_operator_release(ls_hs_operator const *op);

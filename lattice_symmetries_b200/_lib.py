@@ -194,6 +194,8 @@ PROTOTYPES = {
     "ls_b200_host_malloc": (C.c_void_p, [C.c_size_t]),
     "ls_b200_host_free": (None, [C.c_void_p]),
     "ls_b200_operator_release": (None, [C.c_void_p]),
+    "ls_b200_operator_apply_off_diag_projected": (
+        C.c_int64, [C.POINTER(ls_hs_operator), C.c_int64, u64_p, u64_p, C.c_void_p, i64_p, i64_p]),
     # several GPUs of one node (dist.cu)
     "ls_b200_comm_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
     "ls_b200_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),

@@ -397,6 +397,16 @@ IndexData *create_index_from_device(uint64_t *d_reps, int64_t count, int number_
   return ix;
 }
 
+// out[i] = position of needles[i] in the index (device pointers), -1 when absent; on the library stream
+void launch_state_index(IndexData const &ix, int64_t n, uint64_t const *d_needles, int64_t *d_out) {
+  if (n <= 0) return;
+  Runtime &rt = runtime();
+  unsigned const blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)rt.sm_count * 16);
+  state_index_kernel<<<blocks, 256, 0, rt.stream>>>(ix.view(), n, d_needles, d_out);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+}
+
 struct IndexScratch {
   DeviceBuffer<uint64_t> needles;
   DeviceBuffer<int64_t> out;

@@ -1903,7 +1903,10 @@ int ls_b200_matvec_sync(void) {
 
 void ls_b200_operator_release(ls_hs_operator const *op) {
   if (op == nullptr) return;
-  std::lock_guard<std::mutex> lock(runtime().mutex);
+  // Called from finalizers (Python's garbage collector): never wait for a library call in flight on another thread --
+  // that call may itself be waiting for the interpreter (error handler).  Skipping only leaks a few small tables.
+  std::unique_lock<std::mutex> lock(runtime().mutex, std::try_to_lock);
+  if (!lock.owns_lock()) return;
   MatvecScratch &sc = mv_scratch();
   if (sc.phase_op == op) release_phase_slots();
   operator_cache().erase(op);

@@ -149,6 +149,110 @@ static void apply_diag(ls_hs_operator const *op, int64_t n, uint64_t const *alph
   CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
+// ---- projected rows of H (semantics of chapel/src/BatchedOperator.chpl:207-253, 264-282) ----------
+// For every alpha_i: H|alpha_i> = sum_k c_k |beta_k>; every beta is canonicalised -- representative, character, norm
+// (state_info) -- and the coefficient becomes chi_k c_k n(beta_k) / n(alpha_i): the matrix element
+// <rep_k| H |alpha_i> of the symmetry-projected operator.  Zero-norm images keep their slot with coefficient 0, so
+// the offsets are those of the un-projected call.
+__global__ void __launch_bounds__(256)
+project_rows_kernel(int64_t n, int64_t const *__restrict__ offsets, double2 const *__restrict__ chars,
+                    double const *__restrict__ norms_beta, double const *__restrict__ norms_alpha,
+                    double2 *__restrict__ coeffs) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double const na = norms_alpha[i];
+    for (int64_t k = offsets[i]; k < offsets[i + 1]; ++k) {
+      double const nb = norms_beta[k];
+      double2 const c = coeffs[k];
+      // same order as the oracle / the reference: (c n_beta / n_alpha) first, then times the character
+      double const tr = c.x * nb / na, ti = c.y * nb / na;
+      double2 const ch = chars[k];
+      coeffs[k] = nb > 0.0 ? make_double2(ch.x * tr - ch.y * ti, ch.x * ti + ch.y * tr) : make_double2(0.0, 0.0);
+    }
+  }
+}
+// spin inversion without permutations (BatchedOperator.chpl:187-199): rep = min(beta, ~beta), coefficient * character
+__global__ void __launch_bounds__(256)
+project_inversion_kernel(int64_t total, uint64_t mask, double character, uint64_t *__restrict__ betas,
+                         double2 *__restrict__ coeffs) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t const b = betas[k], f = b ^ mask;
+    if (f < b) {
+      betas[k] = f;
+      coeffs[k] = make_double2(coeffs[k].x * character, coeffs[k].y * character);
+    }
+  }
+}
+
+void launch_state_info(GroupData const &g, int64_t n, uint64_t const *d_alphas, uint64_t *d_betas, double2 *d_chars,
+                       double *d_norms);
+void launch_state_index(IndexData const &ix, int64_t n, uint64_t const *d_needles, int64_t *d_out);
+
+static int64_t apply_off_diag_projected(ls_hs_operator const *op, int64_t n, uint64_t const *alphas, uint64_t *reps,
+                                        ls_hs_scalar *coeffs, int64_t *offsets, int64_t *indices) {
+  Runtime &rt = runtime();
+  ApplyScratch &sc = apply_scratch();
+  OperatorDev &od = operator_dev(op);
+  cudaStream_t s = rt.stream;
+  if (od.off.number_terms == 0 || n == 0) {
+    for (int64_t i = 0; i <= n; ++i) offsets[i] = 0;
+    return 0;
+  }
+  BasisInfo const info = basis_info(op->basis);
+  uint64_t *d_a = sc.alphas.reserve((size_t)n);
+  int64_t *d_counts = sc.counts.reserve((size_t)n + 1);
+  int64_t *d_offsets = sc.offsets.reserve((size_t)n + 1);
+  CUDA_CHECK(cudaMemcpyAsync(d_a, alphas, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+  off_diag_count_kernel<<<grid_for(n + 1), 256, 0, s>>>(od.off.view(), n, d_a, d_counts);
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, d_offsets, n + 1, s);
+  unsigned char *tmp = sc.scan_tmp.reserve(tmp_bytes);
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_counts, d_offsets, n + 1, s);
+  count_launch(2);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(offsets, d_offsets, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  int64_t const total = offsets[n];
+  if (total == 0) return 0;
+  uint64_t *d_b = sc.betas.reserve((size_t)total);
+  double2 *d_c = sc.coeffs.reserve((size_t)total);
+  off_diag_fill_kernel<<<grid_for(n), 256, 0, s>>>(od.off.view(), n, d_a, nullptr, d_offsets, d_b, d_c);
+  count_launch();
+  CUDA_CHECK(cudaGetLastError());
+  static DeviceBuffer<uint64_t> rep_buffer, alpha_reps;
+  static DeviceBuffer<double2> char_buffer, alpha_chars;
+  static DeviceBuffer<double> norm_beta, norm_alpha;
+  static DeviceBuffer<int64_t> index_buffer;
+  uint64_t *d_out = d_b;
+  if (info.has_permutation_symmetries) {
+    GroupData const &g = *info.group;
+    d_out = rep_buffer.reserve((size_t)total);
+    double2 *d_ch = char_buffer.reserve((size_t)total);
+    double *d_nb = norm_beta.reserve((size_t)total);
+    double *d_na = norm_alpha.reserve((size_t)n);
+    launch_state_info(g, total, d_b, d_out, d_ch, d_nb);
+    // norms of the alphas themselves (any states are allowed, not only this basis' representatives)
+    launch_state_info(g, n, d_a, alpha_reps.reserve((size_t)n), alpha_chars.reserve((size_t)n), d_na);
+    project_rows_kernel<<<grid_for(n), 256, 0, s>>>(n, d_offsets, d_ch, d_nb, d_na, d_c);
+    count_launch();
+  } else if (info.has_spin_inversion) {
+    uint64_t const mask = op->basis->number_sites >= 64 ? ~uint64_t(0) : ((uint64_t(1) << op->basis->number_sites) - 1);
+    project_inversion_kernel<<<grid_for(total), 256, 0, s>>>(total, mask, (double)op->basis->spin_inversion, d_b, d_c);
+    count_launch();
+  }
+  CUDA_CHECK(cudaGetLastError());
+  if (indices != nullptr) {
+    IndexData const *ix = index_of(op->basis);
+    LSB_CHECK(ix != nullptr, "indices were asked for, but the basis is not built");
+    int64_t *d_j = index_buffer.reserve((size_t)total);
+    launch_state_index(*ix, total, d_out, d_j);
+    CUDA_CHECK(cudaMemcpyAsync(indices, d_j, sizeof(int64_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(reps, d_out, sizeof(uint64_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(coeffs, d_c, sizeof(double2) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  return total;
+}
+
 static void free_host(void *p) { free(p); }
 
 template <class T>
@@ -211,6 +315,18 @@ void ls_chpl_operator_apply_off_diag(ls_hs_operator *op, int64_t count, uint64_t
     apply_off_diag(op, count, alphas, static_cast<uint64_t *>(betas->elts),
                    static_cast<ls_hs_scalar *>(coeffs->elts), static_cast<ptrdiff_t *>(offsets->elts), nullptr);
   });
+}
+
+// Extension: the rows of the PROJECTED operator, batched.  Host pointers; reps / coeffs need room for
+// count * (number of off-diagonal terms) entries, offsets for count + 1; indices (optional, same length as reps)
+// receives the position of every representative in the built basis, -1 when absent.  Returns the number of entries, -1
+// on error.
+int64_t ls_b200_operator_apply_off_diag_projected(ls_hs_operator const *op, int64_t count, uint64_t const *alphas,
+                                                  uint64_t *reps, ls_hs_scalar *coeffs, int64_t *offsets,
+                                                  int64_t *indices) {
+  int64_t total = -1;
+  guarded(__func__, [&] { total = apply_off_diag_projected(op, count, alphas, reps, coeffs, offsets, indices); });
+  return total;
 }
 
 }  // extern "C"

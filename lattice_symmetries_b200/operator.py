@@ -9,6 +9,7 @@ does the same with :mod:`expr` and calls the C ABI for everything else.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import List, Tuple
 
 import numpy as np
@@ -55,6 +56,13 @@ def _external_to_numpy(arr: _lib.chpl_external_array, dtype) -> np.ndarray:
     return out
 
 
+def _release_operator(address: int) -> None:
+    try:
+        lib.ls_b200_operator_release(C.c_void_p(address))
+    except Exception:  # interpreter shutdown
+        pass
+
+
 class Operator(_Base):
     def __init__(self, basis: Basis, expression: Expr):
         if not isinstance(basis, Basis):
@@ -77,6 +85,9 @@ class Operator(_Base):
         if diag is not None:
             op.diag_terms = diag
         self._payload = op
+        # the library caches device copies of the term tables keyed by the struct's address: drop them with the object
+        # (a later operator may be allocated at the same address)
+        weakref.finalize(self, _release_operator, C.addressof(op))
 
     @property
     def basis(self) -> Basis:
@@ -166,6 +177,30 @@ class Operator(_Base):
         _lib.check_error()
         total = int(offsets[-1])
         return betas[:total], coeffs[:total], offsets
+
+    def apply_off_diag_projected(self, states, with_indices: bool = False):
+        """Rows of the symmetry-projected operator, batched on the device (extension; the reference
+        computes them inside its matvec only, chapel/src/BatchedOperator.chpl:207-253): for every ``states[i]``
+        the representatives of its images and the matrix elements  chi c n(beta) / n(alpha_i).
+        Returns (representatives, coefficients, offsets[, indices])."""
+        states = np.ascontiguousarray(states, dtype=np.uint64)
+        count = states.shape[0]
+        cap = max(1, count * max(self.number_off_diag_terms, 1))
+        reps = np.zeros(cap, dtype=np.uint64)
+        coeffs = np.zeros(cap, dtype=np.complex128)
+        offsets = np.zeros(count + 1, dtype=np.int64)
+        indices = np.zeros(cap, dtype=np.int64) if with_indices else None
+        if with_indices:
+            self._check_basis_is_built("apply_off_diag_projected")
+        total = lib.ls_b200_operator_apply_off_diag_projected(
+            C.byref(self._payload), count, states.ctypes.data_as(_lib.u64_p), reps.ctypes.data_as(_lib.u64_p),
+            coeffs.ctypes.data, offsets.ctypes.data_as(_lib.i64_p),
+            indices.ctypes.data_as(_lib.i64_p) if with_indices else None)
+        _lib.check_error()
+        if total < 0:
+            raise RuntimeError("ls_b200_operator_apply_off_diag_projected failed")
+        out = (reps[:total], coeffs[:total], offsets)
+        return out + (indices[:total],) if with_indices else out
 
     def apply_diag(self, states, xs=None) -> np.ndarray:
         """Batched ls_internal_operator_apply_diag_x1 (kernels/reference.c:67-95)."""

@@ -83,6 +83,45 @@ def test_struct_layouts_match_reference_header():
     assert C.sizeof(_lib.ls_chpl_kernels) == 32
 
 
+REFERENCE_KERNELS = Path("/root/reference/kernels")
+HARNESS = ROOT / "tests" / "_build" / "abi_harness"
+
+
+def build_harness() -> Path:
+    """tests/abi_harness.c against the REFERENCE's own header (not ours), linked with the drop-in library.  The binary
+    stays under tests/_build/ (git-ignored, travels to the GPU box, where /root/reference does not exist)."""
+    import subprocess
+    HARNESS.parent.mkdir(exist_ok=True)
+    subprocess.run(
+        ["gcc", "-std=c11", "-O1", "-Wall", "-Werror", f"-I{REFERENCE_KERNELS}", "-DLS_NO_STD_COMPLEX",
+         str(ROOT / "tests" / "abi_harness.c"), "-o", str(HARNESS), f"-L{ROOT / 'lattice_symmetries_b200'}",
+         "-llattice_symmetries_b200", "-Wl,-rpath,$ORIGIN/../../lattice_symmetries_b200"], check=True)
+    return HARNESS
+
+
+@pytest.mark.skipif(not REFERENCE_KERNELS.is_dir(), reason="the reference tree is not mounted")
+def test_reference_header_layout_matches_ours():
+    """Every struct of kernels/lattice_symmetries_types.h as the reference's compiler lays it out (sizeof / offsetof
+    printed by a C harness that includes THAT header) against the binding's structs, which mirror
+    include/lattice_symmetries_b200.h field for field (and csrc/abi_layout.cu pins the same numbers in C++)."""
+    import json
+    import subprocess
+    from lattice_symmetries_b200 import _lib
+    harness = build_harness()
+    layout = json.loads(subprocess.run([str(harness), "layout"], check=True, capture_output=True, text=True).stdout)
+    checked = 0
+    for key, value in layout.items():
+        if key.startswith("sizeof "):
+            assert C.sizeof(getattr(_lib, key.split()[1])) == value, key
+            checked += 1
+        elif "." in key:
+            struct, field = key.split(".")
+            assert getattr(getattr(_lib, struct), field).offset == value, key
+            checked += 1
+    assert checked >= 50
+    assert (layout["LS_HS_SPIN"], layout["LS_HS_SPINFUL_FERMION"], layout["LS_HS_SPINLESS_FERMION"]) == (0, 1, 2)
+
+
 def test_vtable_registration_needs_no_device():
     """ls_chpl_init_kernels (LatticeSymmetries.chpl:18-33) fills the four vtable slots."""
     from lattice_symmetries_b200 import _lib

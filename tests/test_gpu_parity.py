@@ -629,6 +629,47 @@ def test_lanczos_matches_eigsh(oracle, built):
 
 
 # ---- golden fixtures (tests/golden, generated by tests/golden/make_golden.py) -------------------
+def test_c_caller_built_against_the_reference_header(oracle, tmp_path):
+    """tests/abi_harness.c knows only the reference's kernels/lattice_symmetries_types.h; built on the CPU tier
+    (tests/test_abi.py) and linked with the drop-in library, it fills the structs like the Haskell host does
+    (FFI.hs:92-143), builds the basis with ls_hs_build_representatives and multiplies through
+    ls_hs_internal_get_chpl_kernels()->matrix_vector_product.  Representatives bit-exact, y to 1e-12 vs the oracle."""
+    import struct
+    import subprocess
+    from pathlib import Path
+    from lattice_symmetries_b200.expr import compile_terms
+    from lattice_symmetries_b200 import lattices as L
+    harness = Path(__file__).resolve().parent / "_build" / "abi_harness"
+    if not harness.exists():
+        if not Path("/root/reference/kernels").is_dir():
+            pytest.skip("tests/_build/abi_harness has not been built (it needs the reference header: run the CPU tests first)")
+        import test_abi
+        test_abi.build_harness()
+    n, hw, inv = 14, 7, -1
+    model = L.heisenberg_chain(n, symmetric=False)
+    p = H.Problem("chain14_inv", n, model.expression, hamming_weight=hw, spin_inversion=inv)
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    ts = compile_terms(model.expression, n)
+    tables = [[t for t in ts if t.x != 0], [t for t in ts if t.x == 0]]
+    blob = struct.pack("<5i", n, hw, inv, len(tables[0]), len(tables[1]))
+    for tab in tables:
+        blob += b"".join(struct.pack("<2d", t.v.real, t.v.imag) for t in tab)
+        for k in "mlrxs":
+            blob += b"".join(struct.pack("<Q", getattr(t, k)) for t in tab)
+    (tmp_path / "problem.bin").write_bytes(blob)
+    out = subprocess.run([str(harness), "run", str(tmp_path / "problem.bin"), str(tmp_path / "out.bin")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = (tmp_path / "out.bin").read_bytes()
+    dim = struct.unpack("<Q", raw[:8])[0]
+    got_reps = np.frombuffer(raw, dtype=np.uint64, count=dim, offset=8)
+    x = np.frombuffer(raw, dtype=np.float64, count=dim, offset=8 + 8 * dim)
+    y = np.frombuffer(raw, dtype=np.float64, count=dim, offset=8 + 16 * dim)
+    assert np.array_equal(got_reps, reps)
+    want = oracle.matvec(ob, off, diag, index, x)[0]
+    assert _rel_err(y, want) < MATVEC_RTOL
+
+
 def test_golden_fixtures():
     import json
     from pathlib import Path
