@@ -279,7 +279,7 @@ def sampled_rows_check(model, basis, lay, y_local, seed_x: int, complex_vectors:
     got = allreduce(got, torch.float64)
     betas, coeffs, offsets = oracle.apply_off_diag(off, alphas)
     col = np.repeat(np.arange(n), np.diff(offsets))
-    if ob.group is not None:
+    if ob.group is not None and ob.c.has_permutation_symmetries:
         rep_b, chi, n_b = ob.group.state_info(betas)
         n_a = ob.group.state_info(alphas)[2]
     elif model.spin_inversion:

@@ -629,6 +629,89 @@ def test_lanczos_matches_eigsh(oracle, built):
 
 
 # ---- golden fixtures (tests/golden, generated by tests/golden/make_golden.py) -------------------
+@pytest.mark.parametrize("name", ["chain16_symm", "kagome18_c2", "kagome24_c2v_inv", "ladder_2x8_dm", "kagome12_complex",
+                                  "chain12_inv_only", "hubbard_2x4"])
+def test_projected_rows_of_H(oracle, built, name):
+    """ls_b200_operator_apply_off_diag_projected: representatives and offsets bit-exact, coefficients
+    chi c n(beta) / n(alpha) (BatchedOperator.chpl:207-253) to rounding, indices consistent with the basis; and the
+    rows, summed up, reproduce the matrix-vector product."""
+    p, (ob, reps, index, off, diag), basis, op = built(name, oracle)
+    rng = np.random.default_rng(31)
+    sel = np.sort(rng.choice(reps.shape[0], size=min(reps.shape[0], 500), replace=False))
+    alphas = reps[sel]
+    got_reps, got_c, got_off, got_idx = op.apply_off_diag_projected(alphas, with_indices=True)
+    betas, coeffs, offsets = oracle.apply_off_diag(off, alphas)
+    assert np.array_equal(got_off, offsets)
+    col = np.repeat(np.arange(alphas.shape[0]), np.diff(offsets))
+    if ob.c.has_permutation_symmetries:
+        rb, rc, rn = ob.group.state_info(betas)
+        na = ob.group.state_info(alphas)[2]
+        want_c = np.where(rn > 0, rc * (coeffs * rn / na[col]), 0)
+    elif p.spin_inversion:
+        mask = np.uint64((1 << p.number_sites) - 1)
+        flipped = betas ^ mask
+        rb = np.minimum(betas, flipped)
+        want_c = np.where(flipped < betas, float(p.spin_inversion), 1.0) * coeffs
+    else:
+        rb, want_c = betas, coeffs
+    assert np.array_equal(got_reps, rb)
+    assert np.allclose(got_c, want_c, rtol=1e-14, atol=1e-15)
+    assert np.array_equal(got_idx, index(rb))
+    # columns of the projected operator assemble to H: y = sum_i x_i (column i), restricted to the sampled columns
+    if not np.iscomplexobj(want_c) or np.all(np.abs(want_c.imag) < 1e-14):
+        x = np.zeros(reps.shape[0])
+        x[sel] = rng.standard_normal(sel.shape[0])
+        y = oracle.apply_diag(diag, reps) * x if diag.n else np.zeros(reps.shape[0])
+        live = got_idx >= 0
+        np.add.at(y, got_idx[live], (got_c.real * x[sel][col])[live])
+        assert _rel_err(y, op.apply_to_state_vector(x)) < MATVEC_RTOL
+
+
+def test_lanczos_thick_restart_matches_eigsh(oracle, built):
+    """k lowest eigenpairs (Diagonalize.chpl:166-177 numEvals) against scipy's eigsh on the ORACLE's matvec --
+    an independent operator implementation on a problem the plain Lanczos test does not use."""
+    import scipy.sparse.linalg as sla
+    from lattice_symmetries_b200.lanczos import lanczos_ground_state, lanczos_thick_restart
+    p, (ob, reps, index, off, diag), basis, op = built("kagome18_c2", oracle)
+    dim = reps.shape[0]
+    mv = lambda v: oracle.matvec(ob, off, diag, index, np.ascontiguousarray(v, dtype=np.float64).reshape(-1))[0]
+    want = np.sort(sla.eigsh(sla.LinearOperator((dim, dim), matvec=mv, dtype=np.float64), k=4, which="SA", tol=1e-12)[0])
+    res = lanczos_thick_restart(op, k=4, basis_size=32, tol=1e-11)
+    assert res.converged
+    assert np.allclose(res.energies, want, rtol=0, atol=1e-9 * abs(want[0]))
+    # residuals of the returned vectors, computed with the product itself
+    import torch
+    for i in range(4):
+        v = res.eigenvectors[i]
+        w = torch.zeros_like(v)
+        op.matvec_device(v.data_ptr(), w.data_ptr(), sync=True)
+        assert float(torch.linalg.vector_norm(w - res.energies[i] * v)) < 1e-8 * abs(want[0])
+    single = lanczos_ground_state(op, tol=1e-12, energy_tol=1e-13)
+    assert abs(single.energy - want[0]) < 1e-9 * abs(want[0])
+
+
+def test_lanczos_thick_restart_complex_sector(oracle, built):
+    """complex128 vectors (momentum sector with complex characters): lowest eigenvalues against a dense
+    diagonalisation of the matrix assembled from the oracle's per-state primitives."""
+    import torch
+    from lattice_symmetries_b200.lanczos import lanczos_thick_restart
+    p, (ob, reps, index, off, diag), basis, op = built("kagome12_complex", oracle)
+    dim = reps.shape[0]
+    betas, coeffs, offsets = oracle.apply_off_diag(off, reps)
+    rb, rc, rn = ob.group.state_info(betas)
+    na = ob.group.state_info(reps)[2]
+    col = np.repeat(np.arange(dim), np.diff(offsets))
+    j = index(rb)
+    live = rn > 0
+    Hm = np.zeros((dim, dim), dtype=np.complex128)
+    np.add.at(Hm, (j[live], col[live]), (coeffs * rc * rn / na[col])[live])
+    Hm += np.diag(oracle.apply_diag(diag, reps))
+    assert np.allclose(Hm, Hm.conj().T, atol=1e-12)
+    want = np.linalg.eigvalsh(Hm)[:3]
+    res = lanczos_thick_restart(op, k=3, basis_size=30, tol=1e-11, dtype=torch.complex128)
+    assert res.converged and np.allclose(res.energies, want, rtol=0, atol=1e-9 * abs(want[0]))
+
+
 def test_c_caller_built_against_the_reference_header(oracle, tmp_path):
     """tests/abi_harness.c knows only the reference's kernels/lattice_symmetries_types.h; built on the CPU tier
     (tests/test_abi.py) and linked with the drop-in library, it fills the structs like the Haskell host does
