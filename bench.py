@@ -383,6 +383,12 @@ def ncu_capture(kernel: str, workload: str):
         parts = l.split()
         if len(parts) < 2:
             continue
+        if l.startswith("Elapsed Cycles"):
+            try:
+                out["elapsed_cycles"] = float(parts[-1].replace(",", ""))
+            except ValueError:
+                pass
+            continue
         key, val = parts[0], parts[1].replace(",", "")
         try:
             v = float(val)
@@ -392,6 +398,12 @@ def ncu_capture(kernel: str, workload: str):
                    "smsp__inst_executed.sum", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
                    "launch_matrix_elements", "gpu__time_duration.sum"):
             out[key] = v
+    # alu-pipe warp instructions of the captured launch: counted directly when the capture has the counter, else from
+    # the pipe's utilisation: pct x elapsed cycles x 2 warp-instructions per cycle per SM (4 sub-partitions x 16 lanes)
+    pct = out.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")
+    if "smsp__inst_executed_pipe_alu.sum" not in out and pct is not None and "elapsed_cycles" in out:
+        out["smsp__inst_executed_pipe_alu.sum"] = pct / 100.0 * out["elapsed_cycles"] * 2.0 * 148
+        out["alu_inst_source"] = "pct_of_peak x elapsed cycles x 2 warp-inst/clk/SM x 148 SMs"
     return out
 
 

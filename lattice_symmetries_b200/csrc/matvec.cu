@@ -221,7 +221,7 @@ constexpr int kRankThreads = 256;
 constexpr int kRankBatch = LS_RANK_BATCH;
 constexpr unsigned long long kMissBits = 0x7ff8dead00000001ull;  // a quiet NaN no computation produces
 
-template <class Low, bool Wide = false>
+template <class Low, bool Wide = false, bool Sorted = false>
 __global__ void __launch_bounds__(kRankThreads, LS_RANK_MINBLOCKS)  // register cap, also for the (rare) noinline norm check
 rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -252,7 +252,7 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
   for (int u = 0; u < kRankBatch; ++u) {
     uint64_t const q = warp_q0 + (uint64_t)u * 32 + lane;
     live[u] = q < total;
-    needle[u] = live[u] ? (a.perm != nullptr ? __ldcs(a.q_sorted + q) : __ldcs(a.q_rep + q)) : 0;
+    needle[u] = live[u] ? (Sorted ? __ldcs(a.q_sorted + q) : __ldcs(a.q_rep + q)) : 0;
   }
   int64_t j[kRankBatch];
   if (a.debug_skip & 8) {  // profiling only: no index search
@@ -277,7 +277,7 @@ rank_gather_kernel(__grid_constant__ MatvecArgs const a) {
   for (int u = 0; u < kRankBatch; ++u) {
     if (!live[u]) continue;
     uint64_t q = warp_q0 + (uint64_t)u * 32 + lane;
-    if (a.perm != nullptr) q = __ldcs(a.perm + q);  // sorted ranking: back to the element's CSR position
+    if (Sorted) q = __ldcs(a.perm + q);  // sorted ranking: back to the element's CSR position
     bool const missing = j[u] < 0;
     double fr = 1.0, fi = 0.0;
     if (product) {
@@ -1070,6 +1070,14 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
   else if (a.ix.offsets64 != nullptr && !a.ix.identity && (a.ix.lows16 != nullptr || a.ix.lows32 != nullptr))
     // 2^32 states or more (the replicated index of a distributed basis): 64-bit bucket starts, 32-bit windows
     rank_gather = a.ix.lows16 != nullptr ? rank_gather_kernel<uint16_t, true> : rank_gather_kernel<uint32_t, true>;
+  // the same kernels reading the chunk's representatives in sorted order (LS_B200_MV_SORT=1)
+  void (*rank_gather_sorted)(MatvecArgs) = rank_gather_kernel<void, false, true>;
+  if (a.ix.offsets32 != nullptr && !a.ix.identity)
+    rank_gather_sorted = a.ix.lows16 != nullptr   ? rank_gather_kernel<uint16_t, false, true>
+                         : a.ix.lows32 != nullptr ? rank_gather_kernel<uint32_t, false, true>
+                                                  : rank_gather_kernel<uint64_t, false, true>;
+  else if (a.ix.offsets64 != nullptr && !a.ix.identity && (a.ix.lows16 != nullptr || a.ix.lows32 != nullptr))
+    rank_gather_sorted = a.ix.lows16 != nullptr ? rank_gather_kernel<uint16_t, true, true> : rank_gather_kernel<uint32_t, true, true>;
 
   // rank_gather runs as a persistent grid sized to the machine (tables staged once, no empty CTAs: 8 % faster);
   // the orbit kernel keeps one CTA per four blocks (see there).
@@ -1290,7 +1298,8 @@ void matvec_device(ls_hs_operator const *op, int64_t row_begin, int64_t row_end,
       }
       size_t const rank_smem = a.q_tsign != nullptr ? ((size_t)T + (size_t)a.number_chars) * 16 : 0;
       unsigned const blocks = std::min<unsigned>(ceil_div(max_tiles, kRankThreads / 32), rank_resident);
-      rank_gather<<<blocks, kRankThreads, rank_smem, stream_b>>>(a);
+      if (a.perm != nullptr) rank_gather_sorted<<<blocks, kRankThreads, rank_smem, stream_b>>>(a);
+      else rank_gather<<<blocks, kRankThreads, rank_smem, stream_b>>>(a);
       count_launch();
       if (profile) {
         CUDA_CHECK(cudaEventRecord(next_event(sc), stream_b));

@@ -26,3 +26,11 @@ for k in ["dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors.sum",
           "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
           "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_active"]:
     if k in d: print(k, d[k], hdr and "")
+for k in ["smsp__inst_executed.sum", "gpu__time_duration.sum"]:
+    if k in d: print(k, d[k])
+# the element count of the captured launch, printed by tools/profile_workload.py into the ncu log
+import os, re
+log = os.path.join(os.path.dirname(base), "ncu_" + os.path.basename(base).rsplit("_", 1)[0] + ".log")
+if os.path.exists(log):
+    m = re.search(r"launch_matrix_elements (\d+)", open(log, errors="replace").read())
+    if m: print("launch_matrix_elements", m.group(1))

@@ -25,3 +25,9 @@ ms = _lib.lib.ls_b200_last_kernel_ms
 print(name, "dim", dim, "matvec ms %.2f" % ms(b"matvec"), "orbit ms %.2f x%d" % (ms(b"orbit"), ms(b"orbit_launches")),
       "gather ms %.2f x%d" % (ms(b"gather"), ms(b"gather_launches")), "combine ms %.2f" % ms(b"combine"),
       "build ms %.2f" % ms(b"build"))
+# matrix elements of the launch that `ncu -s 1 -c 1` captures (the second chunk of the first product): lets bench.py turn the
+# captured instruction count into instructions per matrix element
+T = max(1, op.number_off_diag_terms)
+chunk_rows = max(1, min(dim, (1 << 27) // T))
+second = op.count_matrix_elements(min(dim, chunk_rows), min(dim, 2 * chunk_rows)) if dim > chunk_rows else op.count_matrix_elements(0, dim)
+print("launch_matrix_elements", second)
