@@ -464,7 +464,9 @@ def main():
     sync()
     # The whole build (enumeration, redistribution to contiguous row ranges when N > 1, host view, state -> index
     # structure) from scratch on a fresh basis object; median of three (one for the largest workloads); all samples listed.
-    number_builds = 1 if total_candidates > (1 << 36) else 3
+    # (N > 1: five samples -- the first build of a process also sets up the NCCL connections, and an allocation that
+    # reaches the driver under peer access can take a second; the median of five shrugs off two such outliers)
+    number_builds = 1 if total_candidates > (1 << 36) else (5 if world > 1 else 3)
     samples = []
     op = None
     for attempt in range(number_builds):

@@ -645,13 +645,9 @@ BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<ui
   // host_visible: the representatives go straight into the managed allocation that will serve as the caller's
   // host view (make_host_view then has nothing to copy)
   auto alloc_reps = [&](uint64_t **p, uint64_t n) {
-    if (host_visible && want_managed_view() && cudaMallocManaged(p, sizeof(uint64_t) * n) == cudaSuccess) {
-      CUDA_CHECK(cudaMemAdvise(*p, sizeof(uint64_t) * n, cudaMemAdviseSetPreferredLocation, rt.device));
-      CUDA_CHECK(cudaMemPrefetchAsync(*p, sizeof(uint64_t) * n, rt.device, rt.stream));
-      return;
-    }
-    (void)cudaGetLastError();
-    CUDA_CHECK(cudaMalloc(p, sizeof(uint64_t) * n));
+    *p = nullptr;
+    if (host_visible && want_managed_view()) *p = static_cast<uint64_t *>(block_alloc(sizeof(uint64_t) * n, true));
+    if (*p == nullptr) *p = static_cast<uint64_t *>(block_alloc(sizeof(uint64_t) * n, false));
   };
   if (!plan.projected) {
     alloc_reps(&res.d_reps, candidates);
@@ -719,7 +715,7 @@ BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<ui
     uint64_t const images = (uint64_t)std::max(1, g.number_masks);
     uint64_t capacity = std::min<uint64_t>(candidates, candidates / images * 5 / 4 + (1u << 16));
     alloc_reps(&res.d_reps, capacity);
-    CUDA_CHECK(cudaMalloc(&res.d_norms, sizeof(double) * capacity));
+    block_alloc(&res.d_norms, sizeof(double) * capacity);
     alloc_ms += since(t_alloc);
     uint64_t emitted = 0, scanned = 0;
     GroupView const gv = g.view();
@@ -807,12 +803,12 @@ BuildResult build_ranges(ls_hs_basis const *basis, Ranges ranges, std::vector<ui
           double *new_norms = nullptr;
           auto const t_grow = std::chrono::steady_clock::now();
           alloc_reps(&new_reps, new_capacity);
-          CUDA_CHECK(cudaMalloc(&new_norms, sizeof(double) * new_capacity));
+          block_alloc(&new_norms, sizeof(double) * new_capacity);
           CUDA_CHECK(cudaMemcpyAsync(new_reps, res.d_reps, sizeof(uint64_t) * emitted, cudaMemcpyDeviceToDevice, rt.stream));
           CUDA_CHECK(cudaMemcpyAsync(new_norms, res.d_norms, sizeof(double) * emitted, cudaMemcpyDeviceToDevice, rt.stream));
           CUDA_CHECK(cudaStreamSynchronize(rt.stream));
-          cudaFree(res.d_reps);
-          cudaFree(res.d_norms);
+          block_free(res.d_reps);
+          block_free(res.d_norms);
           res.d_reps = new_reps;
           res.d_norms = new_norms;
           capacity = new_capacity;
@@ -867,13 +863,13 @@ static void free_pinned(void *p) {
     auto &reg = built_registry();
     auto it = reg.find(p);
     if (it != reg.end()) {
-      if (it->second.d_reps != p) cudaFree(it->second.d_reps);
-      cudaFree(it->second.d_norms);
+      if (it->second.d_reps != p) block_free(it->second.d_reps);
+      block_free(it->second.d_norms);
       reg.erase(it);
     }
   }
   cudaPointerAttributes attr{};
-  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeManaged) cudaFree(p);
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeManaged) block_free(p);
   else cudaFreeHost(p);
 }
 
@@ -906,18 +902,15 @@ static uint64_t *make_host_view(uint64_t *&d_reps, uint64_t count) {
   }
   (void)cudaGetLastError();
   if (managed) {
-    uint64_t *m = nullptr;
-    if (cudaMallocManaged(&m, bytes) == cudaSuccess) {
-      CUDA_CHECK(cudaMemAdvise(m, bytes, cudaMemAdviseSetPreferredLocation, rt.device));
-      CUDA_CHECK(cudaMemPrefetchAsync(m, bytes, rt.device, rt.stream));
+    uint64_t *m = static_cast<uint64_t *>(block_alloc(bytes, true));
+    if (m != nullptr) {
       CUDA_CHECK(cudaMemcpyAsync(m, d_reps, bytes, cudaMemcpyDeviceToDevice, rt.stream));
       CUDA_CHECK(cudaStreamSynchronize(rt.stream));
       CUDA_CHECK(cudaMemAdvise(m, bytes, cudaMemAdviseSetReadMostly, rt.device));
-      cudaFree(d_reps);
+      block_free(d_reps);
       d_reps = m;
       return m;
     }
-    (void)cudaGetLastError();
   }
   uint64_t *host = nullptr;
   CUDA_CHECK(cudaMallocHost(&host, bytes));
@@ -936,7 +929,7 @@ void launch_state_info(GroupData const &g, int64_t n, uint64_t const *d_alphas, 
 void ensure_norms(IndexData &ix, GroupData const &g) {
   if (ix.d_norms != nullptr || ix.number_states == 0) return;
   Runtime &rt = runtime();
-  CUDA_CHECK(cudaMalloc(&ix.d_norms, sizeof(double) * (size_t)ix.number_states));
+  block_alloc(&ix.d_norms, sizeof(double) * (size_t)ix.number_states);
   DeviceBuffer<uint64_t> betas;
   DeviceBuffer<double2> chars;
   int64_t const chunk = int64_t(1) << 24;
@@ -950,16 +943,10 @@ void ensure_norms(IndexData &ix, GroupData const &g) {
 }
 
 uint64_t *alloc_representatives(uint64_t count) {
-  Runtime &rt = runtime();
-  uint64_t *p = nullptr;
   size_t const bytes = sizeof(uint64_t) * std::max<uint64_t>(count, 1);
-  if (getenv("LS_B200_NO_HOST_MIRROR") == nullptr && want_managed_view() && cudaMallocManaged(&p, bytes) == cudaSuccess) {
-    CUDA_CHECK(cudaMemAdvise(p, bytes, cudaMemAdviseSetPreferredLocation, rt.device));
-    CUDA_CHECK(cudaMemPrefetchAsync(p, bytes, rt.device, rt.stream));
-    return p;
-  }
-  (void)cudaGetLastError();
-  CUDA_CHECK(cudaMalloc(&p, bytes));
+  uint64_t *p = nullptr;
+  if (getenv("LS_B200_NO_HOST_MIRROR") == nullptr && want_managed_view()) p = static_cast<uint64_t *>(block_alloc(bytes, true));
+  if (p == nullptr) p = static_cast<uint64_t *>(block_alloc(bytes, false));
   return p;
 }
 
@@ -1011,7 +998,7 @@ int ls_b200_build_blocks(ls_hs_basis const *basis, uint64_t first_begin, uint64_
               (unsigned long long)block_size, (unsigned long long)r.count, runtime().last_build_ms,
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     *representatives_dev = r.d_reps;
-    if (norms_dev != nullptr) *norms_dev = r.d_norms; else cudaFree(r.d_norms);
+    if (norms_dev != nullptr) *norms_dev = r.d_norms; else block_free(r.d_norms);
     status = 0;
   });
   return status;
@@ -1035,7 +1022,7 @@ int ls_b200_build_shard(ls_hs_basis const *basis, uint64_t index_begin, uint64_t
               runtime().last_build_ms,
               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     *representatives_dev = r.d_reps;
-    if (norms_dev != nullptr) *norms_dev = r.d_norms; else cudaFree(r.d_norms);
+    if (norms_dev != nullptr) *norms_dev = r.d_norms; else block_free(r.d_norms);
     *count = r.count;
     status = 0;
   });
@@ -1067,8 +1054,8 @@ void ls_chpl_enumerate_representatives(ls_hs_basis const *basis, uint64_t lower,
       }
       built_registry()[host] = BuiltReps{r.d_reps, r.d_norms, r.count};
     } else {
-      cudaFree(r.d_reps);
-      cudaFree(r.d_norms);
+      block_free(r.d_reps);
+      block_free(r.d_norms);
     }
     dest->elts = host;
     dest->num_elts = r.count;

@@ -62,6 +62,13 @@ struct Runtime {
 };
 Runtime &runtime();
 
+// block cache (runtime.cu): large device allocations are recycled instead of going back to the driver
+void *block_alloc(size_t bytes, bool managed = false);
+void block_free(void *p);            // any device pointer
+size_t block_cache_trim(size_t keep_bytes = 0);
+size_t block_cache_idle_bytes();
+template <class T>
+inline void block_alloc(T **p, size_t bytes, bool managed = false) { *p = static_cast<T *>(block_alloc(bytes, managed)); }
 void *alloc_local(size_t bytes);  // large randomly-accessed tables (runtime.cu)
 template <class T>
 inline void alloc_local(T **p, size_t bytes) { *p = static_cast<T *>(alloc_local(bytes)); }

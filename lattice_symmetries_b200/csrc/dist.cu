@@ -98,7 +98,7 @@ int comm_world() { return g_comm.comm != nullptr ? g_comm.world : 1; }
 
 DistShard::~DistShard() {
   cudaFree(d_splitters);
-  cudaFree(d_xs_full);
+  block_free(d_xs_full);
   delete global_index;
   delete push;
 }
@@ -466,7 +466,7 @@ static void redistribute(Team const &team, std::vector<Piece> const &pieces, std
   }
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
   for (size_t m = 0; m < M; ++m) {
-    cudaFree(data[m]);
+    block_free(data[m]);
     data[m] = fresh[m];
   }
 }
@@ -474,9 +474,7 @@ static void redistribute(Team const &team, std::vector<Piece> const &pieces, std
 static void release_redistribute_scratch(size_t above_bytes);
 static void *allocate_representatives(uint64_t elements) { return alloc_representatives(elements); }
 static void *allocate_plain(uint64_t elements) {
-  void *p = nullptr;
-  CUDA_CHECK(cudaMalloc(&p, 8 * std::max<uint64_t>(elements, 1)));
-  return p;
+  return block_alloc(8 * std::max<uint64_t>(elements, 1), false);
 }
 
 // ---- distributed build ----------------------------------------------------------------------------------------------
@@ -516,6 +514,7 @@ static void build_global_index(Team const &team, std::vector<ls_hs_basis *> cons
     if (char const *env = getenv("LS_B200_DIST_RESERVE_GB")) reserve = (size_t)(atof(env) * (double)(size_t(1) << 30));
     size_t free_bytes = 0, total_bytes = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_bytes, &total_bytes));
+    free_bytes += block_cache_idle_bytes();  // (handed back to the driver on demand)
     if (team.emulated) free_bytes /= std::max<size_t>(1, M);  // virtual ranks share one device
     int64_t const headroom = team.min_host({(int64_t)free_bytes - (int64_t)(need + need / 16) - (int64_t)reserve});
     if (headroom < 0) {
@@ -892,7 +891,7 @@ static void dist_matvec(Team const &team, std::vector<ls_hs_operator const *> co
       DistShard &sh = *local[m]->dist;
       size_t const words = (size_t)sh.dim * scalar;
       if (sh.xs_full_words < words) {
-        cudaFree(sh.d_xs_full);
+        block_free(sh.d_xs_full);
         sh.d_xs_full = nullptr;
         alloc_local(&sh.d_xs_full, sizeof(double) * words);
         sh.xs_full_words = words;

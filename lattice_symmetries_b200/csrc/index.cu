@@ -30,15 +30,15 @@ IndexView IndexData::view() const {
 IndexData::~IndexData() {
   matvec_forget_index(this);
   delete dist;
-  if (owns_d_reps) cudaFree(d_reps);
-  cudaFree(d_offsets32);
-  cudaFree(d_offsets64);
-  cudaFree(d_lows16);
-  cudaFree(d_lows32);
-  cudaFree(d_sub_info);
-  cudaFree(d_subtab);
-  cudaFree(d_entry8);
-  cudaFree(d_norms);
+  if (owns_d_reps) block_free(d_reps);
+  block_free(d_offsets32);
+  block_free(d_offsets64);
+  block_free(d_lows16);
+  block_free(d_lows32);
+  block_free(d_sub_info);
+  block_free(d_subtab);
+  block_free(d_entry8);
+  block_free(d_norms);
   magic = 0;
 }
 
@@ -284,7 +284,7 @@ void build_bucket_table(IndexData &ix, int requested_prefix_bits) {
       d_units = nullptr;
       have_sub = true;
     }
-    if (d_units != nullptr) cudaFree(d_units);  // nothing was crowded
+    if (d_units != nullptr) block_free(d_units);  // nothing was crowded
     CUDA_CHECK(cudaStreamSynchronize(rt.stream));
   }
   if (have_sub) {
@@ -326,7 +326,7 @@ IndexData *create_index(uint64_t const *host_reps, int64_t count, int number_bit
     ix->owns_d_reps = static_cast<void const *>(ix->d_reps) != static_cast<void const *>(host_reps);
     reg.erase(it);
   } else if (count > 0) {
-    CUDA_CHECK(cudaMalloc(&ix->d_reps, sizeof(uint64_t) * (size_t)count));
+    block_alloc(&ix->d_reps, sizeof(uint64_t) * (size_t)count);
     CUDA_CHECK(cudaMemcpyAsync(ix->d_reps, host_reps, sizeof(uint64_t) * (size_t)count,
                                cudaMemcpyHostToDevice, runtime().stream));
   }

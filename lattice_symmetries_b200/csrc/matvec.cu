@@ -1815,6 +1815,7 @@ void ls_chpl_matrix_vector_product(ls_hs_operator *op, int num_vectors, double c
       // DeviceBuffer::reserve, + the 8 B values of the largest chunk) must fit next to everything already resident.
       size_t free_bytes = 0, total_bytes = 0;
       CUDA_CHECK(cudaMemGetInfo(&free_bytes, &total_bytes));
+      free_bytes += block_cache_idle_bytes();
       size_t const needed = (size_t)((double)od.stats_elements * 11.0 * 1.25) + (size_t(3) << 30);
       if (needed > free_bytes) two_phases = false;
     }

@@ -3,6 +3,8 @@
 // of chapel/src/library.c (ls_chpl_init / ls_chpl_finalize).
 #include <atomic>
 
+#include <map>
+
 #include "state.hpp"
 
 namespace lsb {
@@ -53,18 +55,134 @@ void Runtime::ensure() {
   CUDA_CHECK(cudaEventCreate(&ev1));
 }
 
-// Allocation of the large randomly-accessed tables (index levels, keys, the replicated vector).  Default: cudaMalloc.
-// LS_B200_POOL_MALLOC=1: stream-ordered allocations from the device's default memory pool, which -- unlike cudaMalloc
-// once peer access is enabled -- is mapped by this device only.  A/B on 2 x B200 (chain-40, 17 GB of tables, random
-// 8-byte gathers): no difference in kernel time (397 ms either way), so the plain allocator stays the default.
+// ---- block cache ---------------------------------------------------------------------------------------------------
+// Large device allocations of the library (representatives, norms, index tables, the replicated vector, build outputs)
+// go through a caching layer: a freed block is kept (up to LS_B200_CACHE_GB, default 8 GB in total) and handed out
+// again to the next request of about the same size.  cudaMalloc / cudaFree / cudaMallocManaged are device-wide
+// synchronising driver calls whose cost on the test boxes ranges from 0.1 ms to > 1 s once NCCL has enabled peer
+// access (every allocation is then mapped into all peers): a second build of the same basis, or a re-balancing, then
+// never reaches the driver.  block_free accepts any device pointer (foreign ones are cudaFree'd).
+namespace {
+struct BlockInfo {
+  size_t capacity;
+  bool managed;
+};
+struct BlockCache {
+  std::mutex mutex;
+  std::unordered_map<void *, BlockInfo> live;
+  std::multimap<size_t, void *> idle[2];  // [managed]
+  size_t idle_bytes = 0;
+  size_t limit() const {
+    static size_t const value = [] {
+      double gb = 8.0;
+      if (char const *env = getenv("LS_B200_CACHE_GB")) gb = atof(env);
+      return (size_t)(gb * (double)(size_t(1) << 30));
+    }();
+    return value;
+  }
+};
+BlockCache &block_cache() {
+  static BlockCache *c = new BlockCache();  // never destroyed: finalizers may run after static destruction began
+  return *c;
+}
+constexpr size_t kCacheMinBytes = size_t(256) << 10;
+}  // namespace
+
+size_t block_cache_trim(size_t keep_bytes) {
+  BlockCache &c = block_cache();
+  std::lock_guard<std::mutex> lock(c.mutex);
+  size_t released = 0;
+  for (int m = 0; m < 2; ++m) {
+    while (!c.idle[m].empty() && c.idle_bytes > keep_bytes) {
+      auto it = std::prev(c.idle[m].end());  // largest first
+      cudaFree(it->second);
+      released += it->first;
+      c.idle_bytes -= it->first;
+      c.idle[m].erase(it);
+    }
+  }
+  return released;
+}
+
+size_t block_cache_idle_bytes() {
+  BlockCache &c = block_cache();
+  std::lock_guard<std::mutex> lock(c.mutex);
+  return c.idle_bytes;
+}
+
+void *block_alloc(size_t bytes, bool managed) {
+  Runtime &rt = runtime();
+  BlockCache &c = block_cache();
+  bytes = std::max<size_t>(bytes, 8);
+  if (bytes >= kCacheMinBytes) {
+    std::lock_guard<std::mutex> lock(c.mutex);
+    auto &idle = c.idle[managed ? 1 : 0];
+    auto it = idle.lower_bound(bytes);
+    if (it != idle.end() && it->first <= bytes + bytes / 4 + (size_t(2) << 20)) {
+      void *p = it->second;
+      size_t const cap = it->first;
+      idle.erase(it);
+      c.idle_bytes -= cap;
+      c.live[p] = BlockInfo{cap, managed};
+      if (managed) {
+        // the previous owner advised read-mostly once its contents were final: the next one writes from the device
+        (void)cudaMemAdvise(p, cap, cudaMemAdviseUnsetReadMostly, rt.device);
+        (void)cudaMemPrefetchAsync(p, cap, rt.device, rt.stream);
+        (void)cudaGetLastError();
+      }
+      return p;
+    }
+  }
+  size_t const cap = bytes >= kCacheMinBytes ? (bytes + (size_t(2) << 20) - 1) / (size_t(2) << 20) * (size_t(2) << 20) : bytes;
+  void *p = nullptr;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    cudaError_t const e = managed ? cudaMallocManaged(&p, cap) : cudaMalloc(&p, cap);
+    if (e == cudaSuccess) break;
+    (void)cudaGetLastError();
+    p = nullptr;
+    if (attempt == 0 && block_cache_trim(0) > 0) continue;  // give the idle blocks back and try once more
+    if (managed) return nullptr;                            // callers fall back to plain device memory
+    cuda_check(e, "cudaMalloc (block_alloc)", __FILE__, __LINE__);
+  }
+  if (managed) {
+    CUDA_CHECK(cudaMemAdvise(p, cap, cudaMemAdviseSetPreferredLocation, rt.device));
+    CUDA_CHECK(cudaMemPrefetchAsync(p, cap, rt.device, rt.stream));
+  }
+  if (cap >= kCacheMinBytes) {
+    std::lock_guard<std::mutex> lock(c.mutex);
+    c.live[p] = BlockInfo{cap, managed};
+  }
+  return p;
+}
+
+void block_free(void *p) {
+  if (p == nullptr) return;
+  BlockCache &c = block_cache();
+  {
+    std::lock_guard<std::mutex> lock(c.mutex);
+    auto it = c.live.find(p);
+    if (it != c.live.end()) {
+      BlockInfo const info = it->second;
+      c.live.erase(it);
+      if (info.capacity <= c.limit() && c.idle_bytes + info.capacity <= c.limit()) {
+        c.idle[info.managed ? 1 : 0].emplace(info.capacity, p);
+        c.idle_bytes += info.capacity;
+        return;
+      }
+    }
+  }
+  cudaFree(p);
+}
+
+// Allocation of the large randomly-accessed tables (index levels, keys, the replicated vector): the block cache, or --
+// LS_B200_POOL_MALLOC=1, an A/B knob -- stream-ordered allocations from the device's default memory pool, which unlike
+// cudaMalloc under peer access is mapped by this device only.  A/B on 2 x B200 (chain-40, 17 GB of tables, random 8-byte
+// gathers): no difference in kernel time (397 ms either way).
 void *alloc_local(size_t bytes) {
+  static bool const pool = getenv("LS_B200_POOL_MALLOC") != nullptr;
+  if (!pool) return block_alloc(bytes, false);
   Runtime &rt = runtime();
   void *p = nullptr;
-  static bool const plain = getenv("LS_B200_POOL_MALLOC") == nullptr;  // A/B knob
-  if (plain) {
-    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 8)));
-    return p;
-  }
   CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(bytes, 8), rt.stream));
   CUDA_CHECK(cudaStreamSynchronize(rt.stream));
   return p;
@@ -197,11 +315,11 @@ int ls_b200_device_count(void) {
 
 void *ls_b200_device_malloc(size_t bytes) {
   void *p = nullptr;
-  guarded("ls_b200_device_malloc", [&] { CUDA_CHECK(cudaMalloc(&p, bytes)); });
+  guarded("ls_b200_device_malloc", [&] { p = block_alloc(bytes, false); });
   return p;
 }
 void ls_b200_device_free(void *p) {
-  if (p != nullptr) cudaFree(p);
+  if (p != nullptr) block_free(p);
 }
 
 int ls_b200_copy_to_device(void *dst_dev, void const *src_host, size_t bytes) {
