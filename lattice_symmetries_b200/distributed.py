@@ -63,8 +63,9 @@ def even_bounds(dim: int, world: int) -> List[int]:
 
 
 def plan_blocks(total: int, world: int) -> List[Tuple[int, int]]:
-    """Blocks of the candidate-index range, block b scanned by rank b % world (csrc/dist.cu ``dist_block_plan``:
-    small blocks first -- representatives crowd into the low indices -- doubling every 8 * world blocks)."""
+    """Blocks of the candidate-index range, block b scanned by rank b % world (csrc/dist.cu ``dist_block_plan``):
+    equal blocks of a power of two >= 2^20 candidates, at most ~4096 per rank -- representatives crowd into the low
+    indices, dealing many small blocks round-robin gives every rank the same share of every density regime."""
     from ._lib import lib
     n = int(lib.ls_b200_plan_blocks(int(total), int(world), None, None, 0))
     begins = (C.c_uint64 * max(n, 1))()

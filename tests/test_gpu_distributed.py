@@ -203,6 +203,21 @@ def test_emulated_rebalance_respects_the_row_cap(oracle, monkeypatch):
         assert _rel_err(team.matvec(x, mode), want) <= MATVEC_RTOL
 
 
+@pytest.mark.parametrize("prefix", ["4", "10", "14"])
+def test_emulated_wide_index_any_prefix_width(oracle, prefix, monkeypatch):
+    """LS_B200_DIST_PREFIX: the wide replicated index (64-bit bucket starts summed over the ranks + compact keys) with
+    2-byte and 4-byte keys and buckets from a handful to thousands of states."""
+    from lattice_symmetries_b200.distributed import ALLGATHER, WIDE_INDEX
+    monkeypatch.setenv("LS_B200_DIST_PREFIX", prefix)
+    p = _problems()["kagome24_c2v_inv"]()
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    team = _emulated(p, 3, WIDE_INDEX, True)
+    assert team.layouts[0].global_index == 2 and team.layouts[0].prefix_bits == int(prefix)
+    x = np.random.default_rng(23).standard_normal(reps.shape[0])
+    want = oracle.matvec(ob, off, diag, index, x)[0]
+    assert _rel_err(team.matvec(x, ALLGATHER), want) <= MATVEC_RTOL
+
+
 def test_allgather_form_is_dropped_when_it_does_not_fit(oracle, monkeypatch):
     """The replicated index + vector must fit next to the caller's reserve on every rank; otherwise the build leaves
     them out and the automatic product form is all-to-all."""
