@@ -431,6 +431,12 @@ int64_t ls_b200_plan_redistribution(int world, int me, int64_t number_pieces, in
                                     int64_t *rcount, int64_t *rdispl, int64_t *places, int64_t capacity);
 int ls_b200_plan_balanced_bounds(int64_t number_blocks, int64_t const *edges, double const *costs, int world,
                                  int64_t *bounds);
+/* ... of equal cost with at most `cap` rows per rank, boundaries interpolated inside a block (ls_b200_dist_rebalance). */
+int ls_b200_plan_rebalance_bounds(int64_t number_blocks, int64_t const *edges, double const *costs, int world, int64_t cap,
+                                  int64_t *bounds);
+/* A rank's block-cyclic share of the candidate range: out = {block shift (a block holds 32 << shift candidates), blocks
+ * over all ranks, blocks of this rank, candidates of this rank}. */
+int ls_b200_plan_cyclic_share(uint64_t total, int world, int rank, uint64_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -217,6 +217,8 @@ PROTOTYPES = {
         C.c_int64, [C.c_int, C.c_int, C.c_int64, i64_p, C.POINTER(C.c_int32), i64_p, i64_p, i64_p, i64_p, i64_p, i64_p,
                     C.c_int64]),
     "ls_b200_plan_balanced_bounds": (C.c_int, [C.c_int64, i64_p, f64_p, C.c_int, i64_p]),
+    "ls_b200_plan_rebalance_bounds": (C.c_int, [C.c_int64, i64_p, f64_p, C.c_int, C.c_int64, i64_p]),
+    "ls_b200_plan_cyclic_share": (C.c_int, [C.c_uint64, C.c_int, C.c_int, u64_p]),
 }
 
 

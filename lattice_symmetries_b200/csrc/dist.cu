@@ -215,6 +215,44 @@ std::vector<int64_t> dist_balanced_bounds(std::vector<int64_t> const &edges, std
   return bounds;
 }
 
+// Row ranges of equal cost in which no rank holds more than `cap` rows.  The cheap rows sit at the low end of the list,
+// so it is the first ranks that hit the cap: they are fixed at the cap one by one and the rest of the range is balanced
+// over the remaining ranks.
+std::vector<int64_t> dist_capped_bounds(std::vector<int64_t> const &edges, std::vector<double> const &piece_costs, int P,
+                                        int64_t cap) {
+  int64_t const dim = edges.back();
+  std::vector<int64_t> fresh = dist_balanced_bounds(edges, piece_costs, P, true);
+  for (int r0 = 0; r0 + 1 < P; ++r0) {
+    if (fresh[(size_t)r0 + 1] - fresh[(size_t)r0] <= cap) {
+      bool ok = true;
+      for (int r = r0; r < P; ++r) ok = ok && fresh[(size_t)r + 1] - fresh[(size_t)r] <= cap;
+      if (ok) break;
+      // (a later rank is over the cap although this one is not: fix this one where it is and look again)
+    } else {
+      fresh[(size_t)r0 + 1] = fresh[(size_t)r0] + cap;
+    }
+    // balance rows [fresh[r0 + 1], dim) over ranks r0 + 1 .. P - 1
+    int64_t const start = fresh[(size_t)r0 + 1];
+    std::vector<int64_t> e{start};
+    std::vector<double> c;
+    for (size_t b = 0; b + 1 < edges.size(); ++b) {
+      if (edges[b + 1] <= start) continue;
+      double cost = piece_costs[b];
+      if (edges[b] < start) cost *= (double)(edges[b + 1] - start) / (double)(edges[b + 1] - edges[b]);
+      e.push_back(edges[b + 1]);
+      c.push_back(cost);
+    }
+    if (c.empty()) {
+      for (int r = r0 + 2; r <= P; ++r) fresh[(size_t)r] = dim;
+      break;
+    }
+    for (auto &v : e) v -= start;
+    std::vector<int64_t> const rest = dist_balanced_bounds(e, c, P - r0 - 1, true);
+    for (int r = r0 + 1; r <= P; ++r) fresh[(size_t)r] = start + rest[(size_t)(r - r0 - 1)];
+  }
+  return fresh;
+}
+
 // ---- the team: the ranks this process drives --------------------------------------------------------------------
 __global__ void add_i64_kernel(int64_t *__restrict__ acc, int64_t const *__restrict__ other, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -778,35 +816,7 @@ static bool dist_rebalance(Team const &team, std::vector<ls_hs_basis *> const &b
   for (int r = 0; r < P; ++r) cap = std::max(cap, bounds[(size_t)r + 1] - bounds[(size_t)r]);
   cap = cap + cap / 8 + 1;
   if (char const *env = getenv("LS_B200_DIST_MAX_ROWS")) cap = std::max<int64_t>(1, atoll(env));
-  std::vector<int64_t> fresh = dist_balanced_bounds(edges, piece_costs, P, true);
-  for (int r0 = 0; r0 + 1 < P; ++r0) {
-    if (fresh[(size_t)r0 + 1] - fresh[(size_t)r0] <= cap) {
-      bool ok = true;
-      for (int r = r0; r < P; ++r) ok = ok && fresh[(size_t)r + 1] - fresh[(size_t)r] <= cap;
-      if (ok) break;
-      // (a later rank is over the cap although this one is not: fix this one where it is and look again)
-    } else {
-      fresh[(size_t)r0 + 1] = fresh[(size_t)r0] + cap;
-    }
-    // balance rows [fresh[r0 + 1], dim) over ranks r0 + 1 .. P - 1
-    int64_t const start = fresh[(size_t)r0 + 1];
-    std::vector<int64_t> e{start};
-    std::vector<double> c;
-    for (size_t b = 0; b + 1 < edges.size(); ++b) {
-      if (edges[b + 1] <= start) continue;
-      double cost = piece_costs[b];
-      if (edges[b] < start) cost *= (double)(edges[b + 1] - start) / (double)(edges[b + 1] - edges[b]);
-      e.push_back(edges[b + 1]);
-      c.push_back(cost);
-    }
-    if (c.empty()) {
-      for (int r = r0 + 2; r <= P; ++r) fresh[(size_t)r] = dim;
-      break;
-    }
-    for (auto &v : e) v -= start;
-    std::vector<int64_t> const rest = dist_balanced_bounds(e, c, P - r0 - 1, true);
-    for (int r = r0 + 1; r <= P; ++r) fresh[(size_t)r] = start + rest[(size_t)(r - r0 - 1)];
-  }
+  std::vector<int64_t> const fresh = dist_capped_bounds(edges, piece_costs, P, cap);
   if (fresh == bounds) return false;
   // detach the local arrays from the bases (the index and the host view go, the arrays travel)
   std::vector<void *> reps(M, nullptr), norms(M, nullptr);
@@ -1230,6 +1240,29 @@ int64_t ls_b200_plan_redistribution(int world, int me, int64_t number_pieces, in
     places[3 * k + 2] = p.places[k].length;
   }
   return (int64_t)p.places.size();
+}
+
+// Row ranges of equal cost with at most `cap` rows per rank (what ls_b200_dist_rebalance computes from measured costs);
+// boundaries are interpolated inside a block.
+int ls_b200_plan_rebalance_bounds(int64_t number_blocks, int64_t const *edges, double const *costs, int world, int64_t cap,
+                                  int64_t *bounds) {
+  std::vector<int64_t> e(edges, edges + number_blocks + 1);
+  std::vector<double> c(costs, costs + number_blocks);
+  auto const b = dist_capped_bounds(e, c, world, cap);
+  for (int r = 0; r <= world; ++r) bounds[r] = b[(size_t)r];
+  return 0;
+}
+
+// A rank's block-cyclic share of the candidate range as the sharded build scans it: out = {block shift (blocks hold
+// 32 << shift candidates), blocks over all ranks, blocks of this rank, candidates of this rank}.
+int ls_b200_plan_cyclic_share(uint64_t total, int world, int rank, uint64_t out[4]) {
+  int const shift = dist_block_shift(total, world);
+  CyclicShare const sh = cyclic_share(total, shift, world, rank);
+  out[0] = (uint64_t)shift;
+  out[1] = sh.blocks_total;
+  out[2] = sh.number_blocks;
+  out[3] = sh.virtual_candidates;
+  return 0;
 }
 
 int ls_b200_plan_balanced_bounds(int64_t number_blocks, int64_t const *edges, double const *costs, int world,

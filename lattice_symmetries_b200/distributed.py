@@ -30,6 +30,7 @@ import numpy as np
 
 __all__ = [
     "shard_bounds", "row_bounds", "plan_blocks", "plan_redistribution", "even_bounds", "balanced_bounds",
+    "rebalance_bounds", "cyclic_share",
     "init_process", "init_communicator", "Layout", "build_distributed", "rebalance_distributed", "DistributedOperator", "EmulatedRanks",
     "hashed_vector", "hashed_values", "layout_of", "ALLGATHER", "ALLTOALL", "AUTO", "NO_GLOBAL_INDEX", "WIDE_INDEX", "NO_BALANCE",
 ]
@@ -112,6 +113,28 @@ def balanced_bounds(edges: Sequence[int], costs: Sequence[float], world: int) ->
     lib.ls_b200_plan_balanced_bounds(len(costs), edges.ctypes.data_as(i64_p), costs.ctypes.data_as(f64_p), world,
                                      out.ctypes.data_as(i64_p))
     return [int(b) for b in out]
+
+
+def rebalance_bounds(edges: Sequence[int], costs: Sequence[float], world: int, cap: int) -> List[int]:
+    """Row ranges of equal (measured) cost with at most ``cap`` rows per rank, boundaries interpolated inside a block:
+    what ``ls_b200_dist_rebalance`` computes (csrc/dist.cu ``dist_capped_bounds``)."""
+    from ._lib import lib, i64_p, f64_p
+    edges = np.ascontiguousarray(edges, dtype=np.int64)
+    costs = np.ascontiguousarray(costs, dtype=np.float64)
+    assert len(edges) == len(costs) + 1
+    out = np.zeros(world + 1, dtype=np.int64)
+    lib.ls_b200_plan_rebalance_bounds(len(costs), edges.ctypes.data_as(i64_p), costs.ctypes.data_as(f64_p), world, int(cap),
+                                      out.ctypes.data_as(i64_p))
+    return [int(b) for b in out]
+
+
+def cyclic_share(total: int, world: int, rank: int) -> Tuple[int, int, int, int]:
+    """(block shift, blocks over all ranks, blocks of ``rank``, candidates of ``rank``) of the sharded build's
+    block-cyclic scan (csrc/basis_build.cu ``cyclic_share``): block b -- 32 << shift candidates -- belongs to rank b % world."""
+    from ._lib import lib, u64_p
+    out = (C.c_uint64 * 4)()
+    lib.ls_b200_plan_cyclic_share(int(total), int(world), int(rank), out)
+    return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
 
 # ---- process set-up ------------------------------------------------------------------------------------

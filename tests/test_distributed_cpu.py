@@ -20,7 +20,8 @@ for p in (str(ROOT), str(ROOT / "tests")):
         sys.path.insert(0, p)
 
 from lattice_symmetries_b200.distributed import (  # noqa: E402
-    balanced_bounds, even_bounds, plan_blocks, plan_redistribution, row_bounds, shard_bounds)
+    balanced_bounds, cyclic_share, even_bounds, plan_blocks, plan_redistribution, rebalance_bounds, row_bounds,
+    shard_bounds)
 
 
 def _free_port() -> int:
@@ -96,6 +97,54 @@ def test_balanced_bounds(world):
     per = [cum[list(edges).index(b)] for b in bounds]
     shares = np.diff(per)
     assert np.all(np.abs(shares - costs.sum() / world) <= costs.max() + 1e-9)
+
+
+@pytest.mark.parametrize("total", [1, 31, 32, 4096, 2704156, 4537567650, 269128937220])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_cyclic_shares_partition_the_candidates(total, world):
+    """The block-cyclic scan of the sharded build (what every rank walks as one virtual range): the ranks' shares tile
+    the candidate range exactly -- also when the last block is partial or there are fewer blocks than ranks."""
+    plan = plan_blocks(total, world)
+    shares = [cyclic_share(total, world, r) for r in range(world)]
+    shift, blocks_total = shares[0][0], shares[0][1]
+    block = 32 << shift
+    assert all(s[0] == shift and s[1] == blocks_total for s in shares)
+    assert blocks_total == len(plan) == -(-total // block)
+    assert sum(s[2] for s in shares) == blocks_total
+    assert sum(s[3] for s in shares) == total
+    for r, (_, _, mine, candidates) in enumerate(shares):
+        want_blocks = plan[r::world]
+        assert mine == len(want_blocks)
+        assert candidates == sum(hi - lo for lo, hi in want_blocks)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_rebalance_bounds_equal_cost_under_a_row_cap(world):
+    """Measured cost per row rising along the sorted list (the kagome-42 profile: 2.6x from the first to the last rank):
+    without a cap every rank gets the same cost; with the cap the first ranks stop at the cap and the REST is balanced."""
+    rng = np.random.default_rng(5)
+    dim = 1_000_000
+    blocks = 64 * world
+    edges = np.concatenate([[0], np.sort(rng.choice(np.arange(1, dim), size=blocks - 1, replace=False)), [dim]])
+    density = lambda g: 1.0 + 1.6 * g / dim
+    mid = 0.5 * (edges[:-1] + edges[1:])
+    costs = density(mid) * np.diff(edges)
+    cum = lambda g: g + 0.8 * g * g / dim
+    free = rebalance_bounds(edges, costs, world, dim)
+    assert free[0] == 0 and free[-1] == dim and all(a <= b for a, b in zip(free, free[1:]))
+    shares = np.diff([cum(b) for b in free])
+    assert np.all(np.abs(shares - cum(dim) / world) <= 0.01 * cum(dim) / world)
+    cap = int(dim / world * 1.1)
+    capped = rebalance_bounds(edges, costs, world, cap)
+    rows = np.diff(capped)
+    assert capped[0] == 0 and capped[-1] == dim and rows.max() <= cap and rows[0] == cap
+    hit = int(np.sum(rows == cap))
+    assert 1 <= hit < world
+    rest = np.diff([cum(b) for b in capped[hit:]])          # the ranks below the cap share the remaining cost evenly
+    assert np.all(np.abs(rest - rest.mean()) <= 0.02 * rest.mean())
+    # a cap that cannot hold the basis at all: every rank takes the cap, the last one the remainder
+    tight = rebalance_bounds(edges, costs, world, dim // world - 1)
+    assert tight[-1] == dim and np.all(np.diff(tight)[:-1] <= dim // world - 1)
 
 
 def _simulate(world: int, lengths, owners, bounds, data):
