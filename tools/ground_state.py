@@ -34,6 +34,9 @@ def main():
                     help="after the timed products, move the row boundaries by the measured kernel times (sets LS_B200_PROFILE)")
     ap.add_argument("--energy-tol", type=float, default=None, help="stop when E0 moved by less than this (relative) over two checks")
     ap.add_argument("--check-every", type=int, default=10)
+    ap.add_argument("--checkpoint", default=None, help="path prefix: Lanczos vectors + coefficients are saved there")
+    ap.add_argument("--checkpoint-every", type=int, default=0)
+    ap.add_argument("--resume", action="store_true", help="continue from the checkpoint (same layout: do not combine with --rebalance unless the checkpoint was written after re-balancing in the same way)")
     ap.add_argument("--also-mode", default=None, choices=["allgather", "alltoall"],
                     help="time the products in a second form as well (same basis, same vector)")
     ap.add_argument("--out", default=None)
@@ -177,7 +180,8 @@ def main():
         sh.mode = mode
         t1 = time.perf_counter()
         res = lanczos_ground_state(sh, max_iters=args.max_iters, tol=args.tol, time_limit_s=args.time_limit, progress=progress,
-                                   energy_tol=args.energy_tol, check_every=args.check_every)
+                                   energy_tol=args.energy_tol, check_every=args.check_every, checkpoint=args.checkpoint,
+                                   checkpoint_every=args.checkpoint_every, resume=args.resume)
         t_l = time.perf_counter() - t1
         n = model.number_sites
         say(f"Lanczos: {res.iterations} iterations in {t_l:.2f} s ({t_l / max(res.iterations, 1) * 1e3:.1f} ms per iteration)")
