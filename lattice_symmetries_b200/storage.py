@@ -7,11 +7,13 @@ those files (one array in sorted order) and its in-memory *hashed* layout (state
 ``hash64_01(state) % numLocales``, chapel/src/StatesEnumeration.chpl:198-212) with
 chapel/src/BlockToHashed.chpl:106-189 / HashedToBlock.chpl:79-150.
 
-HDF5 is not available in this image, so the container here is the simplest thing that holds the same payload: a
-little-endian raw array behind a one-line JSON header (dtype, shape, layout, CRC-32 of the payload).  A sharded
-basis / vector is one file per rank (``name.r3of8.lsb``), each holding that rank's contiguous range of the sorted
-order -- concatenated in rank order they are the block layout, no conversion needed.  The converters below are
-only for exchanging data with a reference run that uses the hashed layout.
+Two containers.  (1) The native one, for checkpoints: a little-endian raw array behind a one-line JSON header (dtype,
+shape, layout, CRC-32 of the payload); a sharded basis / vector is one file per rank (``name.r3of8.lsb``), each holding
+that rank's contiguous range of the sorted order -- concatenated in rank order they are the block layout, no
+conversion needed.  (2) The reference's own: HDF5, through the dependency-free reader / writer in ``hdf5.py`` (there is
+no libhdf5 in this image) -- ``save_block_h5`` / ``load_block_h5`` write and read the very datasets named above, every
+rank its own rows of ONE file.  The converters below are only for exchanging data with a reference run that uses the
+hashed layout.
 """
 from __future__ import annotations
 
@@ -25,6 +27,7 @@ import numpy as np
 __all__ = [
     "MAGIC", "save_array", "load_array", "rank_path", "save_representatives", "load_representatives",
     "load_all_representatives", "save_vector", "load_vector", "hash64_01", "locale_index_of", "block_to_hashed", "hashed_to_block",
+    "save_block_h5", "load_block_h5",
 ]
 
 MAGIC = "lattice-symmetries-b200/array/1"
@@ -163,3 +166,48 @@ def hashed_to_block(parts: Sequence[np.ndarray], masks) -> np.ndarray:
             raise ValueError(f"locale {l}: {np.asarray(p).shape[-1]} elements, masks say {int(sel.sum())}")
         out[..., sel] = p
     return out
+
+
+# ---- the reference's own container: HDF5 -----------------------------------------------------------------------------
+def save_block_h5(path, dataset: str, block, row_begin: int, dim: int, rank: int = 0, world: int = 1) -> None:
+    """One rank's block (last axis = rows ``[row_begin, row_begin + n)``) of a dataset of the reference's HDF5 files
+    (``/representatives`` u64[dim], ``/x`` f64[1, dim], ``basis/representatives``, ``hamiltonian/eigenvectors``):
+    ``writeDatasetAsBlocks`` (chapel/src/MyHDF5.chpl:266-326, chapel/src/Diagonalize.chpl:227-256).  Rank 0 creates the
+    file / adds the dataset at its full size, then every rank writes its own rows -- the caller puts a barrier between
+    rank 0's call and the others' (one file on a shared file system; contiguous ranges in rank order ARE the block
+    layout).  An existing file keeps its other datasets (it is re-laid-out: HDF5 metadata precedes the data here)."""
+    from . import hdf5
+    path = Path(path)
+    a = block.detach().cpu().numpy() if hasattr(block, "detach") else np.asarray(block)
+    name = "/".join(p for p in dataset.split("/") if p)
+    if rank == 0:
+        specs, keep = {}, {}
+        if path.exists():
+            with hdf5.File(path) as f:
+                for other in f.datasets():
+                    if other.strip("/") != name:
+                        keep[other.strip("/")] = f.read(other)
+        for other, arr in keep.items():
+            specs[other] = hdf5.DatasetSpec(arr.shape, arr.dtype)
+        specs[name] = hdf5.DatasetSpec(tuple(a.shape[:-1]) + (int(dim),), a.dtype)
+        tmp = path.with_name(path.name + ".tmp")
+        hdf5.create(tmp, specs)
+        for other, arr in keep.items():
+            if arr.size:
+                hdf5.write_rows(tmp, other, arr, 0)
+        tmp.replace(path)
+    hdf5.write_rows(path, name, a, int(row_begin))
+
+
+def load_block_h5(path, dataset: str, rank: int = 0, world: int = 1, bounds: Optional[Sequence[int]] = None):
+    """(block, row_begin): rank ``rank``'s rows of the last axis of ``dataset`` -- ``readDatasetAsBlocks``
+    (chapel/src/MyHDF5.chpl:145-215).  ``bounds`` (world + 1 row numbers) selects the row ranges of a balanced layout;
+    by default the even split the reference's block distribution uses."""
+    from . import hdf5
+    with hdf5.File(path) as f:
+        dim = f.shape(dataset)[-1]
+        if bounds is None:
+            bounds = [dim * r // world for r in range(world + 1)]
+        if len(bounds) != world + 1 or bounds[0] != 0 or bounds[-1] != dim:
+            raise ValueError("bounds must run from 0 to the number of rows")
+        return f.read(dataset, rows=(int(bounds[rank]), int(bounds[rank + 1]))), int(bounds[rank])
