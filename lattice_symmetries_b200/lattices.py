@@ -34,13 +34,15 @@ class Model:
     spin_inversion: Optional[int] = None
     symmetries: Optional[Symmetries] = None
     particle: str = "spin-1/2"
-    number_particles: Optional[Tuple[int, int]] = None
+    number_particles: Optional[object] = None   # fermions: None | N | (N_up, N_down)
     bonds: List[Tuple[int, int]] = field(default_factory=list)
 
     def basis(self):
-        from .basis import SpinBasis, SpinfulFermionBasis
+        from .basis import SpinBasis, SpinfulFermionBasis, SpinlessFermionBasis
         if self.particle == "spin-1/2":
             return SpinBasis(self.number_sites, self.hamming_weight, self.spin_inversion, self.symmetries)
+        if self.particle == "spinless-fermion":
+            return SpinlessFermionBasis(self.number_sites, self.number_particles)
         return SpinfulFermionBasis(self.number_sites, self.number_particles)
 
     def operator(self, basis=None):

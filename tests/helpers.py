@@ -200,3 +200,79 @@ def random_fixed_hamming_states(rng, number_bits: int, hamming_weight: int, coun
         bits = rng.choice(number_bits, size=hamming_weight, replace=False)
         out[i] = np.bitwise_or.reduce(np.uint64(1) << bits.astype(np.uint64))
     return out
+
+
+# ---- model files and the stand-in operator of the exact-diagonalisation program -------------------------------------------
+CHAIN10_YAML = """\
+# python/example/getting_started.py:12-51 as a model file (E0 = -18.06178542, dim 13)
+basis:
+  number_spins: 10
+  hamming_weight: 5
+  spin_inversion: -1
+  symmetries:
+    - permutation: [1, 2, 3, 4, 5, 6, 7, 8, 9, 0]
+      sector: 5
+    - permutation: [9, 8, 7, 6, 5, 4, 3, 2, 1, 0]
+      sector: 1
+hamiltonian:
+  name: "Heisenberg Hamiltonian"
+  lattice: &lattice [[0, 1], [1, 2], [2, 3], [3, 4], [4, 5], [5, 6], [6, 7], [7, 8], [8, 9], [9, 0]]
+  terms:
+    - expression: "2 (σ⁺₀ σ⁻₁ + σ⁺₁ σ⁻₀)"
+      sites: *lattice
+    - expression: "σᶻ₀ σᶻ₁"
+      sites: *lattice
+observables:
+  - terms:
+      - expression: "σᶻ₀ σᶻ₁"
+        sites: [[0, 5]]
+number_vectors: 2
+output: "chain10.h5"
+"""
+
+
+def problem_of(parsed) -> Problem:
+    m = parsed.model
+    particle = {"spin-1/2": 0, "spinful-fermion": 1, "spinless-fermion": 2}[m.particle]
+    return Problem(m.name, m.number_sites, parsed.hamiltonian, particle=particle, hamming_weight=m.hamming_weight,
+                   number_particles=m.number_particles, spin_inversion=m.spin_inversion, symmetries=m.symmetries)
+
+
+class OracleOperator:
+    """The solver interface (lanczos._wrap) over the oracle's CPU matvec."""
+    device = "cpu"
+
+    def __init__(self, oracle, problem):
+        self.oracle = oracle
+        self.b, self.reps, self.index, self.off, self.diag = problem.oracle_setup(oracle)
+        dim = int(self.reps.shape[0])
+        from lattice_symmetries_b200.distributed import Layout
+        self.layout = Layout(1, 0, dim, 0, dim, 0, 0, 0, [0, dim])
+
+    def empty_vector(self, dtype=None):
+        import torch
+        return torch.zeros(self.layout.dim, dtype=dtype or torch.float64)
+
+    def matvec(self, x, y, mode=None):
+        import torch
+        out = self.oracle.matvec(self.b, self.off, self.diag, self.index, np.ascontiguousarray(x.numpy()))[0]
+        y.copy_(torch.from_numpy(np.ascontiguousarray(out)))
+
+    def dot(self, a, b):
+        import torch
+        return torch.vdot(a, b).reshape(1)
+
+    def sync(self):
+        pass
+
+    def dense(self) -> np.ndarray:
+        import torch
+        dim = self.layout.dim
+        out = torch.zeros(dim, dtype=torch.float64)
+        cols = []
+        for e in torch.eye(dim, dtype=torch.float64):
+            self.matvec(e, out)
+            cols.append(out.numpy().copy())
+        return np.stack(cols, axis=1)
+
+

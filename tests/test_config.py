@@ -1,0 +1,193 @@
+"""CPU tests of the YAML model reader (``config.py``) and of the exact-diagonalisation program (``diagonalize.py``).
+
+The reader is pinned on the reference's OWN model files, read where they lie under /root/reference (skipped when the
+tree is absent, as on the GPU box): all 32 of them parse; ``chapel/data/heisenberg_chain_24_symm.yaml`` -- BASELINE.json
+configs[0] -- yields bit for bit the term tables and the group the benchmark synthesises; the five ``test/0N_*``
+models reproduce the HPhi energies stored next to them (``HPhi/output/zvo_energy.dat``) through the oracle.  The
+program (YAML in, HDF5 out: chapel/src/Diagonalize.chpl:258-333) runs here on a stand-in operator backed by the oracle;
+on the GPU the same program runs on the library (tests/test_yaml_config.py)."""
+from __future__ import annotations
+
+import glob
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import CHAIN10_YAML, OracleOperator, problem_of
+from lattice_symmetries_b200 import hdf5
+from lattice_symmetries_b200.config import parse_config, parse_yaml_file
+from lattice_symmetries_b200.diagonalize import diagonalize
+from lattice_symmetries_b200.expr import compile_terms
+
+REFERENCE = Path("/root/reference")
+needs_reference = pytest.mark.skipif(not REFERENCE.exists(), reason="the reference tree is not present")
+
+def term_table(expr, n):
+    return sorted((t.m, t.r, t.x, t.s, t.l, complex(t.v)) for t in compile_terms(expr, n))
+
+
+# ---- the reader --------------------------------------------------------------------------------------------------------
+def test_inline_document(tmp_path):
+    import yaml
+    p = parse_config(yaml.safe_load(CHAIN10_YAML), name="chain10")
+    m = p.model
+    assert (m.number_sites, m.hamming_weight, m.spin_inversion, m.particle) == (10, 5, -1, "spin-1/2")
+    assert len(m.symmetries) == 2 and len(m.symmetries.elements) == 20 and not m.symmetries.is_empty
+    assert len(p.observables) == 1 and p.extra == {"number_vectors": 2, "output": "chain10.h5"}
+    want = H.chain10_getting_started()
+    assert term_table(p.hamiltonian, 10) == term_table(want.expr, 10)
+    path = tmp_path / "chain10.yaml"
+    path.write_text(CHAIN10_YAML, encoding="utf-8")
+    q = parse_yaml_file(path)
+    assert q.model.name == "chain10" and term_table(q.hamiltonian, 10) == term_table(want.expr, 10)
+
+
+@pytest.mark.parametrize("document,message", [
+    ({}, "basis"),
+    ({"basis": {"number_spins": 4, "spin_inversion": 2}}, "spin_inversion"),
+    ({"basis": {"number_spins": 4, "hamming_weight": 5}}, "hamming_weight"),
+    ({"basis": {"number_spins": "four"}}, "integer"),
+    ({"basis": {"particle": "boson", "number_sites": 4}}, "particle"),
+    ({"basis": {"number_spins": 4, "symmetries": [{"permutation": [1, 0, 2], "sector": 0}]}}, "length"),
+    ({"basis": {"number_spins": 4, "symmetries": [{"permutation": [1, 0, 3, 2]}]}}, "sector"),
+    ({"basis": {"number_spins": 4}, "hamiltonian": {"terms": []}}, "terms"),
+    ({"basis": {"number_spins": 4}, "hamiltonian": {"terms": [{"sites": [[0, 1]]}]}}, "expression"),
+    ({"basis": {"number_spins": 4}, "hamiltonian": {"terms": [{"expression": "σᶻ₀", "particle": "spinful-fermion"}]}},
+     "particle"),
+    ({"basis": {"particle": "spinful-fermion", "number_sites": 4, "number_particles": [1, 2, 3]}}, "number_particles"),
+    ({"basis": {"number_spins": 4}, "observables": {"terms": []}}, "observables"),
+])
+def test_schema_errors(document, message):
+    with pytest.raises(ValueError, match=message):
+        parse_config(document)
+
+
+def test_fermion_headers():
+    p = parse_config({"basis": {"particle": "spinful-fermion", "number_sites": 3, "number_particles": [2, 1]},
+                      "hamiltonian": {"terms": [{"expression": "n₀↑ n₀↓", "sites": [[0], [1], [2]]}]}})
+    assert p.model.particle == "spinful-fermion" and p.model.number_particles == (2, 1)
+    p = parse_config({"basis": {"particle": "spinful-fermion", "number_sites": 3, "number_particles": 3}})
+    assert p.model.number_particles == 3 and p.hamiltonian is None
+    p = parse_config({"basis": {"particle": "spinless-fermion", "number_sites": 5, "number_particles": 2}})
+    assert (p.model.particle, p.model.number_sites, p.model.number_particles) == ("spinless-fermion", 5, 2)
+
+
+def _reference_models():
+    files = sorted(glob.glob(str(REFERENCE / "chapel/data/*.yaml")) + glob.glob(str(REFERENCE / "test/*/hamiltonian.yaml")))
+    return [f for f in files if "basis:" in Path(f).read_text(encoding="utf-8")]
+
+
+@needs_reference
+def test_every_model_file_of_the_reference_parses():
+    files = _reference_models()
+    assert len(files) == 32
+    for f in files:
+        p = parse_yaml_file(f)
+        m = p.model
+        assert p.hamiltonian is not None and m.number_sites >= 4
+        bits = m.number_sites * (2 if m.particle == "spinful-fermion" else 1)
+        terms = compile_terms(p.hamiltonian, m.number_sites)
+        assert terms and all(0 <= t.x < (1 << bits) and (t.r & ~t.m) == 0 for t in terms), f
+        if m.symmetries is not None:
+            assert len(m.symmetries.elements) >= 2
+
+
+@needs_reference
+def test_chain24_symm_is_the_benchmark_configuration():
+    """BASELINE.json configs[0] = chapel/data/heisenberg_chain_24_symm.yaml: the synthesised model IS that file."""
+    from lattice_symmetries_b200 import lattices as L
+    p = parse_yaml_file(REFERENCE / "chapel/data/heisenberg_chain_24_symm.yaml")
+    mine = L.heisenberg_chain(24)
+    m = p.model
+    assert (m.number_sites, m.hamming_weight, m.spin_inversion) == (mine.number_sites, mine.hamming_weight, mine.spin_inversion)
+    assert term_table(p.hamiltonian, 24) == term_table(mine.expression, 24)
+    assert len(m.symmetries.elements) == len(mine.symmetries.elements) == 48
+    assert np.array_equal(m.symmetries.permutations(), mine.symmetries.permutations())
+    for a, b in zip(m.symmetries.characters(), mine.symmetries.characters()):
+        assert np.array_equal(a, b)
+
+
+@needs_reference
+@pytest.mark.parametrize("folder,restated", [
+    ("01_spin_kagome", H.hphi_01_kagome), ("02_spin_ladder_DM", H.hphi_02_ladder), ("03_spin_hcor", H.hphi_03_hcor),
+    ("04_hubbard_square", H.hphi_04_hubbard_square), ("05_hubbard_tri", H.hphi_05_hubbard_tri)])
+def test_hphi_models_and_energies(oracle, folder, restated):
+    """test/0N_*/hamiltonian.yaml read in place; the energy is the one HPhi stored next to it."""
+    p = parse_yaml_file(REFERENCE / "test" / folder / "hamiltonian.yaml")
+    want = restated()
+    n = p.model.number_sites
+    assert term_table(p.hamiltonian, n) == term_table(want.expr, n)
+    text = (REFERENCE / "test" / folder / "HPhi/output/zvo_energy.dat").read_text()
+    energy = float(text.split()[1])
+    assert abs(energy - want.energy) < 1e-12
+    e0, dim = H.oracle_ground_state_energy(oracle, problem_of(p))
+    assert abs(e0 - energy) < 1e-8, (e0, energy, dim)
+
+
+# ---- the program, on a stand-in operator backed by the oracle ----------------------------------------------------------
+def _run(oracle, yaml_path, out, **kw):
+    made = {}
+
+    def factory(parsed, cached):
+        op = OracleOperator(oracle, problem_of(parsed))
+        if cached is not None:
+            assert np.array_equal(cached, op.reps)
+        made["op"] = op
+        return op, op.reps, None
+
+    lines = []
+    res = diagonalize(yaml_path, out, operator_factory=factory, log=lines.append, **kw)
+    return res, made["op"], lines
+
+
+def test_diagonalize_chain10(oracle, tmp_path):
+    path = tmp_path / "chain10.yaml"
+    path.write_text(CHAIN10_YAML, encoding="utf-8")
+    out = tmp_path / "out" / "chain10.h5"
+    res, op, lines = _run(oracle, path, out, num_evals=3, eps=1e-10)
+    assert res.dim == 13 and res.converged and not res.reused_representatives
+    dense = op.dense()
+    exact = np.linalg.eigvalsh(dense)
+    assert abs(res.eigenvalues[0] - (-18.06178542)) < 1e-8
+    assert np.allclose(res.eigenvalues, exact[:3], atol=1e-9)
+    assert any("Hilbert space dimension: 13" in s for s in lines)
+    with hdf5.File(out) as f:
+        assert f.datasets() == ["/basis/representatives", "/hamiltonian/eigenvalues", "/hamiltonian/eigenvectors",
+                                "/hamiltonian/residuals"]
+        assert np.array_equal(f.read("basis/representatives"), op.reps)
+        assert np.array_equal(f.read("hamiltonian/eigenvalues"), res.eigenvalues)
+        assert np.array_equal(f.read("hamiltonian/residuals"), res.residuals)
+        vecs = f.read("hamiltonian/eigenvectors")
+    assert vecs.shape == (3, 13) and vecs.dtype == np.float64
+    assert np.allclose(vecs @ vecs.T, np.eye(3), atol=1e-9)
+    for e, v in zip(res.eigenvalues, vecs):
+        assert np.linalg.norm(dense @ v - e * v) < 1e-8
+    # a second run finds basis/representatives in the output file and reuses them (makeBasisStates)
+    again, _, lines = _run(oracle, path, out, num_evals=2, eps=1e-10)
+    assert again.reused_representatives and np.allclose(again.eigenvalues, exact[:2], atol=1e-9)
+    assert any("read from the output file" in s for s in lines)
+    with hdf5.File(out) as f:
+        assert f.shape("hamiltonian/eigenvectors") == (2, 13)
+    with pytest.raises(ValueError):
+        _run(oracle, path, out, num_evals=0)
+
+
+@needs_reference
+@pytest.mark.parametrize("name,k", [("heisenberg_kagome_12", 1), ("heisenberg_kagome_12_symm", 2), ("heisenberg_square_4x4", 2),
+                                    ("heisenberg_chain_10", 4)])
+def test_diagonalize_reference_models(oracle, tmp_path, name, k):
+    """The reference's own inputs (chapel/data): restarts are exercised (dim > Krylov basis), eigenpairs checked
+    against the dense matrix of the oracle's operator."""
+    out = tmp_path / f"{name}.h5"
+    res, op, _ = _run(oracle, REFERENCE / "chapel/data" / f"{name}.yaml", out, num_evals=k, eps=1e-9, max_basis_size=20)
+    assert res.converged and res.dim == op.layout.dim
+    if res.dim <= 1500:
+        dense = op.dense()
+        exact = np.linalg.eigvalsh(dense)
+        assert np.allclose(res.eigenvalues, exact[:k], atol=1e-7 * max(1.0, abs(exact[0])))
+        vecs = hdf5.read_dataset(out, "hamiltonian/eigenvectors")
+        for e, v in zip(res.eigenvalues, vecs):
+            assert np.linalg.norm(dense @ v - e * v) < 1e-6 * max(1.0, abs(e))
+    assert np.array_equal(hdf5.read_dataset(out, "basis/representatives"), op.reps)

@@ -1,0 +1,135 @@
+"""GPU tests of the callers either side of the hot path: a basis populated through ``ls_hs_unchecked_set_representatives``
+(kernels/reference.c:196-211 -- what the reference's Chapel driver does on every locale, chapel/src/Diagonalize.chpl:293),
+the YAML model reader feeding the library (python/lattice_symmetries/__init__.py:762-772) and the exact-diagonalisation
+program (YAML in, HDF5 out: chapel/src/Diagonalize.chpl:258-333) on the library's products.  Checked against the CPU
+oracle.  The model files are written by the tests themselves (/root/reference does not exist on the GPU box).
+Run with ``pytest -m gpu`` on a B200."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _yaml_of(model, extra: str = "") -> str:
+    """A Model of lattices.py as the reference's YAML (spin bases with bonds)."""
+    lines = ["basis:", f"  number_spins: {model.number_sites}"]
+    if model.hamming_weight is not None:
+        lines.append(f"  hamming_weight: {model.hamming_weight}")
+    if model.spin_inversion is not None:
+        lines.append(f"  spin_inversion: {model.spin_inversion}")
+    if model.symmetries is not None and len(model.symmetries):
+        lines.append("  symmetries:")
+        for g in model.symmetries.generators:
+            lines.append(f"    - permutation: {[int(i) for i in g.permutation]}")
+            lines.append(f"      sector: {g.sector}")
+    bonds = [[int(a), int(b)] for a, b in model.bonds]
+    lines += ["hamiltonian:", '  name: "Heisenberg Hamiltonian"', f"  lattice: &lattice {bonds}", "  terms:"]
+    for e in ("σˣ₀ σˣ₁", "σʸ₀ σʸ₁", "σᶻ₀ σᶻ₁"):
+        lines += [f'    - expression: "{e}"', "      sites: *lattice"]
+    return "\n".join(lines) + "\n" + extra
+
+
+# ---- ls_hs_unchecked_set_representatives: borrowed representatives, norms computed on first use -----------------------
+@pytest.mark.parametrize("make", [
+    lambda L: L.heisenberg_chain(24), lambda L: L.kagome_heisenberg(18), lambda L: L.kagome_heisenberg(24, spin_inversion=1),
+    lambda L: L.heisenberg_chain(20, translation_sector=3, parity_sector=None, spin_inversion=None)])
+def test_unchecked_set_representatives_then_products(oracle, make):
+    import lattice_symmetries_b200 as ls
+    from lattice_symmetries_b200 import lattices as L
+    model = make(L)
+    p = H.Problem(model.name, model.number_sites, model.expression, hamming_weight=model.hamming_weight,
+                  spin_inversion=model.spin_inversion, symmetries=model.symmetries)
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    basis = p.product_basis()
+    assert not basis.is_built
+    basis.unchecked_set_representatives(reps.copy())
+    assert basis.is_built and basis.number_states == reps.shape[0]
+    assert np.array_equal(basis.states, reps)
+    rng = np.random.default_rng(11)
+    some = reps[rng.integers(0, reps.shape[0], size=2000)]
+    assert np.array_equal(basis.index(some), np.searchsorted(reps, some))
+    assert np.all(basis.index(some ^ np.uint64(1)) == np.where(np.isin(some ^ np.uint64(1), reps),
+                                                                np.searchsorted(reps, some ^ np.uint64(1)), -1))
+    op = ls.Operator(basis, p.expr)
+    real = all((2 * g.phase).denominator == 1 for g in model.symmetries.elements)   # (the oracle's matvec is real-only)
+    if real:
+        x = rng.standard_normal(reps.shape[0])
+        y = op.apply_to_state_vector(x)
+        want, nnz = oracle.matvec(ob, off, diag, index, x)
+        assert np.linalg.norm(y - want) <= 1e-12 * np.linalg.norm(want)
+        assert op.count_matrix_elements() == nnz
+    # the same basis built on the GPU gives the same product bit for bit (the lazily computed norms are the build's)
+    built = p.product_basis()
+    built.build()
+    assert np.array_equal(built.states, reps)
+    if real:
+        assert np.array_equal(ls.Operator(built, p.expr).apply_to_state_vector(x), y)
+
+
+# ---- load_yaml_config -> library ----------------------------------------------------------------------------------------
+def test_load_yaml_config(oracle, tmp_path):
+    from lattice_symmetries_b200.config import load_yaml_config, parse_yaml_file
+    path = tmp_path / "chain10.yaml"
+    path.write_text(H.CHAIN10_YAML, encoding="utf-8")
+    config = load_yaml_config(str(path))
+    assert config.hamiltonian is not None and len(config.observables) == 1
+    config.basis.build()
+    ob, reps, index, off, diag = H.problem_of(parse_yaml_file(path)).oracle_setup(oracle)
+    assert np.array_equal(config.basis.states, reps) and reps.shape[0] == 13
+    x = np.random.default_rng(5).standard_normal(13)
+    want, _ = oracle.matvec(ob, off, diag, index, x)
+    assert np.allclose(config.hamiltonian.apply_to_state_vector(x), want, rtol=1e-12, atol=1e-13)
+    dense = np.stack([config.hamiltonian.apply_to_state_vector(e) for e in np.eye(13)], axis=1)
+    assert np.isclose(np.linalg.eigvalsh(dense)[0], -18.06178542, atol=1e-8)   # python/example/getting_started.py:51
+
+
+# ---- the program ------------------------------------------------------------------------------------------------------
+def test_diagonalize_program_chain10(oracle, tmp_path):
+    from lattice_symmetries_b200 import hdf5
+    from lattice_symmetries_b200.config import parse_yaml_file
+    from lattice_symmetries_b200.diagonalize import diagonalize
+    path = tmp_path / "chain10.yaml"
+    path.write_text(H.CHAIN10_YAML, encoding="utf-8")
+    out = tmp_path / "chain10.h5"
+    res = diagonalize(path, out, num_evals=3, eps=1e-10)
+    stand_in = H.OracleOperator(oracle, H.problem_of(parse_yaml_file(path)))
+    dense = stand_in.dense()
+    exact = np.linalg.eigvalsh(dense)
+    assert res.dim == 13 and res.converged and not res.reused_representatives
+    assert abs(res.eigenvalues[0] - (-18.06178542)) < 1e-8
+    assert np.allclose(res.eigenvalues, exact[:3], atol=1e-9)
+    assert np.array_equal(hdf5.read_dataset(out, "basis/representatives"), stand_in.reps)
+    vecs = hdf5.read_dataset(out, "hamiltonian/eigenvectors")
+    assert vecs.shape == (3, 13)
+    for e, v in zip(res.eigenvalues, vecs):
+        assert np.linalg.norm(dense @ v - e * v) < 1e-8
+    assert np.array_equal(hdf5.read_dataset(out, "hamiltonian/eigenvalues"), res.eigenvalues)
+    # second run: the representatives come from the file (ls_hs_unchecked_set_representatives on the GPU side)
+    again = diagonalize(path, out, num_evals=2, eps=1e-10)
+    assert again.reused_representatives and np.allclose(again.eigenvalues, exact[:2], atol=1e-9)
+
+
+@pytest.mark.parametrize("sites,k", [(16, 2), (20, 3)])
+def test_diagonalize_program_with_restarts(oracle, tmp_path, sites, k):
+    """dim > Krylov basis: thick restarts on the GPU, eigenpairs against the dense matrix of the oracle's operator."""
+    from lattice_symmetries_b200 import hdf5
+    from lattice_symmetries_b200 import lattices as L
+    from lattice_symmetries_b200.config import parse_yaml_file
+    from lattice_symmetries_b200.diagonalize import diagonalize
+    path = tmp_path / f"chain{sites}.yaml"
+    path.write_text(_yaml_of(L.heisenberg_chain(sites)), encoding="utf-8")
+    out = tmp_path / f"chain{sites}.h5"
+    res = diagonalize(path, out, num_evals=k, eps=1e-9, max_basis_size=20)
+    stand_in = H.OracleOperator(oracle, H.problem_of(parse_yaml_file(path)))
+    assert res.dim == stand_in.layout.dim and res.dim > 20 and res.converged
+    dense = stand_in.dense()
+    exact = np.linalg.eigvalsh(dense)
+    assert np.allclose(res.eigenvalues, exact[:k], atol=1e-7 * abs(exact[0]))
+    vecs = hdf5.read_dataset(out, "hamiltonian/eigenvectors")
+    for e, v in zip(res.eigenvalues, vecs):
+        assert np.linalg.norm(dense @ v - e * v) < 1e-6 * abs(e)
+    assert np.array_equal(hdf5.read_dataset(out, "basis/representatives"), stand_in.reps)
