@@ -250,6 +250,12 @@ std::vector<int64_t> dist_capped_bounds(std::vector<int64_t> const &edges, std::
     std::vector<int64_t> const rest = dist_balanced_bounds(e, c, P - r0 - 1, true);
     for (int r = r0 + 1; r <= P; ++r) fresh[(size_t)r] = start + rest[(size_t)(r - r0 - 1)];
   }
+  // The cap is what a rank's memory holds, so it outranks the balance: after the pass above only the LAST rank can
+  // still be over it (costs falling along the list, or all of the cost in a few rows); push its lower boundary up to
+  // the cap and let the excess ripple towards rank 0, which cap * P >= dim leaves within the cap as well.
+  if ((__int128)cap * P >= dim)
+    for (int r = P - 1; r >= 1; --r)
+      if (fresh[(size_t)r + 1] - fresh[(size_t)r] > cap) fresh[(size_t)r] = fresh[(size_t)r + 1] - cap;
   return fresh;
 }
 

@@ -147,6 +147,40 @@ def test_rebalance_bounds_equal_cost_under_a_row_cap(world):
     assert tight[-1] == dim and np.all(np.diff(tight)[:-1] <= dim // world - 1)
 
 
+def test_bounds_properties():
+    """Any blocks, any costs (empty blocks, zero costs, all of the cost in one block, costs FALLING along the list): the
+    bounds are monotone, cover [0, dim], and a feasible row cap -- it stands for what a rank's memory holds -- is honoured
+    by every rank, the last ones included."""
+    from hypothesis import given, settings, strategies as st
+
+    @st.composite
+    def blocks(draw):
+        nb = draw(st.integers(1, 40))
+        lens = draw(st.lists(st.integers(0, 1000), min_size=nb, max_size=nb))
+        costs = draw(st.lists(st.floats(0, 1e6, allow_nan=False), min_size=nb, max_size=nb))
+        return np.concatenate([[0], np.cumsum(lens)]).astype(np.int64), np.array(costs), draw(st.integers(1, 9))
+
+    @settings(max_examples=400, deadline=None, derandomize=True)
+    @given(blocks(), st.integers(1, 5000))
+    def check(b, cap):
+        edges, costs, world = b
+        dim = int(edges[-1])
+        for out in (balanced_bounds(edges, costs, world), rebalance_bounds(edges, costs, world, cap)):
+            assert len(out) == world + 1 and out[0] == 0 and out[-1] == dim
+            assert all(a <= c for a, c in zip(out, out[1:]))
+        if cap * world >= dim > 0:
+            assert np.diff(rebalance_bounds(edges, costs, world, cap)).max() <= cap
+
+    check()
+    # the case the forward pass alone missed: cost falling along the list leaves the LAST rank over the cap
+    edges = np.arange(0, 101, 10)
+    costs = np.linspace(10.0, 1.0, 10)
+    out = rebalance_bounds(edges, costs, 2, 60)
+    assert out == [0, 40, 100]
+    assert rebalance_bounds(edges, costs, 2, 100)[1] < 40     # (uncapped, rank 0 takes fewer, dearer rows)
+    assert rebalance_bounds(np.array([0, 0, 3]), np.array([1.0, 0.0]), 2, 2) == [0, 1, 3]
+
+
 def _simulate(world: int, lengths, owners, bounds, data):
     """All ranks in one process: what every rank ends up with after the planned all-to-all-v."""
     plans = [plan_redistribution(world, r, lengths, owners, bounds) for r in range(world)]
