@@ -15,8 +15,9 @@ from ._lib import lib, LIB_PATH
 from .basis import Basis, SpinBasis, SpinlessFermionBasis, SpinfulFermionBasis
 from .operator import Operator
 from . import lattices
+from .config import load_yaml_config
 
 __all__ = [
     "Symmetry", "Symmetries", "Expr", "NonbranchingTerm", "compile_terms", "Basis", "SpinBasis",
-    "SpinlessFermionBasis", "SpinfulFermionBasis", "Operator", "lattices", "lib", "LIB_PATH",
+    "SpinlessFermionBasis", "SpinfulFermionBasis", "Operator", "lattices", "lib", "LIB_PATH", "load_yaml_config",
 ]

@@ -166,6 +166,31 @@ class Basis:
             return _low_ones(h) << (bits - h)
         return _low_ones(bits)
 
+    # -- text forms (python/lattice_symmetries/__init__.py:248-254, 320-329) --------
+    def state_to_string(self, state: int) -> str:
+        """Pretty-print a basis state."""
+        from .config import state_to_string
+        return state_to_string(state, self.number_bits, self._particle_type == LS_HS_SPINFUL_FERMION)
+
+    def to_json(self) -> str:
+        import json
+        from .config import basis_header
+        particle = {LS_HS_SPIN: "spin-1/2", LS_HS_SPINFUL_FERMION: "spinful-fermion",
+                    LS_HS_SPINLESS_FERMION: "spinless-fermion"}[self._particle_type]
+        occupation = self._number_particles
+        if self._particle_type == LS_HS_SPINFUL_FERMION and self._number_up is not None:
+            occupation = (self._number_up, self._number_particles - self._number_up)
+        return json.dumps(basis_header(particle, self._number_sites, self._number_up, self._spin_inversion,
+                                       self._symmetries, occupation))
+
+    @staticmethod
+    def from_json(json_string: str) -> "Basis":
+        import json
+        from .config import parse_config
+        if not isinstance(json_string, str):
+            raise TypeError(f"expected a str, got {type(json_string).__name__}")
+        return parse_config({"basis": json.loads(json_string)}).model.basis()
+
     # -- build / queries ---------------------------------------------------------
     @property
     def is_built(self) -> bool:

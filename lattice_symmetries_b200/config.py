@@ -26,7 +26,7 @@ from .expr import Expr
 from .lattices import Model
 from .symmetry import Symmetries, Symmetry
 
-__all__ = ["Config", "ParsedConfig", "parse_config", "parse_yaml_file", "load_yaml_config"]
+__all__ = ["Config", "ParsedConfig", "parse_config", "parse_yaml_file", "load_yaml_config", "basis_header", "state_to_string"]
 
 Config = namedtuple("Config", ["basis", "hamiltonian", "observables"], defaults=[None, None])
 ParsedConfig = namedtuple("ParsedConfig", ["model", "hamiltonian", "observables", "extra"])
@@ -135,3 +135,33 @@ def load_yaml_config(filename: str) -> Config:
     hamiltonian = Operator(basis, parsed.hamiltonian) if parsed.hamiltonian is not None else None
     observables = [Operator(basis, e) for e in parsed.observables]
     return Config(basis, hamiltonian, observables)
+
+
+def basis_header(particle: str, number_sites: int, hamming_weight=None, spin_inversion=None, symmetries=None,
+                 number_particles=None) -> Dict[str, Any]:
+    """The JSON object of a basis (``basisHeaderToJSON``, Basis.hs:289-302) -- also the ``basis`` mapping of a model
+    file, so ``parse_config({"basis": basis_header(...)})`` gives the basis back."""
+    if particle == "spin-1/2":
+        return {"particle": "spin-1/2", "number_spins": int(number_sites), "hamming_weight": hamming_weight,
+                "spin_inversion": spin_inversion, "symmetries": symmetries.json_object() if symmetries is not None else []}
+    out: Dict[str, Any] = {"particle": particle, "number_sites": int(number_sites)}
+    if particle == "spinful-fermion":
+        if isinstance(number_particles, (tuple, list)):
+            out["number_particles"] = [int(number_particles[0]), int(number_particles[1])]
+        elif number_particles is not None:
+            out["number_particles"] = int(number_particles)
+    else:
+        out["number_particles"] = None if number_particles is None else int(number_particles)
+    return out
+
+
+def state_to_string(state: int, number_bits: int, spinful: bool = False) -> str:
+    """Pretty-printed basis state (Basis.hs:103-138): most significant bit first; spinful fermions as two kets, the
+    upper half of the bits (the down sites, Basis.hs:621-628) first."""
+    def bits(n: int, x: int) -> str:
+        return "".join("1" if (x >> i) & 1 else "0" for i in reversed(range(n)))
+    state = int(state)
+    if spinful:
+        half = number_bits // 2
+        return "|" + bits(half, state >> half) + "⟩|" + bits(half, state) + "⟩"
+    return "|" + bits(number_bits, state) + "⟩"

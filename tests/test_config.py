@@ -74,6 +74,30 @@ def test_fermion_headers():
     assert (p.model.particle, p.model.number_sites, p.model.number_particles) == ("spinless-fermion", 5, 2)
 
 
+def test_basis_json_and_pretty_states():
+    """``basisHeaderToJSON`` / ``basisHeaderFromJSON`` (Basis.hs:289-319) and the state pretty-printer (Basis.hs:103-138)."""
+    import json
+    from lattice_symmetries_b200 import lattices as L
+    from lattice_symmetries_b200.config import basis_header, state_to_string
+    m = L.heisenberg_chain(10)
+    text = json.dumps(basis_header("spin-1/2", 10, 5, -1, m.symmetries))
+    back = parse_config({"basis": json.loads(text)}).model
+    assert (back.number_sites, back.hamming_weight, back.spin_inversion) == (10, 5, -1)
+    assert np.array_equal(back.symmetries.permutations(), m.symmetries.permutations())
+    assert json.loads(text)["symmetries"][0] == {"permutation": [1, 2, 3, 4, 5, 6, 7, 8, 9, 0], "sector": 0}
+    plain = json.loads(json.dumps(basis_header("spin-1/2", 4)))
+    assert plain == {"particle": "spin-1/2", "number_spins": 4, "hamming_weight": None, "spin_inversion": None,
+                     "symmetries": []}
+    assert parse_config({"basis": plain}).model.symmetries is None
+    for occupation in (None, 3, (2, 1)):
+        h = json.loads(json.dumps(basis_header("spinful-fermion", 3, number_particles=occupation)))
+        assert parse_config({"basis": h}).model.number_particles == occupation
+    h = basis_header("spinless-fermion", 5, number_particles=2)
+    assert h == {"particle": "spinless-fermion", "number_sites": 5, "number_particles": 2}
+    assert state_to_string(0b0101, 4) == "|0101⟩" and state_to_string(1, 1) == "|1⟩"
+    assert state_to_string(0b100110, 6, spinful=True) == "|100⟩|110⟩"
+
+
 def _reference_models():
     files = sorted(glob.glob(str(REFERENCE / "chapel/data/*.yaml")) + glob.glob(str(REFERENCE / "test/*/hamiltonian.yaml")))
     return [f for f in files if "basis:" in Path(f).read_text(encoding="utf-8")]

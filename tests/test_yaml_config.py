@@ -87,6 +87,25 @@ def test_load_yaml_config(oracle, tmp_path):
     assert np.isclose(np.linalg.eigvalsh(dense)[0], -18.06178542, atol=1e-8)   # python/example/getting_started.py:51
 
 
+def test_basis_json_round_trip_and_pretty_states():
+    """python/lattice_symmetries/__init__.py:248-254, 320-329."""
+    import json
+    import lattice_symmetries_b200 as ls
+    from lattice_symmetries_b200 import lattices as L
+    b = L.heisenberg_chain(10).basis()
+    again = ls.Basis.from_json(b.to_json())
+    assert isinstance(again, ls.SpinBasis) and json.loads(again.to_json()) == json.loads(b.to_json())
+    b.build()
+    again.build()
+    assert np.array_equal(b.states, again.states)
+    assert b.state_to_string(int(b.states[0])) == "|" + format(int(b.states[0]), "010b") + "⟩"
+    f = ls.SpinfulFermionBasis(3, (2, 1))
+    assert json.loads(f.to_json()) == {"particle": "spinful-fermion", "number_sites": 3, "number_particles": [2, 1]}
+    assert ls.Basis.from_json(f.to_json()).to_json() == f.to_json()
+    assert f.state_to_string(0b100110) == "|100⟩|110⟩"
+    assert json.loads(ls.SpinlessFermionBasis(5, 2).to_json())["number_particles"] == 2
+
+
 # ---- the program ------------------------------------------------------------------------------------------------------
 def test_diagonalize_program_chain10(oracle, tmp_path):
     from lattice_symmetries_b200 import hdf5
