@@ -9,7 +9,8 @@ the output file with the groups ``basis``, ``hamiltonian`` (``makeFile`` / ``mak
 on the GPU(s) -- or, on one GPU, reuse ``basis/representatives`` if the output file already holds them
 (``makeBasisStates`` :227-245) -- and store them; find the ``numEvals`` lowest eigenpairs (the reference calls PRIMME,
 here the on-device thick-restart Lanczos of ``lanczos.py``; ``kEps`` is the residual tolerance relative to
-max(1, |E|), ``kMaxBasisSize`` the Krylov basis kept in HBM); write ``hamiltonian/eigenvectors`` f64[numEvals, dim],
+max(1, |E|), ``kMaxBasisSize`` the Krylov basis kept in HBM, ``kMaxBlockSize`` > 1 the block method over the library's
+block product); write ``hamiltonian/eigenvectors`` f64[numEvals, dim],
 ``hamiltonian/eigenvalues`` and ``hamiltonian/residuals`` f64[numEvals] (``saveEigenvectors`` :247-256).  With several
 ranks every rank writes its own rows of the one file (``storage.save_block_h5``); the sorted contiguous ranges in rank
 order are the reference's block layout.
@@ -73,14 +74,14 @@ def _complex_dtype():
 
 
 def diagonalize(input, output="exact_diagonalization_output.h5", num_evals: int = 1, eps: float = 1e-6,
-                max_basis_size: int = 0, max_restarts: int = 200, seed: int = 42,
+                max_basis_size: int = 0, max_restarts: int = 200, seed: int = 42, max_block_size: int = 1,
                 operator_factory: Optional[Callable] = None, barrier: Optional[Callable[[], None]] = None,
                 log: Optional[Callable[[str], None]] = None) -> DiagonalizeResult:
     """Run the program described in the module docstring; ``barrier()`` must synchronise the ranks when there are
     several (``torch.distributed.barrier``).  Returns the eigenvalues / residuals (identical on every rank)."""
     from . import hdf5, storage
     from .config import parse_yaml_file
-    from .lanczos import lanczos_thick_restart
+    from .lanczos import lanczos_block_thick_restart, lanczos_thick_restart
     say = log or (lambda s: None)
     if num_evals < 1:
         raise ValueError(f"invalid numEvals: {num_evals}")
@@ -133,8 +134,13 @@ def diagonalize(input, output="exact_diagonalization_output.h5", num_evals: int 
     t0 = time.perf_counter()
     m = int(max_basis_size) if max_basis_size else max(2 * k + 16, 24)
     m = min(max(m, k + 2), L.dim)   # room for a restart, never more vectors than the space has dimensions
-    res = lanczos_thick_restart(sh, k=k, basis_size=m, tol=eps, max_restarts=max_restarts, seed=seed,
-                                dtype=None if _is_real(parsed) else _complex_dtype())
+    dtype = None if _is_real(parsed) else _complex_dtype()
+    if max_block_size > 1:   # kMaxBlockSize: several vectors per pass over the matrix elements (block product)
+        bsz = min(int(max_block_size), L.dim)
+        res = lanczos_block_thick_restart(sh, k=k, block_size=bsz, basis_size=min(max(m, k + 2 * bsz), L.dim), tol=eps,
+                                          max_restarts=max_restarts, seed=seed, dtype=dtype)
+    else:
+        res = lanczos_thick_restart(sh, k=k, basis_size=m, tol=eps, max_restarts=max_restarts, seed=seed, dtype=dtype)
     seconds["eigensolver"] = time.perf_counter() - t0
     evals = np.asarray(res.energies, dtype=np.float64)
     resid = np.asarray(res.residuals, dtype=np.float64)
@@ -159,6 +165,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--numEvals", type=int, default=1)                                 # :168
     ap.add_argument("--kEps", type=float, default=1e-6)                                # :169
     ap.add_argument("--kMaxBasisSize", type=int, default=0)                            # :172
+    ap.add_argument("--kMaxBlockSize", type=int, default=1)                            # :175
     ap.add_argument("--maxRestarts", type=int, default=200)
     args = ap.parse_args(argv)
 
@@ -175,7 +182,7 @@ def main(argv: Optional[List[str]] = None) -> int:
         barrier, rank = dist.barrier, dist.get_rank()
     log = (lambda s: print(s, flush=True)) if rank == 0 else None
     res = diagonalize(args.input, args.kOutput, args.numEvals, args.kEps, args.kMaxBasisSize, args.maxRestarts,
-                      barrier=barrier, log=log)
+                      max_block_size=args.kMaxBlockSize, barrier=barrier, log=log)
     if rank == 0:
         print(f"{res.dim} states, {res.matvecs} products, converged: {res.converged}; "
               f"basis {res.seconds['basis']:.3f} s, eigensolver {res.seconds['eigensolver']:.3f} s -> {res.output}")

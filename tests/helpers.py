@@ -258,6 +258,11 @@ class OracleOperator:
         out = self.oracle.matvec(self.b, self.off, self.diag, self.index, np.ascontiguousarray(x.numpy()))[0]
         y.copy_(torch.from_numpy(np.ascontiguousarray(out)))
 
+    def matvec_block(self, X, Y):
+        self.block_products = getattr(self, "block_products", 0) + 1
+        for x, y in zip(X, Y):
+            self.matvec(x, y)
+
     def dot(self, a, b):
         import torch
         return torch.vdot(a, b).reshape(1)

@@ -196,6 +196,9 @@ def test_diagonalize_chain10(oracle, tmp_path):
         assert f.shape("hamiltonian/eigenvectors") == (2, 13)
     with pytest.raises(ValueError):
         _run(oracle, path, out, num_evals=0)
+    # kMaxBlockSize > 1: the block method over the block product
+    blocked, op, _ = _run(oracle, path, tmp_path / "blocked.h5", num_evals=3, eps=1e-10, max_block_size=3)
+    assert blocked.converged and np.allclose(blocked.eigenvalues, exact[:3], atol=1e-9) and op.block_products > 0
 
 
 @needs_reference
@@ -205,7 +208,8 @@ def test_diagonalize_reference_models(oracle, tmp_path, name, k):
     """The reference's own inputs (chapel/data): restarts are exercised (dim > Krylov basis), eigenpairs checked
     against the dense matrix of the oracle's operator."""
     out = tmp_path / f"{name}.h5"
-    res, op, _ = _run(oracle, REFERENCE / "chapel/data" / f"{name}.yaml", out, num_evals=k, eps=1e-9, max_basis_size=20)
+    res, op, _ = _run(oracle, REFERENCE / "chapel/data" / f"{name}.yaml", out, num_evals=k, eps=1e-9, max_basis_size=20,
+                      max_block_size=2 if name.endswith("4x4") else 1)
     assert res.converged and res.dim == op.layout.dim
     if res.dim <= 1500:
         dense = op.dense()

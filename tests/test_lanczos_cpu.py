@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from lattice_symmetries_b200.distributed import Layout
-from lattice_symmetries_b200.lanczos import lanczos_ground_state, lanczos_thick_restart
+from lattice_symmetries_b200.lanczos import lanczos_block_thick_restart, lanczos_ground_state, lanczos_thick_restart
 
 
 class DenseOperator:
@@ -33,6 +33,19 @@ class DenseOperator:
 
     def sync(self):
         pass
+
+
+class BlockDenseOperator(DenseOperator):
+    """... with the block product of the library (one pass over the matrix for all right-hand sides)."""
+
+    def __init__(self, matrix):
+        super().__init__(matrix)
+        self.block_products = 0
+
+    def matvec_block(self, X, Y):
+        assert X.dtype == torch.float64 and X.is_contiguous() and Y.is_contiguous() and X.shape == Y.shape
+        self.block_products += 1
+        Y.copy_(X @ self.H.t())
 
 
 def _matrix(dim, seed, cplx=False):
@@ -97,3 +110,68 @@ def test_thick_restart_lowest_pairs(cplx):
     for i in range(4):
         v = res.eigenvectors[i]
         assert float(torch.linalg.vector_norm(Ht.to(v.dtype) @ v - res.energies[i] * v)) < 1e-8 * abs(w[0])
+
+
+# ---- block thick-restart Lanczos -----------------------------------------------------------------------------------------
+def _check_pairs(H, res, k, atol=1e-9):
+    w = np.linalg.eigvalsh(H)
+    assert res.converged and np.allclose(res.energies, w[:k], rtol=0, atol=atol * max(1.0, abs(w[0])))
+    Ht = torch.from_numpy(H)
+    for i in range(k):
+        v = res.eigenvectors[i]
+        assert float(torch.linalg.vector_norm(Ht.to(v.dtype) @ v - res.energies[i] * v)) < 1e-7 * max(1.0, abs(w[0]))
+    G = (res.eigenvectors.conj() @ res.eigenvectors.t()).numpy()
+    assert np.allclose(G, np.eye(k), atol=1e-8)
+
+
+@pytest.mark.parametrize("block", [1, 2, 4, 8])
+def test_block_thick_restart_lowest_pairs(block):
+    H = _matrix(400, 6)
+    op = BlockDenseOperator(H)
+    res = lanczos_block_thick_restart(op, k=4, block_size=block, basis_size=48, tol=1e-11)
+    _check_pairs(H, res, 4)
+    if block > 1:   # every step is ONE block product (a shrunken block of one vector goes through the single product)
+        assert op.block_products > 0 and op.products + op.block_products < res.matvecs
+    else:
+        assert op.block_products == 0 and op.products == res.matvecs
+
+
+def test_block_size_one_is_the_single_vector_method():
+    H = _matrix(300, 7)
+    single = lanczos_thick_restart(DenseOperator(H), k=3, basis_size=30, tol=1e-11)
+    block = lanczos_block_thick_restart(DenseOperator(H), k=3, block_size=1, basis_size=30, tol=1e-11)
+    assert np.allclose(single.energies, block.energies, atol=1e-10)
+
+
+def test_block_method_resolves_a_degenerate_level():
+    """Lowest level three-fold degenerate: a single vector sees one copy per Krylov space, a block of >= 3 sees all."""
+    rng = np.random.default_rng(8)
+    q, _ = np.linalg.qr(rng.standard_normal((200, 200)))
+    levels = np.concatenate([[-5.0, -5.0, -5.0, -4.0, -3.5], np.linspace(-3, 3, 195)])
+    H = (q * levels) @ q.T
+    H = (H + H.T) / 2
+    res = lanczos_block_thick_restart(BlockDenseOperator(H), k=5, block_size=4, basis_size=40, tol=1e-11)
+    assert res.converged and np.allclose(res.energies, levels[:5], atol=1e-9)
+    _check_pairs(H, res, 5)
+
+
+def test_block_thick_restart_complex_falls_back_to_single_products():
+    H = _matrix(200, 9, cplx=True)
+    op = BlockDenseOperator(H)
+    res = lanczos_block_thick_restart(op, k=3, block_size=3, basis_size=30, tol=1e-11, dtype=torch.complex128)
+    _check_pairs(H, res, 3)
+    assert op.block_products == 0 and op.products == res.matvecs
+
+
+@pytest.mark.parametrize("dim,k,block", [(1, 1, 4), (3, 2, 4), (10, 10, 3), (24, 3, 8), (40, 5, 4)])
+def test_block_thick_restart_small_spaces(dim, k, block):
+    """The basis may fill the whole space: the residual block loses rank, the iteration stops with exact pairs."""
+    H = _matrix(dim, 10 + dim)
+    res = lanczos_block_thick_restart(BlockDenseOperator(H), k=k, block_size=block, tol=1e-12)
+    _check_pairs(H, res, min(k, dim), atol=1e-10)
+
+
+def test_block_thick_restart_with_many_restarts():
+    H = _matrix(500, 11)
+    res = lanczos_block_thick_restart(BlockDenseOperator(H), k=2, block_size=3, basis_size=14, tol=1e-10, max_restarts=2000)
+    _check_pairs(H, res, 2)

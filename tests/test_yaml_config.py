@@ -152,3 +152,35 @@ def test_diagonalize_program_with_restarts(oracle, tmp_path, sites, k):
     for e, v in zip(res.eigenvalues, vecs):
         assert np.linalg.norm(dense @ v - e * v) < 1e-6 * abs(e)
     assert np.array_equal(hdf5.read_dataset(out, "basis/representatives"), stand_in.reps)
+
+
+# ---- block eigensolver over the library's block product ------------------------------------------------------------------
+@pytest.mark.parametrize("block", [2, 4])
+def test_block_lanczos_on_the_block_product(oracle, block):
+    """k lowest pairs with ``block`` vectors per pass over the matrix elements (ls_b200_matvec_block_device) against
+    scipy's eigsh on the ORACLE's operator and against the single-vector method."""
+    import scipy.sparse.linalg as sla
+    import torch
+    import lattice_symmetries_b200 as ls
+    from lattice_symmetries_b200 import lattices as L
+    from lattice_symmetries_b200.lanczos import lanczos_block_thick_restart, lanczos_thick_restart
+    model = L.kagome_heisenberg(18)
+    p = H.Problem(model.name, model.number_sites, model.expression, hamming_weight=model.hamming_weight,
+                  spin_inversion=model.spin_inversion, symmetries=model.symmetries)
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    basis = p.product_basis()
+    basis.build()
+    op = ls.Operator(basis, p.expr)
+    dim = reps.shape[0]
+    mv = lambda v: oracle.matvec(ob, off, diag, index, np.ascontiguousarray(v, dtype=np.float64).reshape(-1))[0]
+    want = np.sort(sla.eigsh(sla.LinearOperator((dim, dim), matvec=mv, dtype=np.float64), k=4, which="SA", tol=1e-12)[0])
+    res = lanczos_block_thick_restart(op, k=4, block_size=block, basis_size=40, tol=1e-11)
+    assert res.converged
+    assert np.allclose(res.energies, want, rtol=0, atol=1e-9 * abs(want[0]))
+    for i in range(4):
+        v = res.eigenvectors[i].contiguous()
+        w = torch.zeros_like(v)
+        op.matvec_device(v.data_ptr(), w.data_ptr(), sync=True)
+        assert float(torch.linalg.vector_norm(w - res.energies[i] * v)) < 1e-8 * abs(want[0])
+    single = lanczos_thick_restart(op, k=4, basis_size=40, tol=1e-11)
+    assert np.allclose(single.energies, res.energies, rtol=0, atol=1e-9 * abs(want[0]))
