@@ -175,3 +175,103 @@ def test_block_thick_restart_with_many_restarts():
     H = _matrix(500, 11)
     res = lanczos_block_thick_restart(BlockDenseOperator(H), k=2, block_size=3, basis_size=14, tol=1e-10, max_restarts=2000)
     _check_pairs(H, res, 2)
+
+
+# ---- several ranks (gloo): the solvers on row blocks, collectives supplied by the stand-in --------------------------------
+class ShardedDenseOperator:
+    """Rank ``rank`` of ``world`` holds a contiguous block of rows of a dense symmetric matrix; the product all-gathers
+    x (the library's all-gather form), dots and Gram matrices are all-reduced -- what DistributedOperator does over NCCL."""
+    device = "cpu"
+
+    def __init__(self, matrix, rank, world, bounds=None):
+        import torch.distributed as dist
+        self.dist = dist
+        dim = matrix.shape[0]
+        bounds = bounds or [dim * r // world for r in range(world + 1)]
+        self.bounds = bounds
+        self.rows = torch.from_numpy(np.ascontiguousarray(matrix[bounds[rank]:bounds[rank + 1]]))
+        self.layout = Layout(world, rank, dim, bounds[rank], bounds[rank + 1], 0, 0, 0, list(bounds))
+        self.products = 0
+
+    def empty_vector(self, dtype=None):
+        return torch.zeros(self.layout.rows, dtype=dtype or torch.float64)
+
+    def _gather(self, x):
+        """All blocks of a vector (rows = last axis), on every rank: gloo's all_gather wants equal sizes, so every rank
+        adds its block into a zero vector of the full length."""
+        L = self.layout
+        full = torch.zeros(x.shape[:-1] + (L.dim,), dtype=x.dtype)
+        full[..., L.row_begin:L.row_end] = x
+        self.dist.all_reduce(full)
+        return full
+
+    def matvec(self, x, y, mode=None):
+        self.products += 1
+        y.copy_(self.rows.to(x.dtype) @ self._gather(x))
+
+    def matvec_block(self, X, Y):
+        for x, y in zip(X, Y):
+            self.matvec(x, y)
+
+    def dot(self, a, b):
+        return self.allreduce_(torch.vdot(a, b).reshape(1))
+
+    def allreduce_(self, t):
+        t = t.contiguous()
+        self.dist.all_reduce(t)
+        return t
+
+    def sync(self):
+        pass
+
+
+def _worker_solvers(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H = _matrix(240, 21)
+        w = np.linalg.eigvalsh(H)
+        # uneven row ranges, one of them empty when there are three ranks (a re-balanced layout may look like that)
+        bounds = [0, 100, 240] if world == 2 else [0, 100, 100, 240]
+        ok = True
+        op = ShardedDenseOperator(H, rank, world, bounds)
+        plain = lanczos_ground_state(op, max_iters=300, tol=1e-12, check_every=5, compute_eigenvector=True)
+        ok &= bool(plain.converged and abs(plain.energy - w[0]) < 1e-10 * abs(w[0]))
+        thick = lanczos_thick_restart(ShardedDenseOperator(H, rank, world, bounds), k=3, basis_size=30, tol=1e-11)
+        ok &= bool(thick.converged and np.allclose(thick.energies, w[:3], atol=1e-9 * abs(w[0])))
+        block = lanczos_block_thick_restart(ShardedDenseOperator(H, rank, world, bounds), k=3, block_size=3, basis_size=30,
+                                            tol=1e-11)
+        ok &= bool(block.converged and np.allclose(block.energies, w[:3], atol=1e-9 * abs(w[0])))
+        # the eigenvector blocks of all ranks, put together, are eigenvectors of the whole matrix
+        for res in (thick, block):
+            full = op._gather(res.eigenvectors).numpy()
+            for e, v in zip(res.energies, full):
+                ok &= bool(np.linalg.norm(H @ v - e * v) < 1e-8 * abs(w[0]))
+        # the same numbers as a single rank finds: the start vector is a function of the GLOBAL row only
+        alone = lanczos_thick_restart(DenseOperator(H), k=3, basis_size=30, tol=1e-11)
+        ok &= bool(np.allclose(alone.energies, thick.energies, atol=1e-10) and alone.matvecs == thick.matvecs)
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_solvers_on_row_blocks_under_gloo(world):
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as manager:
+        out = manager.dict()
+        procs = [ctx.Process(target=_worker_solvers, args=(r, world, port, out)) for r in range(world)]
+        for pr in procs:
+            pr.start()
+        for pr in procs:
+            pr.join(timeout=300)
+        assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+        assert dict(out) == {r: True for r in range(world)}
