@@ -50,6 +50,35 @@ CASES = {
 }
 
 
+# The same numbers in the REFERENCE's golden-file layout (chapel/test/TestStatesEnumeration.chpl:23-25: /representatives
+# u64[dim]; chapel/test/TestMatrixVectorProduct.chpl:7-11: /x, /y f64[1, dim]) next to a model file in its YAML schema.
+H5_CASES = {
+    "heisenberg_chain_16_symm": ("chain16_symm", lambda: _lattices().heisenberg_chain(16)),
+    "heisenberg_kagome_18_symm": ("kagome18_c2", lambda: _lattices().kagome_heisenberg(18)),
+}
+
+
+def write_h5_cases(out: Path) -> None:
+    from lattice_symmetries_b200 import hdf5
+    from lattice_symmetries_b200.config import parse_yaml_file
+    from lattice_symmetries_b200.expr import compile_terms
+    for stem, (npz_name, make) in H5_CASES.items():
+        model = make()
+        data = np.load(out / f"{npz_name}.npz")
+        (out / f"{stem}.yaml").write_text(H.yaml_of_model(model), encoding="utf-8")
+        back = parse_yaml_file(out / f"{stem}.yaml")
+        table = lambda e: sorted((t.m, t.r, t.x, t.s, t.l, complex(t.v)) for t in compile_terms(e, model.number_sites))
+        assert table(back.hamiltonian) == table(model.expression), stem
+        assert np.array_equal(back.model.symmetries.permutations(), model.symmetries.permutations()), stem
+        hdf5.create(out / f"{stem}.h5", {"/representatives": hdf5.DatasetSpec(data["representatives"].shape, np.uint64),
+                                         "/x": hdf5.DatasetSpec((1, data["x"].shape[0]), np.float64),
+                                         "/y": hdf5.DatasetSpec((1, data["y"].shape[0]), np.float64)}, align=8)
+        hdf5.write_rows(out / f"{stem}.h5", "/representatives", data["representatives"])
+        hdf5.write_rows(out / f"{stem}.h5", "/x", data["x"][None, :])
+        hdf5.write_rows(out / f"{stem}.h5", "/y", data["y"][None, :])
+        print(f"{stem}.h5 / .yaml: dim={data['representatives'].shape[0]}")
+
+
 def main() -> None:
     from oracle import ls_oracle as oracle
     oracle.build()
@@ -75,6 +104,7 @@ def main() -> None:
             data.update(x=x, y=y, nnz=np.int64(nnz))
         np.savez_compressed(out / f"{name}.npz", **data)
         print(f"{name}: dim={reps.shape[0]} real={real}")
+    write_h5_cases(out)
 
 
 if __name__ == "__main__":

@@ -281,3 +281,22 @@ class OracleOperator:
         return np.stack(cols, axis=1)
 
 
+
+
+def yaml_of_model(model, extra: str = "") -> str:
+    """A Model of lattices.py as the reference's YAML (spin bases with bonds)."""
+    lines = ["basis:", f"  number_spins: {model.number_sites}"]
+    if model.hamming_weight is not None:
+        lines.append(f"  hamming_weight: {model.hamming_weight}")
+    if model.spin_inversion is not None:
+        lines.append(f"  spin_inversion: {model.spin_inversion}")
+    if model.symmetries is not None and len(model.symmetries):
+        lines.append("  symmetries:")
+        for g in model.symmetries.generators:
+            lines.append(f"    - permutation: {[int(i) for i in g.permutation]}")
+            lines.append(f"      sector: {g.sector}")
+    bonds = [[int(a), int(b)] for a, b in model.bonds]
+    lines += ["hamiltonian:", '  name: "Heisenberg Hamiltonian"', f"  lattice: &lattice {bonds}", "  terms:"]
+    for e in ("σˣ₀ σˣ₁", "σʸ₀ σʸ₁", "σᶻ₀ σᶻ₁"):
+        lines += [f'    - expression: "{e}"', "      sites: *lattice"]
+    return "\n".join(lines) + "\n" + extra

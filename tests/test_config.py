@@ -219,3 +219,22 @@ def test_diagonalize_reference_models(oracle, tmp_path, name, k):
         for e, v in zip(res.eigenvalues, vecs):
             assert np.linalg.norm(dense @ v - e * v) < 1e-6 * max(1.0, abs(e))
     assert np.array_equal(hdf5.read_dataset(out, "basis/representatives"), op.reps)
+
+
+# ---- golden files in the reference's layout ------------------------------------------------------------------------------
+@pytest.mark.parametrize("stem,npz", [("heisenberg_chain_16_symm", "chain16_symm"), ("heisenberg_kagome_18_symm", "kagome18_c2")])
+def test_reference_style_golden_files_hold_the_oracle_numbers(oracle, stem, npz):
+    """tests/golden/<model>.yaml + <model>.h5 (``/representatives`` u64[dim], ``/x`` ``/y`` f64[1, dim]: the inputs of
+    chapel/test/TestStatesEnumeration.chpl and TestMatrixVectorProduct.chpl) against the oracle, freshly computed."""
+    golden = Path(__file__).parent / "golden"
+    p = problem_of(parse_yaml_file(golden / f"{stem}.yaml"))
+    b, reps, index, off, diag = p.oracle_setup(oracle)
+    with hdf5.File(golden / f"{stem}.h5") as f:
+        assert f.datasets() == ["/representatives", "/x", "/y"]
+        assert f.shape("/x") == f.shape("/y") == (1, reps.shape[0])
+        assert np.array_equal(f.read("/representatives"), reps)
+        x, y = f.read("/x")[0], f.read("/y")[0]
+    want, _ = oracle.matvec(b, off, diag, index, x)
+    assert np.linalg.norm(y - want) <= 1e-13 * np.linalg.norm(want)   # (the oracle adds atomically, like the reference: order varies)
+    data = np.load(golden / f"{npz}.npz")
+    assert np.array_equal(data["representatives"], reps) and np.array_equal(data["x"], x) and np.array_equal(data["y"], y)

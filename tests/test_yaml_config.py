@@ -14,25 +14,6 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def _yaml_of(model, extra: str = "") -> str:
-    """A Model of lattices.py as the reference's YAML (spin bases with bonds)."""
-    lines = ["basis:", f"  number_spins: {model.number_sites}"]
-    if model.hamming_weight is not None:
-        lines.append(f"  hamming_weight: {model.hamming_weight}")
-    if model.spin_inversion is not None:
-        lines.append(f"  spin_inversion: {model.spin_inversion}")
-    if model.symmetries is not None and len(model.symmetries):
-        lines.append("  symmetries:")
-        for g in model.symmetries.generators:
-            lines.append(f"    - permutation: {[int(i) for i in g.permutation]}")
-            lines.append(f"      sector: {g.sector}")
-    bonds = [[int(a), int(b)] for a, b in model.bonds]
-    lines += ["hamiltonian:", '  name: "Heisenberg Hamiltonian"', f"  lattice: &lattice {bonds}", "  terms:"]
-    for e in ("σˣ₀ σˣ₁", "σʸ₀ σʸ₁", "σᶻ₀ σᶻ₁"):
-        lines += [f'    - expression: "{e}"', "      sites: *lattice"]
-    return "\n".join(lines) + "\n" + extra
-
-
 # ---- ls_hs_unchecked_set_representatives: borrowed representatives, norms computed on first use -----------------------
 @pytest.mark.parametrize("make", [
     lambda L: L.heisenberg_chain(24), lambda L: L.kagome_heisenberg(18), lambda L: L.kagome_heisenberg(24, spin_inversion=1),
@@ -106,6 +87,27 @@ def test_basis_json_round_trip_and_pretty_states():
     assert json.loads(ls.SpinlessFermionBasis(5, 2).to_json())["number_particles"] == 2
 
 
+# ---- the reference's golden-file tests, on golden files in its layout -------------------------------------------------------
+@pytest.mark.parametrize("stem", ["heisenberg_chain_16_symm", "heisenberg_kagome_18_symm"])
+def test_reference_style_golden_files(stem):
+    """chapel/test/TestStatesEnumeration.chpl:23-27 (representatives ``==``) and TestMatrixVectorProduct.chpl:15-20, 34-52
+    (y within max(1e-13, 1e-11 max(|a|, |b|))): model from the YAML file, data from the HDF5 file (tests/golden, written
+    by tests/golden/make_golden.py from the oracle)."""
+    from pathlib import Path
+    from lattice_symmetries_b200 import hdf5
+    from lattice_symmetries_b200.config import load_yaml_config
+    golden = Path(__file__).parent / "golden"
+    config = load_yaml_config(str(golden / f"{stem}.yaml"))
+    config.basis.build()
+    reference = hdf5.read_dataset(golden / f"{stem}.h5", "/representatives")
+    assert np.array_equal(config.basis.states, reference)
+    x = np.ascontiguousarray(hdf5.read_dataset(golden / f"{stem}.h5", "/x")[0])
+    y = hdf5.read_dataset(golden / f"{stem}.h5", "/y")[0]
+    z = config.hamiltonian.apply_to_state_vector(x)
+    assert np.all(np.abs(z - y) <= np.maximum(1e-13, 1e-11 * np.maximum(np.abs(z), np.abs(y))))
+    assert np.linalg.norm(z - y) <= 1e-12 * np.linalg.norm(y)
+
+
 # ---- the program ------------------------------------------------------------------------------------------------------
 def test_diagonalize_program_chain10(oracle, tmp_path):
     from lattice_symmetries_b200 import hdf5
@@ -140,7 +142,7 @@ def test_diagonalize_program_with_restarts(oracle, tmp_path, sites, k):
     from lattice_symmetries_b200.config import parse_yaml_file
     from lattice_symmetries_b200.diagonalize import diagonalize
     path = tmp_path / f"chain{sites}.yaml"
-    path.write_text(_yaml_of(L.heisenberg_chain(sites)), encoding="utf-8")
+    path.write_text(H.yaml_of_model(L.heisenberg_chain(sites)), encoding="utf-8")
     out = tmp_path / f"chain{sites}.h5"
     res = diagonalize(path, out, num_evals=k, eps=1e-9, max_basis_size=20)
     stand_in = H.OracleOperator(oracle, H.problem_of(parse_yaml_file(path)))
