@@ -43,12 +43,13 @@ def test_unchecked_set_representatives_then_products(oracle, make):
         want, nnz = oracle.matvec(ob, off, diag, index, x)
         assert np.linalg.norm(y - want) <= 1e-12 * np.linalg.norm(want)
         assert op.count_matrix_elements() == nnz
-    # the same basis built on the GPU gives the same product bit for bit (the lazily computed norms are the build's)
+    # the same basis built on the GPU gives the same product (the lazily computed norms are the build's)
     built = p.product_basis()
     built.build()
     assert np.array_equal(built.states, reps)
     if real:
-        assert np.array_equal(ls.Operator(built, p.expr).apply_to_state_vector(x), y)
+        again = ls.Operator(built, p.expr).apply_to_state_vector(x)
+        assert np.linalg.norm(again - y) <= 1e-14 * np.linalg.norm(y)
 
 
 # ---- load_yaml_config -> library ----------------------------------------------------------------------------------------
