@@ -238,3 +238,65 @@ def test_reference_style_golden_files_hold_the_oracle_numbers(oracle, stem, npz)
     assert np.linalg.norm(y - want) <= 1e-13 * np.linalg.norm(want)   # (the oracle adds atomically, like the reference: order varies)
     data = np.load(golden / f"{npz}.npz")
     assert np.array_equal(data["representatives"], reps) and np.array_equal(data["x"], x) and np.array_equal(data["y"], y)
+
+
+# ---- the program on several ranks: one output file, every rank writes its rows ------------------------------------------
+def _worker_diagonalize(rank, world, port, folder, out):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import ls_oracle as oracle
+        from test_lanczos_cpu import ShardedDenseOperator
+        oracle.build()
+        path = Path(folder) / "model.yaml"
+        target = Path(folder) / "result.h5"
+        made = {}
+
+        def factory(parsed, cached):
+            assert cached is None                     # several ranks always build
+            whole = OracleOperator(oracle, problem_of(parsed))
+            dense = whole.dense()
+            dim = dense.shape[0]
+            bounds = [0, dim // 3, dim] if world == 2 else [0, dim // 3, dim // 3, dim]
+            made["dense"], made["reps"], made["bounds"] = dense, whole.reps, bounds
+            op = ShardedDenseOperator(dense, rank, world, bounds)
+            return op, whole.reps[bounds[rank]:bounds[rank + 1]], None
+
+        res = diagonalize(path, target, num_evals=3, eps=1e-10, max_basis_size=24, operator_factory=factory,
+                          barrier=dist.barrier)
+        ok = bool(res.converged and res.dim == made["dense"].shape[0])
+        exact = np.linalg.eigvalsh(made["dense"])
+        ok &= bool(np.allclose(res.eigenvalues, exact[:3], atol=1e-8 * abs(exact[0])))
+        # after the final barrier the one file holds every rank's rows
+        ok &= bool(np.array_equal(hdf5.read_dataset(target, "basis/representatives"), made["reps"]))
+        vecs = hdf5.read_dataset(target, "hamiltonian/eigenvectors")
+        for e, v in zip(res.eigenvalues, vecs):
+            ok &= bool(np.linalg.norm(made["dense"] @ v - e * v) < 1e-7 * abs(exact[0]))
+        ok &= bool(np.array_equal(hdf5.read_dataset(target, "hamiltonian/eigenvalues"), res.eigenvalues))
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_diagonalize_across_ranks_under_gloo(tmp_path, world):
+    import socket
+    import torch.multiprocessing as mp
+    from lattice_symmetries_b200 import lattices as L
+    (tmp_path / "model.yaml").write_text(H.yaml_of_model(L.heisenberg_chain(16)), encoding="utf-8")
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as manager:
+        out = manager.dict()
+        procs = [ctx.Process(target=_worker_diagonalize, args=(r, world, port, str(tmp_path), out)) for r in range(world)]
+        for pr in procs:
+            pr.start()
+        for pr in procs:
+            pr.join(timeout=300)
+        assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
+        assert dict(out) == {r: True for r in range(world)}
