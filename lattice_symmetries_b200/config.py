@@ -20,7 +20,7 @@ non-branching terms.  GHC is absent here, so this module reads the same files in
 from __future__ import annotations
 
 from collections import namedtuple
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Optional
 
 from .expr import Expr
 from .lattices import Model

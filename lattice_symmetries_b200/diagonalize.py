@@ -12,7 +12,7 @@ here the on-device thick-restart Lanczos of ``lanczos.py``; ``kEps`` is the resi
 max(1, |E|), ``kMaxBasisSize`` the Krylov basis kept in HBM, ``kMaxBlockSize`` > 1 the block method over the library's
 block product); write ``hamiltonian/eigenvectors`` f64[numEvals, dim],
 ``hamiltonian/eigenvalues`` and ``hamiltonian/residuals`` f64[numEvals] (``saveEigenvectors`` :247-256).  With several
-ranks every rank writes its own rows of the one file (``storage.save_block_h5``); the sorted contiguous ranges in rank
+ranks every rank writes its own rows of the one file (``hdf5.write_rows``); the sorted contiguous ranges in rank
 order are the reference's block layout.
 
 The solver and the file logic are host code over the small operator interface of ``lanczos._wrap``; the GPU enters
@@ -24,7 +24,7 @@ from __future__ import annotations
 import time
 from dataclasses import dataclass, field
 from pathlib import Path
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, List, Optional
 
 import numpy as np
 
@@ -79,7 +79,7 @@ def diagonalize(input, output="exact_diagonalization_output.h5", num_evals: int 
                 log: Optional[Callable[[str], None]] = None) -> DiagonalizeResult:
     """Run the program described in the module docstring; ``barrier()`` must synchronise the ranks when there are
     several (``torch.distributed.barrier``).  Returns the eigenvalues / residuals (identical on every rank)."""
-    from . import hdf5, storage
+    from . import hdf5
     from .config import parse_yaml_file
     from .lanczos import lanczos_block_thick_restart, lanczos_thick_restart
     say = log or (lambda s: None)

@@ -62,12 +62,14 @@ class File:
     def __init__(self, path):
         self.path = Path(path)
         self._f = open(self.path, "rb")
-        self._objects: Dict[str, int] = {}
         try:
             self._read_superblock()
         except (struct.error, IndexError) as e:
             self._f.close()
             raise Hdf5Error(f"{self.path}: truncated or corrupt superblock") from e
+        except Exception:
+            self._f.close()
+            raise
 
     def close(self):
         self._f.close()
@@ -264,10 +266,6 @@ class File:
             return True
         except KeyError:
             return False
-
-    def _is_group(self, address: int) -> bool:
-        return any(t in (0x11, 0x02, 0x06) for t, _ in self._messages(address)) and \
-            not any(t == 0x08 for t, _ in self._messages(address))
 
     def datasets(self, group: str = "/") -> List[str]:
         """Full names of all datasets below ``group`` (depth first, sorted by name)."""
