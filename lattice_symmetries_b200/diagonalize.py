@@ -28,7 +28,7 @@ from typing import Callable, List, Optional
 
 import numpy as np
 
-__all__ = ["DiagonalizeResult", "diagonalize", "main"]
+__all__ = ["DiagonalizeResult", "diagonalize", "run_options", "main"]
 
 
 @dataclass
@@ -157,17 +157,35 @@ def diagonalize(input, output="exact_diagonalization_output.h5", num_evals: int 
     return DiagonalizeResult(evals, resid, L.dim, output, res.matvecs, bool(res.converged), cached is not None, seconds)
 
 
+def run_options(input, output=None, num_evals=None, max_basis_size=None, max_block_size=None) -> dict:
+    """The options of a run: what the caller gives wins, else what the model file itself says -- the reference's model
+    files carry ``output``, ``number_vectors``, ``max_primme_basis_size``, ``max_primme_block_size``
+    (chapel/data/heisenberg_kagome_16.yaml:16-18, heisenberg_square_6x6.yaml:72-77) -- else the driver's defaults
+    (chapel/src/Diagonalize.chpl:166-177)."""
+    from .config import parse_yaml_file
+    extra = parse_yaml_file(input).extra
+
+    def pick(given, key, default):
+        return given if given is not None else extra.get(key, default)
+
+    return {"output": str(pick(output, "output", "exact_diagonalization_output.h5")),
+            "num_evals": int(pick(num_evals, "number_vectors", 1)),
+            "max_basis_size": int(pick(max_basis_size, "max_primme_basis_size", 0)),
+            "max_block_size": int(pick(max_block_size, "max_primme_block_size", 1))}
+
+
 def main(argv: Optional[List[str]] = None) -> int:
     import argparse
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("--input", default="data/heisenberg_chain_10.yaml")                # Diagonalize.chpl:166
-    ap.add_argument("--kOutput", default="exact_diagonalization_output.h5")           # :167
-    ap.add_argument("--numEvals", type=int, default=1)                                 # :168
+    ap.add_argument("--kOutput", default=None)                                         # :167
+    ap.add_argument("--numEvals", type=int, default=None)                              # :168
     ap.add_argument("--kEps", type=float, default=1e-6)                                # :169
-    ap.add_argument("--kMaxBasisSize", type=int, default=0)                            # :172
-    ap.add_argument("--kMaxBlockSize", type=int, default=1)                            # :175
+    ap.add_argument("--kMaxBasisSize", type=int, default=None)                         # :172
+    ap.add_argument("--kMaxBlockSize", type=int, default=None)                         # :175
     ap.add_argument("--maxRestarts", type=int, default=200)
     args = ap.parse_args(argv)
+    options = run_options(args.input, args.kOutput, args.numEvals, args.kMaxBasisSize, args.kMaxBlockSize)
 
     import os
     barrier = None
@@ -181,8 +199,8 @@ def main(argv: Optional[List[str]] = None) -> int:
         init_communicator()
         barrier, rank = dist.barrier, dist.get_rank()
     log = (lambda s: print(s, flush=True)) if rank == 0 else None
-    res = diagonalize(args.input, args.kOutput, args.numEvals, args.kEps, args.kMaxBasisSize, args.maxRestarts,
-                      max_block_size=args.kMaxBlockSize, barrier=barrier, log=log)
+    res = diagonalize(args.input, options["output"], options["num_evals"], args.kEps, options["max_basis_size"],
+                      args.maxRestarts, max_block_size=options["max_block_size"], barrier=barrier, log=log)
     if rank == 0:
         print(f"{res.dim} states, {res.matvecs} products, converged: {res.converged}; "
               f"basis {res.seconds['basis']:.3f} s, eigensolver {res.seconds['eigensolver']:.3f} s -> {res.output}")

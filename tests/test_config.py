@@ -151,6 +151,18 @@ def test_hphi_models_and_energies(oracle, folder, restated):
 
 
 # ---- the program, on a stand-in operator backed by the oracle ----------------------------------------------------------
+def test_run_options_come_from_the_model_file(tmp_path):
+    from lattice_symmetries_b200.diagonalize import run_options
+    path = tmp_path / "chain10.yaml"
+    path.write_text(CHAIN10_YAML, encoding="utf-8")
+    assert run_options(path) == {"output": "chain10.h5", "num_evals": 2, "max_basis_size": 0, "max_block_size": 1}
+    assert run_options(path, output="x.h5", num_evals=5, max_basis_size=30, max_block_size=4) == \
+        {"output": "x.h5", "num_evals": 5, "max_basis_size": 30, "max_block_size": 4}
+    if REFERENCE.exists():
+        got = run_options(REFERENCE / "chapel/data/heisenberg_square_6x6.yaml")
+        assert got == {"output": "data/heisenberg_square_6x6.h5", "num_evals": 2, "max_basis_size": 20, "max_block_size": 4}
+
+
 def _run(oracle, yaml_path, out, **kw):
     made = {}
 
