@@ -160,7 +160,8 @@ def oracle_problem(model):
     return oracle, ob, off, diag
 
 
-def cpu_matvec_sample(model, reps, seconds_per_pass: float, passes: int = 1, warmup: int = 0, prefix: bool = False):
+def cpu_matvec_sample(model, reps, seconds_per_pass: float, passes: int = 1, warmup: int = 0, prefix: bool = False,
+                      uniform: bool = False):
     """Times the reference's CPU path for one y = H x (push form: apply_off_diag -> state_info on betas and alphas ->
     state_index -> atomic add; OpenMP over all host cores) on a bounded sample of the columns.
 
@@ -169,7 +170,9 @@ def cpu_matvec_sample(model, reps, seconds_per_pass: float, passes: int = 1, war
     Halide-generated and cannot be built here).  ``prefix`` = False: ``reps`` is the whole basis and the sample is
     UNIFORM (one block of 64 columns every ``stride`` columns); True: ``reps`` is only a sorted prefix of the basis
     (the stand-alone CPU arm cannot enumerate 9e9 candidates), all its columns are processed, and matrix elements
-    that leave the prefix are searched for and dropped.  Returns (elements/s, description, cores, s per pass)."""
+    that leave the prefix are searched for and dropped; with ``uniform`` as well, ``reps`` is a uniform thinning of the
+    basis (cpu_build_sample with ``spread``) and its columns are sampled by stride like a whole basis.
+    Returns (elements/s, description, cores, s per pass)."""
     oracle, ob, off, diag = oracle_problem(model)
     cores = oracle.num_threads()
     use_ref = oracle.ref_available()
@@ -186,7 +189,7 @@ def cpu_matvec_sample(model, reps, seconds_per_pass: float, passes: int = 1, war
 
     # calibrate on ~1024 columns per core, then size the sample for `seconds_per_pass`
     probe_cols = min(dim, 1024 * cores)
-    if prefix:
+    if prefix and not uniform:
         dt, _ = run(64, probe_cols)
         rows, stride = int(min(dim, max(probe_cols, probe_cols * seconds_per_pass / max(dt, 1e-4)))), 64
     else:
@@ -202,17 +205,28 @@ def cpu_matvec_sample(model, reps, seconds_per_pass: float, passes: int = 1, war
     dt = sum(times) / len(times)
     columns = rows if stride == 64 else ((rows + stride - 1) // stride) * 64
     elements = nnz + columns  # off-diagonal elements + the diagonal
-    where = ("columns [0,%d) of a CPU-built sorted prefix of the basis" % rows) if prefix else (
-        "%d columns sampled uniformly (64 every %d) from the basis (dim %d)" % (columns, stride, dim))
+    if prefix and uniform:
+        where = ("%d columns (64 every %d) of a CPU-built uniform thinning of the basis (%d representatives from blocks "
+                 "spaced evenly over the candidate range)" % (columns, stride, dim))
+    elif prefix:
+        where = "columns [0,%d) of a CPU-built sorted prefix of the basis" % rows
+    else:
+        where = "%d columns sampled uniformly (64 every %d) from the basis (dim %d)" % (columns, stride, dim)
     kernels = ("apply_off_diag + state_index = the reference's compiled kernels/reference.c + indexing.c, state_info = C port"
                if use_ref else "all kernels = C port (oracle/_ref/libref.so absent)")
     return (elements / dt, f"{where}: {nnz} off-diagonal elements per pass, {dt:.2f} s per pass, {len(times)} timed "
             f"pass(es); {kernels}", cores, dt)
 
 
-def cpu_build_sample(model, seconds_target: float = 8.0, want_reps: int = 0):
+def cpu_build_sample(model, seconds_target: float = 8.0, want_reps: int = 0, spread: int = 1):
     """Times the oracle's enumeration (Gosper stepping + is_representative, OpenMP over chunks like
-    StatesEnumeration.chpl:392-458) on the first n candidates; returns (stats, representatives found)."""
+    StatesEnumeration.chpl:392-458) on n candidates; returns (stats, representatives found, sorted).
+
+    ``spread`` = 1: the first n candidates (a sorted PREFIX of the basis -- what the in-line baseline compares with
+    the head of the GPU-built basis).  ``spread`` > 1: n candidates in that many equal blocks spaced evenly over the
+    whole candidate range, i.e. a uniform thinning of the basis: representatives crowd into the low indices (the
+    first 3 % of kagome-36's range hold 90 % of them) and cost differently to find there, so a prefix alone says
+    little about the whole scan -- or about the columns of the whole matrix."""
     oracle, ob, _, _ = oracle_problem(model)
     if model.particle != "spin-1/2" or model.hamming_weight is None:
         reps = ob.enumerate()
@@ -224,16 +238,22 @@ def cpu_build_sample(model, seconds_target: float = 8.0, want_reps: int = 0):
     total = r_hi - r_lo + 1
     n = min(total, 1 << 21)
     hw = model.hamming_weight
+    state_at = lambda k: int(lib.oracle_fixed_hamming_index_to_state(r_lo + k, hw))
     while True:
-        upper = int(lib.oracle_fixed_hamming_index_to_state(r_lo + n - 1, hw))
+        blocks = max(1, min(spread, n >> 16)) if n < total else 1
+        size = n // blocks
+        starts = [0] if blocks == 1 else [(total - size) * k // (blocks - 1) for k in range(blocks)]
         t0 = time.perf_counter()
-        reps = ob.enumerate_range(lo, upper)
+        parts = [ob.enumerate_range(state_at(a), state_at(a + size - 1)) for a in starts]
         dt = time.perf_counter() - t0
+        reps = np.concatenate(parts) if len(parts) > 1 else parts[0]
+        scanned = blocks * size
         if n == total or (dt > seconds_target / 3 and reps.shape[0] >= want_reps):
             break
         n = int(min(total, max(2 * n, n * seconds_target / 1.5 / max(dt, 1e-3))))
-    stats = {"candidates_per_s": n / dt, "representatives_per_s": reps.shape[0] / dt, "cores": oracle.num_threads(),
-             "sample": f"first {n} of {total} candidates, {dt:.2f} s"}
+    where = f"first {scanned}" if blocks == 1 else f"{blocks} blocks of {size} spaced evenly over the range, {scanned}"
+    stats = {"candidates_per_s": scanned / dt, "representatives_per_s": reps.shape[0] / dt, "cores": oracle.num_threads(),
+             "sample": f"{where} of {total} candidates, {dt:.2f} s"}
     return stats, reps
 
 
@@ -346,17 +366,19 @@ def run_reference(args):
     """CPU arm: the reference's path for this metric on the host cores.  The reference's orbit kernels are
     Halide-generated and its driver is Chapel -- neither toolchain exists here -- so the loop and state_info are the
     oracle port (oracle/ls_oracle.c, a line-by-line restatement), with the reference's own compiled apply_off_diag
-    and state_index (oracle/_ref/libref.so) inside it.  Self-contained on the CPU: it builds a prefix of the basis
-    itself, then times matvec passes over those columns.  Under torchrun rank 0 alone runs, on ALL host cores."""
+    and state_index (oracle/_ref/libref.so) inside it.  Self-contained on the CPU: it scans blocks of candidates spaced
+    evenly over the whole range (a uniform thinning of the basis -- a prefix would hold only the cheap low-index
+    columns), then times matvec passes over columns sampled evenly from those.  Under torchrun rank 0 alone runs, on
+    ALL host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     model, desc = make_model(args.workload)
     passes = max(1, args.steps)
     warm = max(0, min(args.warmup, 1))
-    build_stats, reps = cpu_build_sample(model, 10.0, want_reps=20000)
+    build_stats, reps = cpu_build_sample(model, 10.0, want_reps=20000, spread=16)
     per_pass = min(10.0, 60.0 / (passes + warm))
-    value, sample, cores, dt = cpu_matvec_sample(model, reps, per_pass, passes, warm, prefix=True)
+    value, sample, cores, dt = cpu_matvec_sample(model, reps, per_pass, passes, warm, prefix=True, uniform=True)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
