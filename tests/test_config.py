@@ -312,3 +312,53 @@ def test_diagonalize_across_ranks_under_gloo(tmp_path, world):
             pr.join(timeout=300)
         assert all(pr.exitcode == 0 for pr in procs), [pr.exitcode for pr in procs]
         assert dict(out) == {r: True for r in range(world)}
+
+
+# ---- the reference's test programs (chapel/test, chapel/benchmark) on a stand-in backend --------------------------------
+def _oracle_backend(oracle):
+    import torch
+
+    def backend(parsed):
+        op = OracleOperator(oracle, problem_of(parsed))
+
+        def matvec(x):
+            y = torch.zeros(op.layout.dim, dtype=torch.float64)
+            op.matvec(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)), y)
+            return y.numpy()
+
+        count = lambda: oracle.matvec(op.b, op.off, op.diag, op.index, np.zeros(op.layout.dim))[1]
+        return op.reps, matvec, count, 0.0, op
+    return backend
+
+
+def test_reference_test_programs(oracle, tmp_path):
+    from lattice_symmetries_b200 import reference_tests as R
+    golden = Path(__file__).parent / "golden"
+    model, data = golden / "heisenberg_chain_16_symm.yaml", golden / "heisenberg_chain_16_symm.h5"
+    backend = _oracle_backend(oracle)
+    lines = []
+    out = R.check_states(model, data, backend=backend, log=lines.append)
+    assert out.ok and out.details["dim"] == 257 and len(lines) == 1 and float(lines[0]) >= 0
+    lines = []
+    out = R.check_matvec(model, data, backend=backend, log=lines.append)
+    assert out.ok and lines[0] == "true" and out.details["max_abs_err"] < 1e-13
+    lines = []
+    out = R.benchmark(model, backend=backend, log=lines.append, repeats=1)
+    assert lines[0] == "Hilbert space dimension: 257" and out.details["matrix_elements"] > 257
+    # a golden file that disagrees: one representative and one entry of y changed
+    reps = hdf5.read_dataset(data, "/representatives").copy()
+    y = hdf5.read_dataset(data, "/y").copy()
+    reps[5] += 1
+    y[0, 7] += 1e-9
+    bad = tmp_path / "bad.h5"
+    hdf5.write_file(bad, {"/representatives": reps, "/x": hdf5.read_dataset(data, "/x"), "/y": y})
+    lines = []
+    out = R.check_states(model, bad, backend=backend, log=lines.append)
+    assert not out.ok and lines[0].startswith("at index 5: ")
+    lines = []
+    out = R.check_matvec(model, bad, backend=backend, log=lines.append)
+    assert not out.ok and lines[0] == "false" and lines[1].startswith("at 7: ")
+    assert np.array_equal(R.approx_equal([1.0, 1.0, 0.0], [1.0 + 5e-12, 1.0 + 2e-11, 5e-14]), [True, False, True])
+    short = tmp_path / "short.h5"
+    hdf5.write_file(short, {"/representatives": reps[:100]})
+    assert not R.check_states(model, short, backend=backend, log=lines.append).ok

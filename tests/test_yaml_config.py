@@ -92,21 +92,20 @@ def test_basis_json_round_trip_and_pretty_states():
 @pytest.mark.parametrize("stem", ["heisenberg_chain_16_symm", "heisenberg_kagome_18_symm"])
 def test_reference_style_golden_files(stem):
     """chapel/test/TestStatesEnumeration.chpl:23-27 (representatives ``==``) and TestMatrixVectorProduct.chpl:15-20, 34-52
-    (y within max(1e-13, 1e-11 max(|a|, |b|))): model from the YAML file, data from the HDF5 file (tests/golden, written
-    by tests/golden/make_golden.py from the oracle)."""
+    (y within max(1e-13, 1e-11 max(|a|, |b|))) as ``reference_tests.check_states`` / ``check_matvec``: model from the YAML
+    file, data from the HDF5 file (tests/golden, written by tests/golden/make_golden.py from the oracle)."""
     from pathlib import Path
     from lattice_symmetries_b200 import hdf5
-    from lattice_symmetries_b200.config import load_yaml_config
+    from lattice_symmetries_b200 import reference_tests as R
     golden = Path(__file__).parent / "golden"
-    config = load_yaml_config(str(golden / f"{stem}.yaml"))
-    config.basis.build()
-    reference = hdf5.read_dataset(golden / f"{stem}.h5", "/representatives")
-    assert np.array_equal(config.basis.states, reference)
-    x = np.ascontiguousarray(hdf5.read_dataset(golden / f"{stem}.h5", "/x")[0])
-    y = hdf5.read_dataset(golden / f"{stem}.h5", "/y")[0]
-    z = config.hamiltonian.apply_to_state_vector(x)
-    assert np.all(np.abs(z - y) <= np.maximum(1e-13, 1e-11 * np.maximum(np.abs(z), np.abs(y))))
-    assert np.linalg.norm(z - y) <= 1e-12 * np.linalg.norm(y)
+    model, data = golden / f"{stem}.yaml", golden / f"{stem}.h5"
+    lines = []
+    out = R.check_states(model, data, log=lines.append)
+    assert out.ok and out.details["dim"] == hdf5.File(data).shape("/representatives")[0], lines
+    out = R.check_matvec(model, data, log=lines.append)
+    assert out.ok and out.details["max_abs_err"] < 1e-12, lines
+    out = R.benchmark(model, log=lines.append, repeats=1)
+    assert out.details["matrix_elements_per_s"] > 0 and out.details["dim"] == hdf5.File(data).shape("/representatives")[0]
 
 
 # ---- the program ------------------------------------------------------------------------------------------------------
