@@ -52,6 +52,30 @@ def test_unchecked_set_representatives_then_products(oracle, make):
         assert np.linalg.norm(again - y) <= 1e-14 * np.linalg.norm(y)
 
 
+# ---- the reference's headline example, as it is written there ----------------------------------------------------------
+def test_getting_started_example(oracle):
+    """python/example/getting_started.py: NO Hamming weight on the basis (every magnetisation sector the symmetries allow:
+    34 states, enumerated by plain index under the projection), ``eigsh`` on the operator, E0 = -18.06178542."""
+    import importlib.util
+    from pathlib import Path
+    import lattice_symmetries_b200 as ls
+    path = Path(__file__).resolve().parent.parent / "examples" / "getting_started.py"
+    spec = importlib.util.spec_from_file_location("getting_started_example", path)
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    assert abs(module.main(verbose=False) - (-18.06178542)) < 1e-7
+    # the same basis against the oracle, state by state
+    p = H.chain10_getting_started()
+    p.hamming_weight = None
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    basis = ls.SpinBasis(10, None, -1, p.symmetries)
+    basis.build()
+    assert reps.shape[0] == 34 and np.array_equal(basis.states, reps)
+    x = np.random.default_rng(3).standard_normal(34)
+    want, _ = oracle.matvec(ob, off, diag, index, x)
+    assert np.allclose(ls.Operator(basis, p.expr).apply_to_state_vector(x), want, rtol=1e-12, atol=1e-13)
+
+
 # ---- load_yaml_config -> library ----------------------------------------------------------------------------------------
 def test_load_yaml_config(oracle, tmp_path):
     from lattice_symmetries_b200.config import load_yaml_config, parse_yaml_file
