@@ -76,6 +76,32 @@ def test_getting_started_example(oracle):
     assert np.allclose(ls.Operator(basis, p.expr).apply_to_state_vector(x), want, rtol=1e-12, atol=1e-13)
 
 
+@pytest.mark.parametrize("sites,inversion,translation,parity", [(16, 1, 0, 0), (14, -1, 7, 1), (18, None, 2, None)])
+def test_projected_basis_without_a_hamming_weight(oracle, sites, inversion, translation, parity):
+    """The combination of the reference's example at sizes where the scan spans many 32-candidate words: all 2^n states
+    are candidates (plain index, no combinadics), the group projection keeps the representatives of every magnetisation."""
+    import lattice_symmetries_b200 as ls
+    from lattice_symmetries_b200 import lattices as L
+    model = L.heisenberg_chain(sites)
+    syms = L.chain_symmetries(sites, translation, parity)
+    p = H.Problem(f"chain{sites}_nohw", sites, model.expression, hamming_weight=None, spin_inversion=inversion,
+                  symmetries=syms)
+    ob, reps, index, off, diag = p.oracle_setup(oracle)
+    basis = p.product_basis()
+    basis.build()
+    assert np.array_equal(basis.states, reps)
+    betas, chars, norms = basis.state_info(reps)
+    want_norms = ob.group.state_info(reps)[2]
+    assert np.array_equal(betas, reps) and np.array_equal(norms.view(np.uint64), want_norms.view(np.uint64))
+    assert np.array_equal(basis.index(reps), np.arange(reps.shape[0]))
+    if all((2 * g.phase).denominator == 1 for g in syms.elements):
+        x = np.random.default_rng(sites).standard_normal(reps.shape[0])
+        want, nnz = oracle.matvec(ob, off, diag, index, x)
+        op = ls.Operator(basis, p.expr)
+        y = op.apply_to_state_vector(x)
+        assert np.linalg.norm(y - want) <= 1e-12 * np.linalg.norm(want) and op.count_matrix_elements() == nnz
+
+
 # ---- load_yaml_config -> library ----------------------------------------------------------------------------------------
 def test_load_yaml_config(oracle, tmp_path):
     from lattice_symmetries_b200.config import load_yaml_config, parse_yaml_file
